@@ -1,0 +1,168 @@
+/*
+ * pmg.h -- C ABI of the B200-native geometric multigrid solver for the 2-D Poisson problem.
+ *
+ * This is the drop-in boundary for the reference's multigrid hot path.  The reference
+ * (FraVirgu/Parallel-Geometric-Multigrid-for-Poisson-problem) has no FFI layer: its boundary is the
+ * C++ class surface
+ *     Smoother::smooth                                   Smoother.hpp:23-28
+ *     MultigridSolver::{v_cycle,w_cycle,f_cycle}         2_part_MG/MultiGrid.hpp:57,96,138
+ *     Parallel::{ComputeJacobi,ComputeResidual,ComputeRestriction,ComputeProlungator}
+ *                                                        3_part_parallel/Parallel_Method.cu:144-199
+ *     ParallelMultiGridSolver::{v_cycle,w_cycle}         3_part_parallel/Parallel_Mg.cu:21,62
+ * include/pmg.hpp re-creates those class shapes on top of the functions below, so a reference
+ * runner is re-pointed at this library by changing an #include.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, `pmg_status` return codes (the reference has no error
+ *     reporting at all; here every CUDA/NCCL failure is surfaced, nothing falls back to the CPU).
+ *   - Field layout at the ABI = the reference's: row-major N x N doubles INCLUDING the Dirichlet
+ *     ring, idx = y*width + x (Smoother.hpp:65), N = 2^k + 1, h = 1/(N-1).  Internally the solver
+ *     re-lays fields out on a padded, 128-byte-pitched hierarchy in HBM.
+ *   - Sweep counts are TRUE sweep counts.  The reference's `num_iter` means num_iter+1 sweeps
+ *     (Smoother.hpp:59); the C++ shims in pmg.hpp do the +1.
+ *   - fp64 throughout.  The stencil arithmetic reproduces the reference's expression order without
+ *     FMA contraction, so operator outputs are bit-identical to the CPU path; only the residual
+ *     NORM (a parallel tree sum instead of a left-to-right sum) differs, by ~1e-15 relative.
+ *   - One solver handle is used by one host thread at a time; different handles are independent.
+ */
+#ifndef PMG_H
+#define PMG_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMG_VERSION_MAJOR 0
+#define PMG_VERSION_MINOR 1
+
+typedef enum pmg_status {
+    PMG_OK = 0,
+    PMG_ERR_INVALID = 1,     /* bad argument (size not 2^k+1, null pointer, bad enum ...)          */
+    PMG_ERR_CUDA = 2,        /* a CUDA runtime call or kernel failed; see pmg_last_error()         */
+    PMG_ERR_NO_DEVICE = 3,   /* no sm_100 device visible: there is NO CPU fallback                 */
+    PMG_ERR_ALLOC = 4,       /* device or pinned-host allocation failed                            */
+    PMG_ERR_COMM = 5,        /* NCCL / peer-access failure in the multi-GPU path                   */
+    PMG_ERR_UNSUPPORTED = 6  /* valid request this build cannot serve (documented at the function) */
+} pmg_status;
+
+/* MultigridSolver::v_cycle / w_cycle / f_cycle (MultiGrid.hpp:57 / :96 / :138) */
+typedef enum pmg_cycle_kind { PMG_CYCLE_V = 0, PMG_CYCLE_W = 1, PMG_CYCLE_F = 2 } pmg_cycle_kind;
+
+/* PMG_PROLONG_REFERENCE reproduces MultigridSolver::prolongation (MultiGrid.hpp:208-226): fine row 1
+ * and fine column 1 receive no correction.  PMG_PROLONG_FULL corrects every interior fine point
+ * (what the reference's GPU kernel does, Parallel_Method.cu:79-138) -- not parity with the CPU path,
+ * 3x fewer cycles. */
+typedef enum pmg_prolong_mode { PMG_PROLONG_REFERENCE = 0, PMG_PROLONG_FULL = 1 } pmg_prolong_mode;
+
+typedef enum pmg_mem { PMG_MEM_HOST = 0, PMG_MEM_DEVICE = 1 } pmg_mem;
+
+typedef enum pmg_engine {
+    PMG_ENGINE_FUSED = 0,   /* temporally blocked streaming kernels (2 HBM passes per level visit)  */
+    PMG_ENGINE_OPERATOR = 1 /* one kernel per reference operator (Parallel::Compute* granularity)  */
+} pmg_engine;
+
+typedef struct pmg_config {
+    int n;               /* grid points per side, 2^k + 1, k >= 1                                   */
+    int nu1, nu2;        /* pre / post smoothing sweeps (reference v1+1 / v2+1 = 2 / 2)             */
+    double omega;        /* Jacobi weight; 1.0 = the reference's undamped smoother bit for bit      */
+    int gamma;           /* W-cycle recursion count (reference `alpha`, MultiGrid.hpp:13,124)       */
+    int n_coarse;        /* coarsest level size (MultiGrid.hpp:19: 5)                               */
+    int coarse_sweeps;   /* sweeps on the coarsest level (MultiGrid.hpp:61: 10+1)                   */
+    int fmg_sweeps;      /* sweeps per level on the way up in the F-cycle (MultiGrid.hpp:153: 3+1)  */
+    int prolong_mode;    /* pmg_prolong_mode                                                        */
+    int engine;          /* pmg_engine                                                              */
+    double smoother_eps; /* Smoother::epsilon (Smoother.hpp:11,84): absolute ||r|| early exit tested */
+                         /* after every sweep.  0 disables it (parity runs).  > 0 forces  */
+                         /* the OPERATOR engine with a host readback per sweep.                      */
+    int device;          /* CUDA ordinal, -1 = current device                                       */
+    int use_graph;       /* 1: replay each cycle as a CUDA graph                                    */
+    /* ---- multi-GPU (row-slab decomposition, one process per GPU); leave zeroed for 1 GPU ---- */
+    int rank, n_ranks;
+    int agglomerate_below; /* levels with n <= this run on rank 0 only                              */
+    int reserved[8];
+} pmg_config;
+
+typedef struct pmg_solver pmg_solver; /* opaque */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char *pmg_version(void);
+/* message of the most recent failure on the calling thread ("" if none) */
+const char *pmg_last_error(void);
+const char *pmg_status_string(pmg_status s);
+/* reference defaults: V(2,2), omega = 2/3 is NOT the reference default -- it has no omega; the
+ * struct is filled with nu1=nu2=2, omega=1, gamma=3, n_coarse=5, coarse_sweeps=11, fmg_sweeps=4,
+ * REFERENCE prolongation, FUSED engine, smoother_eps=0. */
+void pmg_config_default(pmg_config *cfg, int n);
+/* number of this library's kernels launched by the calling process so far (bench gpu_launches) */
+unsigned long long pmg_kernel_launches(void);
+
+/* ---- solver handle (replaces MultigridSolver / ParallelMultiGridSolver objects) ---------------- */
+pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out);
+void pmg_destroy(pmg_solver *s);
+/* f / phi: n*n doubles in the reference layout, in host or device memory */
+pmg_status pmg_set_rhs(pmg_solver *s, const double *f, pmg_mem where);
+pmg_status pmg_set_guess(pmg_solver *s, const double *phi, pmg_mem where);
+pmg_status pmg_get_solution(pmg_solver *s, double *phi, pmg_mem where);
+/* phi = 0 (DynamicGridUtils::initialize_zeros, DynamicGridUtils.hpp:14-18) */
+pmg_status pmg_zero_guess(pmg_solver *s);
+/* f = 2 pi^2 sin(pi x) sin(pi y) generated on the device (DynamicGridUtils::compute_rhs, :111-124,
+ * globals a=p=q=1); bit-identical to the host function */
+pmg_status pmg_set_rhs_sine(pmg_solver *s);
+/* ||f - A phi||_2, un-scaled, as MultiGridTestRunner.hpp:210-211 */
+pmg_status pmg_residual_norm(pmg_solver *s, double *norm_out);
+/* one cycle in place (MultiGridTestRunner.hpp:190-209; F = the runner's wrapper :192-205);
+ * res_norm_out (nullable) receives ||f - A phi|| after the cycle */
+pmg_status pmg_cycle(pmg_solver *s, pmg_cycle_kind kind, double *res_norm_out);
+/* cycles until ||r|| < rel_tol*||r0|| or max_cycles; res_history (nullable, max_cycles+1 doubles):
+ * [0] = ||r0||, [k] = after cycle k; n_cycles_out (nullable) = cycles done.  The "residual-history
+ * output" the reference computes and discards (MultiGridTestRunner.hpp:210-212). */
+pmg_status pmg_solve(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max_cycles,
+                     double *res_history, int *n_cycles_out);
+/* device time of the last pmg_solve / pmg_cycle in milliseconds (CUDA events on the solver stream) */
+pmg_status pmg_last_device_ms(pmg_solver *s, double *ms_out);
+/* the CUDA stream (cudaStream_t) the solver launches on, for callers that time with their own events */
+void *pmg_stream(pmg_solver *s);
+
+/* ---- operator level (replaces class Parallel, Parallel_Method.cu:144-199, and the DynamicGridUtils
+ *      helpers); DEVICE pointers, dense reference layout (pitch = width), synchronous on return like
+ *      the reference wrappers.  `stream` is a cudaStream_t (NULL = default stream). ------------------ */
+/* `sweeps` weighted-Jacobi sweeps in place on x; scratch: width*height doubles (nullable: allocated
+ * and freed inside).  Parallel::ComputeJacobi(d_x,d_f,height,width,h,v) == sweeps = v+1, omega = 1,
+ * but race-free (double buffered) unlike jacobi_kernel (Parallel_Method.cu:6-24). */
+pmg_status pmg_jacobi(double *x, const double *f, int width, int height, double h, double omega,
+                      int sweeps, double *scratch, void *stream);
+/* r = f - A x on the interior (ring of r untouched); norm2_out (nullable, HOST pointer) = sum r^2 */
+pmg_status pmg_residual(double *r, const double *x, const double *f, int width, int height, double h,
+                        double *norm2_out, void *stream);
+/* coarse interior = full weighting of fine (MultiGrid.hpp:187-205); coarse ring untouched */
+pmg_status pmg_restrict_fw(const double *fine, double *coarse, int nf, int nc, void *stream);
+/* fine += P coarse (MultiGrid.hpp:208-226) */
+pmg_status pmg_prolong_add(const double *coarse, double *fine, int nc, int nf, int mode, void *stream);
+/* sum v[i]^2 over l entries -> HOST double (DynamicGridUtils::norm squared, :21-27) */
+pmg_status pmg_norm2(const double *v, size_t l, double *norm2_out, void *stream);
+
+/* ---- memory helpers for callers without a CUDA toolchain ------------------------------------- */
+pmg_status pmg_device_alloc(void **p, size_t bytes);
+pmg_status pmg_device_free(void *p);
+pmg_status pmg_host_alloc_pinned(void **p, size_t bytes);
+pmg_status pmg_host_free_pinned(void *p);
+pmg_status pmg_memcpy(void *dst, const void *src, size_t bytes, int dst_is_device, int src_is_device);
+pmg_status pmg_device_synchronize(void);
+int pmg_device_count(void);
+
+/* ---- multi-GPU bootstrap (one process per GPU; ids travel over the caller's own channel, e.g.
+ *      torch.distributed) -------------------------------------------------------------------------- */
+#define PMG_COMM_ID_BYTES 128
+pmg_status pmg_comm_unique_id(unsigned char id[PMG_COMM_ID_BYTES]);
+/* must be called (collectively) before pmg_create with cfg.n_ranks > 1 */
+pmg_status pmg_comm_init(const unsigned char id[PMG_COMM_ID_BYTES], int rank, int n_ranks, int device);
+pmg_status pmg_comm_finalize(void);
+/* rows [*y0, *y1) of an n-row level owned by `rank` (even-aligned splits); pure host arithmetic */
+pmg_status pmg_partition_rows(int n, int n_ranks, int rank, int *y0, int *y1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMG_H */

@@ -1,0 +1,303 @@
+"""ctypes front-end over libpmg.so (the C ABI of include/pmg.h).
+
+The product is the C/C++/CUDA library; this module is glue for the tests and bench.py.  It never
+computes anything itself and has NO fallback: if libpmg.so is missing or no B200 is visible, calls
+raise.  (The directory name contains hyphens, so import it through the repo-root shim `pmg_b200`.)
+
+Reference surface mirrored here (see include/pmg.hpp for the C++ twin):
+  Solver.cycle / Solver.solve   <- MultigridSolver::{v,w,f}_cycle + the runner loop
+                                   (2_part_MG/MultiGrid.hpp:57-183, MultiGridTestRunner.hpp:190-212)
+  jacobi / residual / restrict_fw / prolong_add / norm2
+                                <- class Parallel + DynamicGridUtils
+                                   (3_part_parallel/Parallel_Method.cu:144-199, DynamicGridUtils.hpp:21-69)
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmg.so")
+
+V, W, F = 0, 1, 2
+PROLONG_REFERENCE, PROLONG_FULL = 0, 1
+ENGINE_FUSED, ENGINE_OPERATOR = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+OK = 0
+STATUS_NAMES = {0: "PMG_OK", 1: "PMG_ERR_INVALID", 2: "PMG_ERR_CUDA", 3: "PMG_ERR_NO_DEVICE",
+                4: "PMG_ERR_ALLOC", 5: "PMG_ERR_COMM", 6: "PMG_ERR_UNSUPPORTED"}
+
+
+class PmgError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), message))
+        self.status = status
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int), ("nu1", ctypes.c_int), ("nu2", ctypes.c_int),
+                ("omega", ctypes.c_double), ("gamma", ctypes.c_int), ("n_coarse", ctypes.c_int),
+                ("coarse_sweeps", ctypes.c_int), ("fmg_sweeps", ctypes.c_int),
+                ("prolong_mode", ctypes.c_int), ("engine", ctypes.c_int),
+                ("smoother_eps", ctypes.c_double), ("device", ctypes.c_int), ("use_graph", ctypes.c_int),
+                ("rank", ctypes.c_int), ("n_ranks", ctypes.c_int), ("agglomerate_below", ctypes.c_int),
+                ("reserved", ctypes.c_int * 8)]
+
+
+# every symbol include/pmg.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = [
+    "pmg_version", "pmg_last_error", "pmg_status_string", "pmg_config_default", "pmg_kernel_launches",
+    "pmg_create", "pmg_destroy", "pmg_set_rhs", "pmg_set_guess", "pmg_get_solution", "pmg_zero_guess",
+    "pmg_set_rhs_sine", "pmg_residual_norm", "pmg_cycle", "pmg_solve", "pmg_last_device_ms", "pmg_stream",
+    "pmg_jacobi", "pmg_residual", "pmg_restrict_fw", "pmg_prolong_add", "pmg_norm2",
+    "pmg_device_alloc", "pmg_device_free", "pmg_host_alloc_pinned", "pmg_host_free_pinned", "pmg_memcpy",
+    "pmg_device_synchronize", "pmg_device_count",
+    "pmg_comm_unique_id", "pmg_comm_init", "pmg_comm_finalize", "pmg_partition_rows",
+]
+
+_lib = None
+
+
+def build():
+    """Compile libpmg.so for sm_100a with the package Makefile (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-s", "-C", _HERE, "-j4"], check=True)
+
+
+def lib():
+    """The loaded library.  Fails loudly when the CUDA build is missing -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libpmg.so is not built (%s): run `python -c 'import __graft_entry__ as g; "
+                           "g.build()'` or `make -C %s`; there is no CPU fallback" % (LIB_PATH, _HERE))
+    L = ctypes.CDLL(LIB_PATH)
+    vp, dp, i, d, sz = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+    pd = ctypes.POINTER(ctypes.c_double)
+    pi = ctypes.POINTER(ctypes.c_int)
+    L.pmg_version.restype = ctypes.c_char_p
+    L.pmg_last_error.restype = ctypes.c_char_p
+    L.pmg_status_string.restype = ctypes.c_char_p
+    L.pmg_status_string.argtypes = [i]
+    L.pmg_config_default.restype = None
+    L.pmg_config_default.argtypes = [ctypes.POINTER(Config), i]
+    L.pmg_kernel_launches.restype = ctypes.c_ulonglong
+    L.pmg_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(vp)]
+    L.pmg_destroy.restype = None
+    L.pmg_destroy.argtypes = [vp]
+    for name in ("pmg_set_rhs", "pmg_set_guess", "pmg_get_solution"):
+        getattr(L, name).argtypes = [vp, dp, i]
+    L.pmg_zero_guess.argtypes = [vp]
+    L.pmg_set_rhs_sine.argtypes = [vp]
+    L.pmg_residual_norm.argtypes = [vp, pd]
+    L.pmg_cycle.argtypes = [vp, i, pd]
+    L.pmg_solve.argtypes = [vp, i, d, i, pd, pi]
+    L.pmg_last_device_ms.argtypes = [vp, pd]
+    L.pmg_stream.restype = vp
+    L.pmg_stream.argtypes = [vp]
+    L.pmg_jacobi.argtypes = [dp, dp, i, i, d, d, i, dp, vp]
+    L.pmg_residual.argtypes = [dp, dp, dp, i, i, d, pd, vp]
+    L.pmg_restrict_fw.argtypes = [dp, dp, i, i, vp]
+    L.pmg_prolong_add.argtypes = [dp, dp, i, i, i, vp]
+    L.pmg_norm2.argtypes = [dp, sz, pd, vp]
+    L.pmg_device_alloc.argtypes = [ctypes.POINTER(vp), sz]
+    L.pmg_device_free.argtypes = [vp]
+    L.pmg_host_alloc_pinned.argtypes = [ctypes.POINTER(vp), sz]
+    L.pmg_host_free_pinned.argtypes = [vp]
+    L.pmg_memcpy.argtypes = [vp, vp, sz, i, i]
+    L.pmg_partition_rows.argtypes = [i, i, i, pi, pi]
+    L.pmg_smooth.argtypes = [vp, i, i]
+    L.pmg_bench_pass.argtypes = [vp, i, i, i, pd]
+    L.pmg_fused_set_variant.restype = None
+    L.pmg_fused_set_variant.argtypes = [i]
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != OK:
+        raise PmgError(status, lib().pmg_last_error().decode())
+
+
+def device_count():
+    return lib().pmg_device_count()
+
+
+def kernel_launches():
+    return int(lib().pmg_kernel_launches())
+
+
+def default_config(n, **overrides):
+    cfg = Config()
+    lib().pmg_config_default(ctypes.byref(cfg), n)
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError("unknown config field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def partition_rows(n, n_ranks, rank):
+    y0, y1 = ctypes.c_int(), ctypes.c_int()
+    check(lib().pmg_partition_rows(n, n_ranks, rank, ctypes.byref(y0), ctypes.byref(y1)))
+    return y0.value, y1.value
+
+
+class DeviceArray:
+    """A device buffer of doubles owned through pmg_device_alloc (tests need no torch)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+        self.size = int(np.prod(self.shape))
+        p = ctypes.c_void_p()
+        check(lib().pmg_device_alloc(ctypes.byref(p), max(self.size, 1) * 8))
+        self.ptr = p.value
+
+    @classmethod
+    def from_numpy(cls, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        d = cls(a.shape)
+        check(lib().pmg_memcpy(d.ptr, a.ctypes.data, a.size * 8, 1, 0))
+        return d
+
+    def numpy(self):
+        out = np.empty(self.shape, dtype=np.float64)
+        check(lib().pmg_memcpy(out.ctypes.data, self.ptr, self.size * 8, 0, 1))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().pmg_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _ptr_and_mem(a):
+    """(address, pmg_mem) of a numpy array, a DeviceArray or a torch tensor."""
+    if isinstance(a, DeviceArray):
+        return a.ptr, MEM_DEVICE
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data, MEM_HOST
+    if hasattr(a, "data_ptr"):  # torch tensor
+        assert a.is_contiguous() and str(a.dtype) == "torch.float64"
+        return a.data_ptr(), (MEM_DEVICE if a.is_cuda else MEM_HOST)
+    raise TypeError(type(a))
+
+
+class Solver:
+    """One multigrid hierarchy resident in HBM (pmg_solver)."""
+
+    def __init__(self, n, **cfg):
+        self.cfg = default_config(n, **cfg)
+        self.n = n
+        h = ctypes.c_void_p()
+        check(lib().pmg_create(ctypes.byref(self.cfg), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pmg_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_rhs(self, f):
+        p, m = _ptr_and_mem(f)
+        check(lib().pmg_set_rhs(self._h, p, m))
+
+    def set_rhs_sine(self):
+        check(lib().pmg_set_rhs_sine(self._h))
+
+    def set_guess(self, phi):
+        p, m = _ptr_and_mem(phi)
+        check(lib().pmg_set_guess(self._h, p, m))
+
+    def zero_guess(self):
+        check(lib().pmg_zero_guess(self._h))
+
+    def get_solution(self, out=None):
+        if out is None:
+            out = np.empty((self.n, self.n))
+        p, m = _ptr_and_mem(out)
+        check(lib().pmg_get_solution(self._h, p, m))
+        return out
+
+    def residual_norm(self):
+        v = ctypes.c_double()
+        check(lib().pmg_residual_norm(self._h, ctypes.byref(v)))
+        return v.value
+
+    def cycle(self, kind=V, want_norm=True):
+        v = ctypes.c_double()
+        check(lib().pmg_cycle(self._h, kind, ctypes.byref(v) if want_norm else None))
+        return v.value if want_norm else None
+
+    def solve(self, kind=V, rel_tol=1e-8, max_cycles=100):
+        hist = (ctypes.c_double * (max_cycles + 1))()
+        k = ctypes.c_int()
+        check(lib().pmg_solve(self._h, kind, rel_tol, max_cycles, hist, ctypes.byref(k)))
+        return k.value, np.array(hist[: k.value + 1])
+
+    def smooth(self, sweeps, block=1):
+        check(lib().pmg_smooth(self._h, sweeps, block))
+
+    def bench_pass(self, which, level=0, reps=5):
+        """Average device ms of one fused pass in isolation (0: Pass A, 1: Pass B + norm, 2: Pass B,
+        3: Pass A from a zero iterate).  Clobbers the iterate."""
+        v = ctypes.c_double()
+        check(lib().pmg_bench_pass(self._h, which, level, reps, ctypes.byref(v)))
+        return v.value
+
+    @property
+    def last_ms(self):
+        v = ctypes.c_double()
+        check(lib().pmg_last_device_ms(self._h, ctypes.byref(v)))
+        return v.value
+
+    @property
+    def stream(self):
+        return lib().pmg_stream(self._h)
+
+
+# ---- operator level (device pointers, dense reference layout) ----------------------------------------
+def jacobi(x, f, h, omega=1.0, sweeps=1, scratch=None):
+    check(lib().pmg_jacobi(x.ptr, f.ptr, x.shape[1], x.shape[0], h, omega, sweeps,
+                           scratch.ptr if scratch is not None else None, None))
+
+
+def residual(r, x, f, h, want_norm2=False):
+    v = ctypes.c_double()
+    check(lib().pmg_residual(r.ptr if r is not None else None, x.ptr, f.ptr, x.shape[1], x.shape[0], h,
+                             ctypes.byref(v) if want_norm2 else None, None))
+    return v.value if want_norm2 else None
+
+
+def restrict_fw(fine, coarse):
+    check(lib().pmg_restrict_fw(fine.ptr, coarse.ptr, fine.shape[0], coarse.shape[0], None))
+
+
+def prolong_add(coarse, fine, mode=PROLONG_REFERENCE):
+    check(lib().pmg_prolong_add(coarse.ptr, fine.ptr, coarse.shape[0], fine.shape[0], mode, None))
+
+
+def norm2(v):
+    out = ctypes.c_double()
+    check(lib().pmg_norm2(v.ptr, v.size, ctypes.byref(out), None))
+    return out.value
+
+
+def set_fused_variant(v):
+    lib().pmg_fused_set_variant(v)

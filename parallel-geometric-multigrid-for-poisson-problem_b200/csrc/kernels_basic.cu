@@ -1,0 +1,317 @@
+// kernels_basic.cu -- one kernel per reference operator (the PMG_ENGINE_OPERATOR engine and the
+// operator-level C ABI that replaces class Parallel, 3_part_parallel/Parallel_Method.cu:144-199).
+//
+// Every kernel takes pointers to logical (0,0) plus a row pitch, so the same code serves the dense
+// reference layout (pitch = width) and the solver's padded hierarchy.  Arithmetic follows the
+// reference's evaluation order with explicit round-to-nearest adds/multiplies (no FMA contraction):
+// outputs are bit-identical to the CPU path.  All are HBM-bound: 24 B/pt (Jacobi, residual),
+// 10 B/fine-pt (restriction), 18 B/fine-pt (prolongation) -- see DESIGN.md section 4.
+#include <atomic>
+
+#include "pmg_internal.h"
+
+namespace pmg {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+
+constexpr int BX = 64, BY = 4;  // 256 threads; a warp covers 32 consecutive columns of one row
+
+inline dim3 grid2d(int nx, int ny) { return dim3((nx + BX - 1) / BX, (ny + BY - 1) / BY); }
+
+// ---- weighted Jacobi sweep: Smoother.hpp:61-70 (replaces jacobi_kernel, Parallel_Method.cu:6-24,
+//      which updates in place and races) -------------------------------------------------------------
+__global__ void __launch_bounds__(BX *BY)
+    k_jacobi_sweep(double *__restrict__ out, const double *__restrict__ in, const double *__restrict__ f,
+                   int nx, int ny, int pitch_x, int pitch_f, JacobiCoef c)
+{
+    int x = blockIdx.x * BX + threadIdx.x;
+    int y = blockIdx.y * BY + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    size_t i = (size_t)y * pitch_x + x;
+    double v = in[i];
+    if (x > 0 && x < nx - 1 && y > 0 && y < ny - 1)
+        v = jacobi_point(c, f[(size_t)y * pitch_f + x], v, in[i - 1], in[i + 1], in[i - pitch_x],
+                         in[i + pitch_x]);
+    out[i] = v;
+}
+
+// ---- all sweeps of a small level inside one CTA (coarsest-grid solve, MultiGrid.hpp:59-63) ---------
+__global__ void __launch_bounds__(1024)
+    k_jacobi_small(double *__restrict__ xg, const double *__restrict__ fg, int nx, int ny, int pitch_x,
+                   int pitch_f, JacobiCoef c, int sweeps, int x_is_zero)
+{
+    __shared__ double a[SMALL_MAX_POINTS], b[SMALL_MAX_POINTS], fs[SMALL_MAX_POINTS];
+    int l = nx * ny;
+    for (int i = threadIdx.x; i < l; i += blockDim.x) {
+        int y = i / nx, x = i - y * nx;
+        double v = x_is_zero ? 0.0 : xg[(size_t)y * pitch_x + x];
+        a[i] = v;
+        b[i] = v;
+        fs[i] = fg[(size_t)y * pitch_f + x];
+    }
+    __syncthreads();
+    double *src = a, *dst = b;
+    for (int s = 0; s < sweeps; ++s) {
+        for (int i = threadIdx.x; i < l; i += blockDim.x) {
+            int y = i / nx, x = i - y * nx;
+            if (x > 0 && x < nx - 1 && y > 0 && y < ny - 1)
+                dst[i] = jacobi_point(c, fs[i], src[i], src[i - 1], src[i + 1], src[i - nx], src[i + nx]);
+        }
+        __syncthreads();
+        double *t = src;
+        src = dst;
+        dst = t;
+    }
+    for (int i = threadIdx.x; i < l; i += blockDim.x) {
+        int y = i / nx, x = i - y * nx;
+        xg[(size_t)y * pitch_x + x] = src[i];
+    }
+}
+
+// ---- residual: DynamicGridUtils.hpp:59-69 (replaces device_compute_residual, Parallel_Method.cu:26-46)
+__global__ void __launch_bounds__(BX *BY)
+    k_residual(double *__restrict__ r, const double *__restrict__ xg, const double *__restrict__ f, int nx,
+               int ny, int pitch_r, int pitch_x, int pitch_f, double inv_h2)
+{
+    int x = blockIdx.x * BX + threadIdx.x;
+    int y = blockIdx.y * BY + threadIdx.y;
+    if (x < 1 || y < 1 || x >= nx - 1 || y >= ny - 1) return;
+    size_t i = (size_t)y * pitch_x + x;
+    r[(size_t)y * pitch_r + x] = residual_point(inv_h2, f[(size_t)y * pitch_f + x], xg[i], xg[i - 1],
+                                                xg[i + 1], xg[i - pitch_x], xg[i + pitch_x]);
+}
+
+// ---- deterministic sum reductions -------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int RED_BLOCKS = 148 * 8;
+
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double warp_part[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_xor_sync(0xffffffffu, v, o));
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) warp_part[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? warp_part[threadIdx.x] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    return v;  // valid in thread 0
+}
+
+// sum over the interior of (f - A x)^2 without materialising r (16 B/pt)
+__global__ void __launch_bounds__(RED_THREADS)
+    k_residual_norm2(const double *__restrict__ xg, const double *__restrict__ f, int nx, int ny,
+                     int pitch_x, int pitch_f, double inv_h2, double *__restrict__ partials)
+{
+    double acc = 0.0;
+    int chunks_x = (nx + RED_THREADS - 1) / RED_THREADS;
+    long total = (long)chunks_x * ny;
+    for (long t = blockIdx.x; t < total; t += gridDim.x) {
+        int y = (int)(t / chunks_x);
+        int x = (int)(t - (long)y * chunks_x) * RED_THREADS + threadIdx.x;
+        if (x >= 1 && y >= 1 && x < nx - 1 && y < ny - 1) {
+            size_t i = (size_t)y * pitch_x + x;
+            double r = residual_point(inv_h2, f[(size_t)y * pitch_f + x], xg[i], xg[i - 1], xg[i + 1],
+                                      xg[i - pitch_x], xg[i + pitch_x]);
+            acc = dadd(acc, dmul(r, r));
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+    k_norm2(const double *__restrict__ v, size_t l, double *__restrict__ partials)
+{
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * RED_THREADS + threadIdx.x; i < l;
+         i += (size_t)gridDim.x * RED_THREADS) {
+        double t = v[i];
+        acc = dadd(acc, dmul(t, t));
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(1024) k_final_sum(const double *__restrict__ partials, int count,
+                                                    double *__restrict__ out)
+{
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) acc = dadd(acc, partials[i]);
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) *out = acc;
+}
+
+// ---- full-weighting restriction: MultiGrid.hpp:187-205 (replaces restriction_kernel_full_weighting,
+//      Parallel_Method.cu:48-78) ---------------------------------------------------------------------
+__global__ void __launch_bounds__(BX *BY)
+    k_restrict(const double *__restrict__ fine, double *__restrict__ coarse, int nc, int pitch_f, int pitch_c)
+{
+    int ic = blockIdx.x * BX + threadIdx.x;
+    int jc = blockIdx.y * BY + threadIdx.y;
+    if (ic < 1 || jc < 1 || ic >= nc - 1 || jc >= nc - 1) return;
+    const double *c = fine + (size_t)(2 * jc) * pitch_f + 2 * ic;
+    coarse[(size_t)jc * pitch_c + ic] =
+        restrict_point(c[0], c[1], c[-1], c[pitch_f], c[-pitch_f], c[-pitch_f - 1], c[-pitch_f + 1],
+                       c[pitch_f - 1], c[pitch_f + 1]);
+}
+
+// ---- bilinear prolongation-and-add: MultiGrid.hpp:208-226.  One thread per FINE point; the parity of
+//      (x, y) selects the same expression the reference's coarse-point loop evaluates for that point.
+//      lo = 2 (REFERENCE: fine row/col 1 skipped) or 1 (FULL). ---------------------------------------
+__global__ void __launch_bounds__(BX *BY)
+    k_prolong_add(const double *__restrict__ coarse, double *__restrict__ fine, int nf, int pitch_c,
+                  int pitch_f, int lo)
+{
+    int x = blockIdx.x * BX + threadIdx.x;
+    int y = blockIdx.y * BY + threadIdx.y;
+    if (x < lo || y < lo || x > nf - 2 || y > nf - 2) return;
+    int ic = x >> 1, jc = y >> 1;
+    const double *c = coarse + (size_t)jc * pitch_c + ic;
+    double v;
+    if ((y & 1) == 0)
+        v = ((x & 1) == 0) ? c[0] : dmul(0.5, dadd(c[0], c[1]));
+    else
+        v = ((x & 1) == 0) ? dmul(0.5, dadd(c[0], c[pitch_c]))
+                           : dmul(0.25, dadd(dadd(dadd(c[0], c[1]), c[pitch_c]), c[pitch_c + 1]));
+    size_t i = (size_t)y * pitch_f + x;
+    fine[i] = dadd(fine[i], v);
+}
+
+__global__ void __launch_bounds__(BX *BY)
+    k_copy2d(double *__restrict__ dst, int pitch_d, const double *__restrict__ src, int pitch_s, int nx, int ny)
+{
+    int x = blockIdx.x * BX + threadIdx.x;
+    int y = blockIdx.y * BY + threadIdx.y;
+    if (x < nx && y < ny) dst[(size_t)y * pitch_d + x] = src[(size_t)y * pitch_s + x];
+}
+
+__global__ void __launch_bounds__(BX *BY) k_fill2d(double *__restrict__ dst, int pitch_d, int nx, int ny, double v)
+{
+    int x = blockIdx.x * BX + threadIdx.x;
+    int y = blockIdx.y * BY + threadIdx.y;
+    if (x < nx && y < ny) dst[(size_t)y * pitch_d + x] = v;
+}
+
+__global__ void __launch_bounds__(BX *BY)
+    k_rhs_separable(double *__restrict__ f, int pitch, int nx, int ny, double factor,
+                    const double *__restrict__ sx, const double *__restrict__ sy)
+{
+    int x = blockIdx.x * BX + threadIdx.x;
+    int y = blockIdx.y * BY + threadIdx.y;
+    if (x < nx && y < ny) f[(size_t)y * pitch + x] = dmul(dmul(factor, sx[x]), sy[y]);
+}
+
+inline JacobiCoef make_coef(double h, double omega)
+{
+    JacobiCoef c;
+    c.h2 = h * h;
+    c.omega = omega;
+    c.om1 = 1.0 - omega;
+    c.weighted = (omega != 1.0);
+    return c;
+}
+
+}  // namespace
+
+JacobiCoef jacobi_coef(double h, double omega) { return make_coef(h, omega); }
+
+void launch_jacobi_sweep(double *out, const double *in, const double *f, int nx, int ny, int pitch_x,
+                         int pitch_f, double h, double omega, cudaStream_t st)
+{
+    k_jacobi_sweep<<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(out, in, f, nx, ny, pitch_x, pitch_f,
+                                                            make_coef(h, omega));
+    count_launch();
+}
+
+void launch_jacobi_small(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h,
+                         double omega, int sweeps, bool x_is_zero, cudaStream_t st)
+{
+    int l = nx * ny;
+    int threads = l >= 1024 ? 1024 : ((l + 31) / 32) * 32;
+    k_jacobi_small<<<1, threads, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, make_coef(h, omega), sweeps, x_is_zero ? 1 : 0);
+    count_launch();
+}
+
+void launch_residual(double *r, const double *x, const double *f, int nx, int ny, int pitch_r, int pitch_x,
+                     int pitch_f, double h, cudaStream_t st)
+{
+    k_residual<<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(r, x, f, nx, ny, pitch_r, pitch_x, pitch_f,
+                                                        1.0 / (h * h));
+    count_launch();
+}
+
+int reduce_partials() { return RED_BLOCKS; }
+
+void launch_final_sum(const double *d_partials, int count, double *d_out, cudaStream_t st)
+{
+    k_final_sum<<<1, 1024, 0, st>>>(d_partials, count, d_out);
+    count_launch();
+}
+
+void launch_residual_norm2(const double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f,
+                           double h, double *d_partials, double *d_out, cudaStream_t st)
+{
+    long chunks = (long)((nx + RED_THREADS - 1) / RED_THREADS) * ny;
+    int blocks = (int)(chunks < RED_BLOCKS ? chunks : RED_BLOCKS);
+    if (blocks < 1) blocks = 1;
+    k_residual_norm2<<<blocks, RED_THREADS, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, 1.0 / (h * h), d_partials);
+    count_launch();
+    launch_final_sum(d_partials, blocks, d_out, st);
+}
+
+void launch_norm2(const double *v, size_t l, double *d_partials, double *d_out, cudaStream_t st)
+{
+    size_t want = (l + RED_THREADS - 1) / RED_THREADS;
+    int blocks = (int)(want < (size_t)RED_BLOCKS ? want : (size_t)RED_BLOCKS);
+    if (blocks < 1) blocks = 1;
+    k_norm2<<<blocks, RED_THREADS, 0, st>>>(v, l, d_partials);
+    count_launch();
+    launch_final_sum(d_partials, blocks, d_out, st);
+}
+
+void launch_restrict(const double *fine, double *coarse, int nf, int nc, int pitch_f, int pitch_c, cudaStream_t st)
+{
+    (void)nf;
+    k_restrict<<<grid2d(nc, nc), dim3(BX, BY), 0, st>>>(fine, coarse, nc, pitch_f, pitch_c);
+    count_launch();
+}
+
+void launch_prolong_add(const double *coarse, double *fine, int nc, int nf, int pitch_c, int pitch_f, int mode,
+                        cudaStream_t st)
+{
+    (void)nc;
+    k_prolong_add<<<grid2d(nf, nf), dim3(BX, BY), 0, st>>>(coarse, fine, nf, pitch_c, pitch_f,
+                                                           mode == PMG_PROLONG_FULL ? 1 : 2);
+    count_launch();
+}
+
+void launch_copy2d(double *dst, int pitch_d, const double *src, int pitch_s, int nx, int ny, cudaStream_t st)
+{
+    k_copy2d<<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(dst, pitch_d, src, pitch_s, nx, ny);
+    count_launch();
+}
+
+void launch_fill2d(double *dst, int pitch_d, int nx, int ny, double v, cudaStream_t st)
+{
+    k_fill2d<<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(dst, pitch_d, nx, ny, v);
+    count_launch();
+}
+
+void launch_rhs_separable(double *f, int pitch, int nx, int ny, double factor, const double *sx,
+                          const double *sy, cudaStream_t st)
+{
+    k_rhs_separable<<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(f, pitch, nx, ny, factor, sx, sy);
+    count_launch();
+}
+
+}  // namespace pmg

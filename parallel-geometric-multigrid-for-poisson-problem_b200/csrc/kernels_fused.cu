@@ -1,0 +1,562 @@
+// kernels_fused.cu -- temporally blocked, warp-streaming kernels: the PMG_ENGINE_FUSED engine.
+//
+// One multigrid level visit costs two passes over HBM instead of the reference's eight-plus:
+//
+//   Pass A  (k_down)  xb = S^nu1(x);  f_coarse = R(f - A xb)        reads x,f   writes xb, f_coarse
+//                     = Smoother::smooth + compute_residual + restrict_full_weighting
+//                       (MultiGrid.hpp:66-78)                         26 B / point  (18 if x == 0)
+//   Pass B  (k_up)    x  = S^nu2(xb + P e_coarse) [, sum (f - A x)^2] reads xb,e,f  writes x
+//                     = prolongation + Smoother::smooth (+ the runner's residual norm)
+//                       (MultiGrid.hpp:86-89, MultiGridTestRunner.hpp:210-211)   26 B / point
+//
+// Execution model.  No shared memory, no block barriers: every WARP owns a
+// strip of 128 columns (32 lanes x 4 consecutive columns, two 128-bit loads per lane per row per
+// array) and streams down a chunk of rows.  All stages of the pass are pipelined over the rows in
+// registers: sweep k finalises row j-k when input row j arrives, the residual follows one row behind
+// the last sweep and the full-weighting stencil one row behind that.  Horizontal neighbours come from
+// two warp shuffles per stage per row; vertical neighbours are the register window.  Strips overlap
+// by HALO columns on each side (the temporally blocked stages eat one column per stage), chunks
+// overlap by the pipeline depth in rows; overlapped data is re-read from L2, not HBM.  Rows are
+// prefetched PF rows ahead into registers, so each warp keeps 2*PF KB in flight (x and f).
+//
+// Arithmetic is the reference's, operation for operation and in its order (pmg_internal.h), with no
+// FMA contraction: every value written is bit-identical to the CPU path.  Partial sums
+// ((h^2 f + W) + E) + S are formed when a row arrives and completed with + N one row later, which is
+// exactly the reference's left-to-right evaluation.
+#include "pmg_internal.h"
+
+namespace pmg {
+
+namespace {
+
+// Tunables (template parameters of the kernels; `Variant` picks a combination at run time):
+//   C     columns per lane (4: two 128-bit accesses per row per array, strip = 128; 2: one, strip = 64)
+//   PF    rows prefetched ahead into registers (even)
+//   MINB  CTAs per SM promised to the compiler (register budget = 65536 / (128*MINB))
+constexpr int WARPS_PER_CTA = 4;
+
+__host__ __device__ constexpr int halo_for(int stages) { return stages <= 4 ? 4 : 8; }
+
+struct StripGeom {
+    int n;           // logical points per side
+    int pitch;       // row pitch of x / xb / f (doubles)
+    int n_strips;    // strips across
+    int n_chunks;    // row chunks
+    int chunk_rows;  // rows per chunk (even)
+    int halo;        // strip overlap per side (multiple of 4)
+    int stride;      // STRIP - 2*halo: columns owned per strip
+};
+
+template <int C>
+struct Row {
+    double v[C];
+};
+
+template <int C>
+__device__ __forceinline__ Row<C> load_row(const double *__restrict__ p)
+{
+    // 128-bit read-only loads; p is 16*C/2-byte aligned by construction of the layout
+    Row<C> r;
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(p) + k);
+        r.v[2 * k] = a.x;
+        r.v[2 * k + 1] = a.y;
+    }
+    return r;
+}
+
+template <int C>
+__device__ __forceinline__ void store_row(double *__restrict__ p, const Row<C> &r)
+{
+#pragma unroll
+    for (int k = 0; k < C / 2; ++k)
+        reinterpret_cast<double2 *>(p)[k] = make_double2(r.v[2 * k], r.v[2 * k + 1]);
+}
+
+template <int C>
+__device__ __forceinline__ Row<C> zero_row()
+{
+    Row<C> r;
+#pragma unroll
+    for (int k = 0; k < C; ++k) r.v[k] = 0.0;
+    return r;
+}
+
+// west / east neighbours of a lane's C columns
+template <int C>
+__device__ __forceinline__ void neighbours(const Row<C> &c, Row<C> &w, Row<C> &e)
+{
+    double from_left = __shfl_up_sync(0xffffffffu, c.v[C - 1], 1);
+    double from_right = __shfl_down_sync(0xffffffffu, c.v[0], 1);
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        w.v[k] = (k == 0) ? from_left : c.v[k == 0 ? 0 : k - 1];
+        e.v[k] = (k == C - 1) ? from_right : c.v[k == C - 1 ? k : k + 1];
+    }
+}
+
+// One weighted-Jacobi stage of the row pipeline.  `cen` = input row i-1, `part` = the partial sum
+// ((h^2 f + W) + E) + S of row i-1.  Given input row i (`in`) and f of row i it returns the finished
+// output row i-1 and advances the state to row i.
+template <int C>
+struct SweepStage {
+    Row<C> cen, part;
+    __device__ __forceinline__ void init()
+    {
+        cen = zero_row<C>();
+        part = zero_row<C>();
+    }
+    __device__ __forceinline__ Row<C> step(const Row<C> &in, const Row<C> &f_row, const JacobiCoef &c,
+                                           bool out_row_interior, const bool (&col_interior)[C])
+    {
+        Row<C> out, w, e;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            double jac = dmul(0.25, dadd(part.v[k], in.v[k]));
+            double val = c.weighted ? dadd(dmul(c.om1, cen.v[k]), dmul(c.omega, jac)) : jac;
+            out.v[k] = (out_row_interior && col_interior[k]) ? val : cen.v[k];
+        }
+        neighbours<C>(in, w, e);
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            part.v[k] = dadd(dadd(dadd(dmul(c.h2, f_row.v[k]), w.v[k]), e.v[k]), cen.v[k]);
+        cen = in;
+        return out;
+    }
+};
+
+// Residual stage: same pipeline shape; returns r of row i-1 given x row i.
+template <int C>
+struct ResidualStage {
+    Row<C> part;  // ((4x - W) - E) - S of row i-1
+    Row<C> cen;   // x row i-1
+    __device__ __forceinline__ void init()
+    {
+        cen = zero_row<C>();
+        part = zero_row<C>();
+    }
+    __device__ __forceinline__ Row<C> step(const Row<C> &in, const Row<C> &f_prev, double inv_h2)
+    {
+        Row<C> r, w, e;
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            r.v[k] = dsub(f_prev.v[k], dmul(inv_h2, dsub(part.v[k], in.v[k])));
+        neighbours<C>(in, w, e);
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            part.v[k] = dsub(dsub(dsub(dmul(4.0, in.v[k]), w.v[k]), e.v[k]), cen.v[k]);
+        cen = in;
+        return r;
+    }
+};
+
+template <int C>
+__device__ __forceinline__ void strip_setup(const StripGeom &g, int wid, int lane, int &col, int &r0, int &r1,
+                                            bool &owner, bool (&col_interior)[C])
+{
+    int chunk = wid / g.n_strips;
+    int strip = wid - chunk * g.n_strips;
+    col = -g.halo + strip * g.stride + C * lane;
+    r0 = chunk * g.chunk_rows;
+    r1 = min(r0 + g.chunk_rows, g.n);
+    int first_owner = g.halo / C;
+    owner = (lane >= first_owner) && (lane < first_owner + g.stride / C);
+#pragma unroll
+    for (int k = 0; k < C; ++k) col_interior[k] = (col + k > 0) && (col + k < g.n - 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pass A.  S sweeps; RESID adds residual + full weighting into the coarse RHS; ZEROX: x == 0 on entry.
+// ---------------------------------------------------------------------------------------------------
+template <int C, int PF, int MINB, int S, bool ZEROX, bool RESID>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
+    k_down(const double *__restrict__ x, double *__restrict__ xo, const double *__restrict__ f,
+           double *__restrict__ cf, StripGeom g, int pitch_c, int nc, JacobiCoef coef, double inv_h2)
+{
+    constexpr int NP = C / 2;  // coarse points per lane (fine columns v0, v2, ...)
+    const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= g.n_strips * g.n_chunks) return;
+    int col, r0, r1;
+    bool owner, cin[C];
+    strip_setup<C>(g, wid, lane, col, r0, r1, owner, cin);
+
+    const int lead = RESID ? 2 : 0;  // extra finished rows needed above the chunk
+    const int j_start = r0 - lead - S;
+    const int j_end = r1 - 1 + (RESID ? 1 : 0) + S;  // inclusive
+
+    SweepStage<C> st[S];
+    ResidualStage<C> rs;
+#pragma unroll
+    for (int k = 0; k < S; ++k) st[k].init();
+    rs.init();
+    Row<C> fq[S + 2];  // fq[d] = f of row j-d
+#pragma unroll
+    for (int d = 0; d < S + 2; ++d) fq[d] = zero_row<C>();
+    // full-weighting state per coarse point of this lane:
+    //   south row 2jc-1: s_mid (centre value), s_cor = SW + SE;  centre row 2jc: c_mid, c_ew = E + W
+    double s_mid[NP], s_cor[NP], c_mid[NP], c_ew[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) s_mid[q] = s_cor[q] = c_mid[q] = c_ew[q] = 0.0;
+
+    Row<C> xbuf[PF], fbuf[PF];
+#pragma unroll
+    for (int d = 0; d < PF; ++d) {
+        xbuf[d] = ZEROX ? zero_row<C>() : load_row<C>(x + (ptrdiff_t)(j_start + d) * g.pitch + col);
+        fbuf[d] = load_row<C>(f + (ptrdiff_t)(j_start + d) * g.pitch + col);
+    }
+    const int last_row = g.n + PADY - 1;  // last row that exists in the allocation
+
+    for (int j = j_start; j <= j_end; j += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int jj = j + u;  // input row of this step (steps past j_end are harmless: stores are masked)
+            Row<C> cur = xbuf[u];
+#pragma unroll
+            for (int d = S + 1; d > 0; --d) fq[d] = fq[d - 1];
+            fq[0] = fbuf[u];
+            {   // refill the slot with row jj + PF (clamped to the allocation)
+                int nr = min(jj + PF, last_row);
+                if (!ZEROX) xbuf[u] = load_row<C>(x + (ptrdiff_t)nr * g.pitch + col);
+                fbuf[u] = load_row<C>(f + (ptrdiff_t)nr * g.pitch + col);
+            }
+            // sweeps: stage k consumes x_k row jj-k and finishes x_{k+1} row jj-k-1
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                const int out_row = jj - k - 1;
+                cur = st[k].step(cur, fq[k], coef, out_row > 0 && out_row < g.n - 1, cin);
+            }
+            // cur = x_S row jj - S
+            const int xrow = jj - S;
+            if (owner && xrow >= r0 && xrow < r1) store_row<C>(xo + (ptrdiff_t)xrow * g.pitch + col, cur);
+            if (RESID) {
+                Row<C> r = rs.step(cur, fq[S + 1], inv_h2);  // r of row jj - S - 1
+                const int rrow = jj - S - 1;
+                double left = __shfl_up_sync(0xffffffffu, r.v[C - 1], 1);
+                if (rrow & 1) {
+                    // north row 2jc+1 of coarse row jc: finish the stencil
+                    const int jc = (rrow - 1) >> 1;
+                    const int ic = col >> 1;  // col is a multiple of C => exact
+                    double o[NP];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        double west = (q == 0) ? left : r.v[q == 0 ? 0 : 2 * q - 1];
+                        double edge = dadd(dadd(c_ew[q], r.v[2 * q]), s_mid[q]);
+                        double corner = dadd(dadd(s_cor[q], west), r.v[2 * q + 1]);
+                        double val = dadd(dadd(dmul(0.25, c_mid[q]), dmul(0.125, edge)), dmul(0.0625, corner));
+                        o[q] = (ic + q >= 1 && ic + q < nc - 1) ? val : 0.0;
+                        // this row is also the south row of coarse row jc+1
+                        s_mid[q] = r.v[2 * q];
+                        s_cor[q] = dadd(west, r.v[2 * q + 1]);
+                    }
+                    if (owner && jc >= 1 && jc < nc - 1 && 2 * jc >= r0 && 2 * jc < r1) {
+                        double *dst = cf + (ptrdiff_t)jc * pitch_c + ic;
+                        if (NP == 2)
+                            *reinterpret_cast<double2 *>(dst) = make_double2(o[0], o[NP - 1]);
+                        else
+                            *dst = o[0];
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        double west = (q == 0) ? left : r.v[q == 0 ? 0 : 2 * q - 1];
+                        c_mid[q] = r.v[2 * q];
+                        c_ew[q] = dadd(r.v[2 * q + 1], west);  // E + W (MultiGrid.hpp:200: idx+1 first, then idx-1)
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pass B.  x = S^nu2(xb + P e) ; NORM adds sum over the interior of (f - A x)^2 (one partial per warp).
+// PROLONG = false makes it a plain smoothing (+norm) pass.
+// ---------------------------------------------------------------------------------------------------
+template <int C>
+struct CoarseRow {
+    double v[C / 2 + 1];  // coarse columns cc .. cc + C/2
+};
+
+template <int C>
+__device__ __forceinline__ CoarseRow<C> load_coarse(const double *__restrict__ p)
+{
+    CoarseRow<C> r;
+    if (C == 4) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+
+template <int C, int PF, int MINB, int S, bool PROLONG, bool NORM>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
+    k_up(const double *__restrict__ xb, double *__restrict__ xo, const double *__restrict__ f,
+         const double *__restrict__ e, StripGeom g, int pitch_c, int lo, JacobiCoef coef, double inv_h2,
+         double *__restrict__ partials)
+{
+    static_assert(PF % 2 == 0, "rows are processed in (even, odd) pairs");
+    constexpr int NP = C / 2;
+    const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= g.n_strips * g.n_chunks) return;
+    int col, r0, r1;
+    bool owner, cin[C];
+    strip_setup<C>(g, wid, lane, col, r0, r1, owner, cin);
+
+    // r0 is even; start on an even row so that row parity is static inside the unrolled body
+    int j_start = r0 - S - (NORM ? 1 : 0);
+    j_start -= (j_start & 1);
+    const int j_end = r1 - 1 + S + (NORM ? 1 : 0);
+
+    SweepStage<C> st[S];
+    ResidualStage<C> rs;
+#pragma unroll
+    for (int k = 0; k < S; ++k) st[k].init();
+    rs.init();
+    Row<C> fq[S + 2];
+#pragma unroll
+    for (int d = 0; d < S + 2; ++d) fq[d] = zero_row<C>();
+    double acc = 0.0;
+
+    bool cprol[C];  // columns that receive a correction
+#pragma unroll
+    for (int k = 0; k < C; ++k) cprol[k] = (col + k >= lo) && (col + k <= g.n - 2);
+
+    Row<C> xbuf[PF], fbuf[PF];
+#pragma unroll
+    for (int d = 0; d < PF; ++d) {
+        xbuf[d] = load_row<C>(xb + (ptrdiff_t)(j_start + d) * g.pitch + col);
+        fbuf[d] = load_row<C>(f + (ptrdiff_t)(j_start + d) * g.pitch + col);
+    }
+    const int last_row = g.n + PADY - 1;
+
+    // coarse rows: ec = row jc, en = row jc+1, eb = prefetch of row jc+2 (raw, before the shuffle)
+    const int cc = col >> 1;
+    const int nc_last_row = ((g.n - 1) >> 1) + PADY;  // last coarse row in the allocation
+    CoarseRow<C> ec, en, eb;
+#pragma unroll
+    for (int q = 0; q <= NP; ++q) ec.v[q] = en.v[q] = eb.v[q] = 0.0;
+    if (PROLONG) {
+        const int jc0 = j_start >> 1;  // j_start even (possibly negative: arithmetic shift == floor)
+        ec = load_coarse<C>(e + (ptrdiff_t)jc0 * pitch_c + cc);
+        ec.v[NP] = __shfl_down_sync(0xffffffffu, ec.v[0], 1);
+        eb = load_coarse<C>(e + (ptrdiff_t)(jc0 + 1) * pitch_c + cc);
+    }
+
+    for (int j = j_start; j <= j_end; j += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int jj = j + u;  // u even: fine row 2jc, u odd: fine row 2jc+1
+            Row<C> cur = xbuf[u];
+#pragma unroll
+            for (int d = S + 1; d > 0; --d) fq[d] = fq[d - 1];
+            fq[0] = fbuf[u];
+            {
+                int nr = min(jj + PF, last_row);
+                xbuf[u] = load_row<C>(xb + (ptrdiff_t)nr * g.pitch + col);
+                fbuf[u] = load_row<C>(f + (ptrdiff_t)nr * g.pitch + col);
+            }
+            if (PROLONG) {
+                const bool rowp = (jj >= lo) && (jj <= g.n - 2);
+                double corr[C];
+                if ((u & 1) == 0) {
+                    // coarse row jc+1 arrives (loaded one pair ago); fetch jc+2 for the next pair
+                    en = eb;
+                    en.v[NP] = __shfl_down_sync(0xffffffffu, eb.v[0], 1);
+                    int nr = min((jj >> 1) + 2, nc_last_row);
+                    eb = load_coarse<C>(e + (ptrdiff_t)nr * pitch_c + cc);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        corr[2 * q] = ec.v[q];
+                        corr[2 * q + 1] = dmul(0.5, dadd(ec.v[q], ec.v[q + 1]));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        corr[2 * q] = dmul(0.5, dadd(ec.v[q], en.v[q]));
+                        corr[2 * q + 1] =
+                            dmul(0.25, dadd(dadd(dadd(ec.v[q], ec.v[q + 1]), en.v[q]), en.v[q + 1]));
+                    }
+                    ec = en;
+                }
+#pragma unroll
+                for (int k = 0; k < C; ++k)
+                    if (rowp && cprol[k]) cur.v[k] = dadd(cur.v[k], corr[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                const int out_row = jj - k - 1;
+                cur = st[k].step(cur, fq[k], coef, out_row > 0 && out_row < g.n - 1, cin);
+            }
+            const int xrow = jj - S;
+            if (owner && xrow >= r0 && xrow < r1) store_row<C>(xo + (ptrdiff_t)xrow * g.pitch + col, cur);
+            if (NORM) {
+                Row<C> r = rs.step(cur, fq[S + 1], inv_h2);
+                const int rrow = jj - S - 1;
+                if (owner && rrow >= r0 && rrow < r1 && rrow > 0 && rrow < g.n - 1) {
+#pragma unroll
+                    for (int k = 0; k < C; ++k)
+                        if (cin[k]) acc = dadd(acc, dmul(r.v[k], r.v[k]));
+                }
+            }
+        }
+    }
+    if (NORM) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc = dadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        if (lane == 0) partials[wid] = acc;
+    }
+}
+
+// ---- run-time variant table ---------------------------------------------------------------------
+struct VariantDesc {
+    int c, pf, minb;
+};
+constexpr int NUM_VARIANTS = 4;
+constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {{4, 2, 3}, {4, 2, 2}, {2, 2, 5}, {2, 4, 4}};
+int g_variant = 0;
+
+int g_num_sms = 0;
+int num_sms()
+{
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+StripGeom make_geom(int n, int pitch, int stages, const VariantDesc &v)
+{
+    StripGeom g;
+    g.n = n;
+    g.pitch = pitch;
+    g.halo = halo_for(stages);
+    g.stride = 32 * v.c - 2 * g.halo;
+    g.n_strips = (n + g.stride - 1) / g.stride;
+    // one resident wave: every warp of the grid is on an SM for the whole pass (no tail wave)
+    int resident = num_sms() * v.minb * WARPS_PER_CTA;
+    int chunks = resident / g.n_strips;
+    if (chunks < 1) chunks = 1;
+    int rows = (n + chunks - 1) / chunks;
+    rows += rows & 1;
+    if (rows < 16) rows = 16;
+    g.chunk_rows = rows;
+    g.n_chunks = (n + rows - 1) / rows;
+    return g;
+}
+
+inline int grid_for(const StripGeom &g)
+{
+    int warps = g.n_strips * g.n_chunks;
+    return (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+}
+
+template <int C, int PF, int MINB, int S>
+void down_launch(const FusedLevel &lv, double *cf, int pitch_c, double omega, bool x_is_zero, bool resid,
+                 cudaStream_t st)
+{
+    StripGeom g = make_geom(lv.n, lv.pitch, S + (resid ? 2 : 0), VariantDesc{C, PF, MINB});
+    JacobiCoef c = jacobi_coef(lv.h, omega);
+    double inv = 1.0 / (lv.h * lv.h);
+    int nc = (lv.n - 1) / 2 + 1;
+    dim3 grid(grid_for(g)), block(32 * WARPS_PER_CTA);
+    if (resid) {
+        if (x_is_zero)
+            k_down<C, PF, MINB, S, true, true><<<grid, block, 0, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv);
+        else
+            k_down<C, PF, MINB, S, false, true><<<grid, block, 0, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv);
+    } else {
+        k_down<C, PF, MINB, S, false, false><<<grid, block, 0, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv);
+    }
+    count_launch();
+}
+
+template <int C, int PF, int MINB, int S>
+void up_launch(const FusedLevel &lv, const double *e, int pitch_c, double omega, int lo, bool norm,
+               double *d_partials, int *n_partials, cudaStream_t st)
+{
+    StripGeom g = make_geom(lv.n, lv.pitch, S + (norm ? 2 : 1), VariantDesc{C, PF, MINB});
+    JacobiCoef c = jacobi_coef(lv.h, omega);
+    double inv = 1.0 / (lv.h * lv.h);
+    dim3 grid(grid_for(g)), block(32 * WARPS_PER_CTA);
+    if (e != nullptr) {
+        if (norm)
+            k_up<C, PF, MINB, S, true, true><<<grid, block, 0, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+        else
+            k_up<C, PF, MINB, S, true, false><<<grid, block, 0, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+    } else {
+        if (norm)
+            k_up<C, PF, MINB, S, false, true><<<grid, block, 0, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+        else
+            k_up<C, PF, MINB, S, false, false><<<grid, block, 0, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+    }
+    count_launch();
+    if (n_partials) *n_partials = norm ? g.n_strips * g.n_chunks : 0;
+}
+
+}  // namespace
+
+bool fused_supported(int nu) { return nu >= 1 && nu <= 4; }
+
+int fused_num_variants() { return NUM_VARIANTS; }
+void fused_set_variant(int v) { g_variant = (v >= 0 && v < NUM_VARIANTS) ? v : 0; }
+int fused_get_variant() { return g_variant; }
+
+int fused_max_partials(int n)
+{
+    int best = 0;
+    for (int v = 0; v < NUM_VARIANTS; ++v) {
+        StripGeom g = make_geom(n, level_pitch(n), 8, VARIANTS[v]);
+        int c = g.n_strips * g.n_chunks;
+        g = make_geom(n, level_pitch(n), 4, VARIANTS[v]);
+        if (g.n_strips * g.n_chunks > c) c = g.n_strips * g.n_chunks;
+        if (c > best) best = c;
+    }
+    return best + 64;
+}
+
+// The tuning variants exist for the headline V(2,2) configuration only; other sweep counts use variant 0.
+#define PMG_DISPATCH_S2(FN, ...)                                          \
+    switch (g_variant) {                                                  \
+        case 1: FN<4, 2, 2, 2>(__VA_ARGS__); break;                       \
+        case 2: FN<2, 2, 5, 2>(__VA_ARGS__); break;                       \
+        case 3: FN<2, 4, 4, 2>(__VA_ARGS__); break;                       \
+        default: FN<4, 2, 3, 2>(__VA_ARGS__); break;                      \
+    }
+
+void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int nu1, double omega,
+                       bool x_is_zero, cudaStream_t st)
+{
+    bool resid = coarse_f != nullptr;
+    switch (nu1) {
+        case 1: down_launch<4, 2, 3, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 2: PMG_DISPATCH_S2(down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 3: down_launch<4, 2, 3, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 4: down_launch<4, 2, 3, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        default: break;
+    }
+}
+
+void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, int nu2, double omega,
+                     int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st)
+{
+    bool norm = d_partials != nullptr;
+    int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
+    switch (nu2) {
+        case 1: up_launch<4, 2, 3, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 2: PMG_DISPATCH_S2(up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 3: up_launch<4, 2, 3, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 4: up_launch<4, 2, 3, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        default: break;
+    }
+}
+
+}  // namespace pmg

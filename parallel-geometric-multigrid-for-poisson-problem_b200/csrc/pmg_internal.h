@@ -1,0 +1,126 @@
+// pmg_internal.h -- declarations shared by the CUDA translation units of libpmg.so.
+// Nothing here is part of the public ABI (that is include/pmg.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "pmg.h"
+
+namespace pmg {
+
+// ---- HBM layout of one level -------------------------------------------------
+// A level with n x n logical points (ring included) is stored as (n + 2*PADY) rows of `pitch`
+// doubles.  Logical (row y, col x) lives at base[(y + PADY) * pitch + PADX + x].  PADX doubles on the
+// left make logical column -PADX 128-byte aligned (base comes from cudaMalloc, pitch % 16 == 0), which
+// is what the streaming kernels' 32-byte vector accesses need; the right padding lets every warp strip
+// load its full 128 columns without a bounds test; PADY zero rows above and below do the same for the
+// row pipeline warm-up/drain.  Padding is zero-filled once and never becomes non-zero.
+constexpr int PADX = 16;
+constexpr int PADY = 8;
+
+inline int level_pitch(int n) { return ((PADX + n + 144) + 15) / 16 * 16; }
+inline size_t level_elems(int n) { return (size_t)level_pitch(n) * (size_t)(n + 2 * PADY); }
+inline size_t level_origin(int n) { return (size_t)PADY * level_pitch(n) + PADX; }
+
+// un-fused arithmetic in the reference's evaluation order (no FMA contraction, whatever -fmad says)
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+
+struct JacobiCoef {
+    double h2;      // h*h
+    double omega;   // w
+    double om1;     // 1.0 - w
+    int weighted;   // w != 1.0
+};
+
+// Smoother.hpp:66-68 + the omega form of SURVEY.md 8c:
+//   jac = 0.25*((h*h*f) + W + E + S + N);  out = (w == 1) ? jac : (1-w)*x + w*jac
+// `s` = up (row y-1, "idx - width"), `n` = down (row y+1, "idx + width")
+__device__ __forceinline__ double jacobi_point(const JacobiCoef &c, double f, double xc, double xw,
+                                               double xe, double xs, double xn)
+{
+    double acc = dadd(dadd(dadd(dadd(dmul(c.h2, f), xw), xe), xs), xn);
+    double jac = dmul(0.25, acc);
+    return c.weighted ? dadd(dmul(c.om1, xc), dmul(c.omega, jac)) : jac;
+}
+
+// DynamicGridUtils.hpp:66:  f - (1.0/(h*h)) * (4*x - W - E - S - N)
+__device__ __forceinline__ double residual_point(double inv_h2, double f, double xc, double xw,
+                                                 double xe, double xs, double xn)
+{
+    double t = dsub(dsub(dsub(dsub(dmul(4.0, xc), xw), xe), xs), xn);
+    return dsub(f, dmul(inv_h2, t));
+}
+
+// MultiGrid.hpp:199-202:  0.25*c + 0.125*(E + W + N + S) + 0.0625*(SW + SE + NW + NE)
+// (s* = row 2jc-1, n* = row 2jc+1; the reference adds "+1, -1, +Nf, -Nf" then "-Nf-1, -Nf+1, +Nf-1, +Nf+1")
+__device__ __forceinline__ double restrict_point(double c, double e, double w, double n, double s,
+                                                 double sw, double se, double nw, double ne)
+{
+    double edge = dadd(dadd(dadd(e, w), n), s);
+    double corner = dadd(dadd(dadd(sw, se), nw), ne);
+    return dadd(dadd(dmul(0.25, c), dmul(0.125, edge)), dmul(0.0625, corner));
+}
+
+// ---- launch bookkeeping ---------------------------------------------------------------------------
+void count_launch(int n = 1);
+unsigned long long launches_so_far();
+JacobiCoef jacobi_coef(double h, double omega);
+
+// ---- operator-granular kernels (kernels_basic.cu); all pointers address logical (0,0) ------------
+// out = one weighted-Jacobi sweep of in (interior); ring and nothing else copied from in
+void launch_jacobi_sweep(double *out, const double *in, const double *f, int nx, int ny, int pitch_x,
+                         int pitch_f, double h, double omega, cudaStream_t st);
+// whole `sweeps` on a level that fits one CTA's shared memory (nx*ny <= SMALL_MAX_POINTS); in place
+constexpr int SMALL_MAX_POINTS = 33 * 33;
+// x_is_zero: start from x == 0 without reading x (first visit of a coarse level)
+void launch_jacobi_small(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h,
+                         double omega, int sweeps, bool x_is_zero, cudaStream_t st);
+void launch_residual(double *r, const double *x, const double *f, int nx, int ny, int pitch_r,
+                     int pitch_x, int pitch_f, double h, cudaStream_t st);
+// sum over the interior of (f - A x)^2 -> *d_out (device double); `d_partials` >= reduce_partials() doubles
+int reduce_partials();
+void launch_residual_norm2(const double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f,
+                           double h, double *d_partials, double *d_out, cudaStream_t st);
+void launch_norm2(const double *v, size_t l, double *d_partials, double *d_out, cudaStream_t st);
+// fixed-order sum of `count` partials -> *d_out
+void launch_final_sum(const double *d_partials, int count, double *d_out, cudaStream_t st);
+void launch_restrict(const double *fine, double *coarse, int nf, int nc, int pitch_f, int pitch_c,
+                     cudaStream_t st);
+void launch_prolong_add(const double *coarse, double *fine, int nc, int nf, int pitch_c, int pitch_f,
+                        int mode, cudaStream_t st);
+// dst(y,x) = src(y,x) for a ny x nx window, arbitrary pitches (layout conversion at the ABI)
+void launch_copy2d(double *dst, int pitch_d, const double *src, int pitch_s, int nx, int ny,
+                   cudaStream_t st);
+void launch_fill2d(double *dst, int pitch_d, int nx, int ny, double v, cudaStream_t st);
+// f(y,x) = (factor * sx[x]) * sy[y]   (DynamicGridUtils.hpp:113-122 with 1-D sine tables)
+void launch_rhs_separable(double *f, int pitch, int nx, int ny, double factor, const double *sx,
+                          const double *sy, cudaStream_t st);
+
+// ---- fused streaming kernels (kernels_fused.cu) ---------------------------------------------------
+struct FusedLevel {
+    double *x;    // logical (0,0) of the level's current iterate
+    double *xb;   // ping-pong partner
+    const double *f;
+    int n, pitch;
+    double h;
+};
+// Pass A (down): xb = S^nu1(x);  coarse_f(interior) = R(f - A xb).  x_is_zero: the iterate is known to
+// be identically zero on entry (coarse levels of a V-cycle) so x is not read.
+bool fused_supported(int nu);
+void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int nu1, double omega,
+                       bool x_is_zero, cudaStream_t st);
+// Pass B (up): x = S^nu2(xb + P coarse_x); optionally sum (f - A x)^2 over the interior into partials
+// (count returned through *n_partials; reduce with launch_final_sum)
+void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, int nu2, double omega,
+                     int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st);
+int fused_max_partials(int n);
+// tuning: which (columns per lane, prefetch depth, CTAs per SM) instantiation the nu == 2 passes use
+int fused_num_variants();
+void fused_set_variant(int v);
+int fused_get_variant();
+
+}  // namespace pmg

@@ -1,0 +1,835 @@
+// solver.cu -- host side of libpmg.so: the level hierarchy in HBM, the V/W/F cycle drivers and the C ABI
+// of include/pmg.h.  It mirrors the control flow of MultigridSolver (2_part_MG/MultiGrid.hpp:57-183) and
+// of the runner's outer loop (2_part_MG/MultiGridTestRunner.hpp:190-212), but every buffer is allocated
+// once at pmg_create (the reference allocates three arrays per level per call, MultiGrid.hpp:70-82, and
+// its GPU twin leaks them, Parallel_Mg.cu:38-54) and no stage ever runs on the CPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pmg_internal.h"
+
+namespace pmg {
+
+thread_local std::string g_last_error;
+
+static pmg_status fail(pmg_status s, const std::string &msg)
+{
+    g_last_error = msg;
+    return s;
+}
+
+#define PMG_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(PMG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" +  \
+                                          __FILE__ + ":" + std::to_string(__LINE__) + ")");         \
+    } while (0)
+
+static bool is_pow2_plus_1(int n) { return n >= 3 && ((n - 1) & (n - 2)) == 0; }
+
+struct Level {
+    int n = 0, pitch = 0;
+    double h = 0.0;
+    size_t elems = 0;
+    double *base_x = nullptr, *base_xb = nullptr, *base_f = nullptr, *base_r = nullptr;
+    double *x = nullptr, *xb = nullptr, *f = nullptr, *r = nullptr;  // logical (0,0)
+    double *d_sin = nullptr;  // sin(pi * i * h), i < n  (F-cycle analytic RHS; lazily built)
+};
+
+}  // namespace pmg
+
+using namespace pmg;
+
+struct pmg_solver {
+    pmg_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<Level> lv;
+    double *d_partials = nullptr;
+    int partials_cap = 0;
+    double *d_scalar = nullptr;  // device double (sum of squares)
+    double *h_scalar = nullptr;  // pinned host mirror
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    // F-cycle: level-0 analytic RHS lives in its own array so the caller's f survives
+    double *base_f_fmg0 = nullptr, *f_fmg0 = nullptr;
+    bool fmg_ready = false;
+    // CUDA graphs of one fused cycle, keyed by [kind V/W][with norm]
+    cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int graph_kernels[2][2] = {{0, 0}, {0, 0}};  // kernel nodes per replay (launch bookkeeping)
+    bool fused = false;
+};
+
+namespace pmg {
+
+static void drop_graphs(pmg_solver *s)
+{
+    for (auto &row : s->graph)
+        for (auto &g : row)
+            if (g) {
+                cudaGraphExecDestroy(g);
+                g = nullptr;
+            }
+}
+
+static FusedLevel fused_view(const Level &L)
+{
+    FusedLevel v;
+    v.x = L.x;
+    v.xb = L.xb;
+    v.f = L.f;
+    v.n = L.n;
+    v.pitch = L.pitch;
+    v.h = L.h;
+    return v;
+}
+
+static pmg_status alloc_zero(double **p, size_t elems)
+{
+    if (cudaMalloc((void **)p, elems * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PMG_ERR_ALLOC, "cudaMalloc of " + std::to_string(elems * sizeof(double)) + " bytes failed");
+    }
+    PMG_CUDA(cudaMemset(*p, 0, elems * sizeof(double)));
+    return PMG_OK;
+}
+
+// ---- smoothing on one level (Smoother::smooth, Smoother.hpp:38-116) -----------------------------------
+// Operator-granular: ping-pong sweeps; with smoother_eps > 0 the reference's per-sweep absolute-norm exit.
+static pmg_status smooth_operator(pmg_solver *s, int l, int sweeps, bool x_is_zero)
+{
+    Level &L = s->lv[l];
+    const pmg_config &c = s->cfg;
+    if (x_is_zero && !(c.smoother_eps <= 0.0 && L.n * L.n <= SMALL_MAX_POINTS))
+        launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);
+    if (c.smoother_eps > 0.0) {
+        for (int it = 0; it < sweeps; ++it) {
+            launch_jacobi_sweep(L.xb, L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, s->stream);
+            std::swap(L.x, L.xb);
+            std::swap(L.base_x, L.base_xb);
+            launch_residual_norm2(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
+            PMG_CUDA(cudaMemcpyAsync(s->h_scalar, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+            PMG_CUDA(cudaStreamSynchronize(s->stream));
+            if (std::sqrt(*s->h_scalar) < c.smoother_eps) break;  // Smoother.hpp:84-88
+        }
+        return PMG_OK;
+    }
+    if (L.n * L.n <= SMALL_MAX_POINTS) {
+        launch_jacobi_small(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, sweeps, x_is_zero, s->stream);
+        return PMG_OK;
+    }
+    for (int it = 0; it < sweeps; ++it) {
+        launch_jacobi_sweep(L.xb, L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, s->stream);
+        std::swap(L.x, L.xb);
+        std::swap(L.base_x, L.base_xb);
+    }
+    return PMG_OK;
+}
+
+// MultigridSolver::v_cycle / w_cycle (MultiGrid.hpp:57-94 / 96-136), one kernel per reference operator
+static pmg_status cycle_operator(pmg_solver *s, int l, bool w_form, bool x_is_zero)
+{
+    const pmg_config &c = s->cfg;
+    Level &L = s->lv[l];
+    if (L.n <= c.n_coarse || l + 1 == (int)s->lv.size())
+        return smooth_operator(s, l, c.coarse_sweeps, x_is_zero);  // :59-63
+    pmg_status rc = smooth_operator(s, l, c.nu1, x_is_zero);       // :66
+    if (rc != PMG_OK) return rc;
+    Level &K = s->lv[l + 1];
+    launch_residual(L.r, L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.pitch, L.h, s->stream);  // :69-71
+    launch_restrict(L.r, K.f, L.n, K.n, L.pitch, K.pitch, s->stream);                     // :74-78
+    int reps = w_form ? c.gamma : 1;
+    for (int k = 0; k < reps; ++k) {  // :81-83 / :121-125 (e_coarse = 0 before the first visit)
+        rc = cycle_operator(s, l + 1, w_form, k == 0);
+        if (rc != PMG_OK) return rc;
+    }
+    launch_prolong_add(K.x, L.x, K.n, L.n, K.pitch, L.pitch, c.prolong_mode, s->stream);  // :86
+    return smooth_operator(s, l, c.nu2, false);                                          // :89
+}
+
+// The same cycle on the fused engine: two streaming passes per level visit.
+static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero, bool want_norm, int *n_partials)
+{
+    const pmg_config &c = s->cfg;
+    Level &L = s->lv[l];
+    if (L.n <= c.n_coarse || l + 1 == (int)s->lv.size()) return smooth_operator(s, l, c.coarse_sweeps, x_is_zero);
+    Level &K = s->lv[l + 1];
+    launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream);
+    int reps = w_form ? c.gamma : 1;
+    for (int k = 0; k < reps; ++k) {
+        pmg_status rc = cycle_fused(s, l + 1, w_form, k == 0, false, nullptr);
+        if (rc != PMG_OK) return rc;
+    }
+    launch_fused_up(fused_view(L), K.x, K.pitch, c.nu2, c.omega, c.prolong_mode,
+                    want_norm ? s->d_partials : nullptr, n_partials, s->stream);
+    return PMG_OK;
+}
+
+static pmg_status residual_norm2_async(pmg_solver *s)
+{
+    Level &L = s->lv[0];
+    launch_residual_norm2(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
+    return PMG_OK;
+}
+
+static pmg_status read_scalar(pmg_solver *s, double *out)
+{
+    PMG_CUDA(cudaMemcpyAsync(s->h_scalar, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    PMG_CUDA(cudaStreamSynchronize(s->stream));
+    PMG_CUDA(cudaGetLastError());
+    *out = *s->h_scalar;
+    return PMG_OK;
+}
+
+// ---- F-cycle -------------------------------------------------------------------------------------------
+static pmg_status ensure_fmg(pmg_solver *s)
+{
+    if (s->fmg_ready) return PMG_OK;
+    for (Level &L : s->lv) {
+        // DynamicGridUtils.hpp:120-122 with globals a = p = q = 1: sin(p * M_PI * x / a), x = i*h
+        std::vector<double> tab(L.n);
+        const double a = 1.0, p = 1.0;
+        for (int i = 0; i < L.n; ++i) {
+            double x = i * L.h;
+            tab[i] = std::sin(p * M_PI * x / a);
+        }
+        PMG_CUDA(cudaMalloc((void **)&L.d_sin, L.n * sizeof(double)));
+        PMG_CUDA(cudaMemcpy(L.d_sin, tab.data(), L.n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    pmg_status rc = alloc_zero(&s->base_f_fmg0, s->lv[0].elems);
+    if (rc != PMG_OK) return rc;
+    s->f_fmg0 = s->base_f_fmg0 + level_origin(s->lv[0].n);
+    s->fmg_ready = true;
+    return PMG_OK;
+}
+
+static void analytic_rhs(pmg_solver *s, const Level &L, double *f)
+{
+    const double a = 1.0, p = 1.0, q = 1.0;
+    double factor = (M_PI * M_PI / (a * a)) * (p * p + q * q);  // DynamicGridUtils.hpp:113
+    launch_rhs_separable(f, L.pitch, L.n, L.n, factor, L.d_sin, L.d_sin, s->stream);
+}
+
+// The runner's F-cycle wrapper (MultiGridTestRunner.hpp:192-205) + MultigridSolver::f_cycle
+// (MultiGrid.hpp:138-183) + compute_coarsest_grid (:28-55).
+static pmg_status cycle_f(pmg_solver *s)
+{
+    pmg_status rc = ensure_fmg(s);
+    if (rc != PMG_OK) return rc;
+    const pmg_config &c = s->cfg;
+    const int nl = (int)s->lv.size();
+    int lc = nl - 1;  // index of the coarsest level (n == n_coarse, or the 3x3 grid)
+    if (lc == 0) return PMG_OK;  // N <= N_coarse: f_cycle's while loop never runs (MultiGrid.hpp:150)
+    drop_graphs(s);              // the pass below may swap x/xb roles on levels >= 1
+    // (1) phi restricted down to the coarsest grid; the scratch of level l is its xb array (ring == 0)
+    for (int l = 0; l < lc; ++l) {
+        const Level &L = s->lv[l];
+        Level &K = s->lv[l + 1];
+        launch_restrict(l == 0 ? L.x : L.xb, K.xb, L.n, K.n, L.pitch, K.pitch, s->stream);
+    }
+    if (lc > 0) launch_copy2d(s->lv[lc].x, s->lv[lc].pitch, s->lv[lc].xb, s->lv[lc].pitch, s->lv[lc].n, s->lv[lc].n, s->stream);
+    // (2) nested iteration upwards with the ANALYTIC right-hand side on every level (MultiGrid.hpp:162)
+    double *user_f = s->lv[0].f;
+    analytic_rhs(s, s->lv[lc], s->lv[lc].f);  // MultiGridTestRunner.hpp:142
+    for (int l = lc - 1; l >= 0; --l) {
+        Level &K = s->lv[l + 1];
+        Level &L = s->lv[l];
+        // smoother->smooth(phi_current, f_current, N, N, h, 3)  (:153)
+        if (s->fused && fused_supported(c.fmg_sweeps) && K.n * K.n > SMALL_MAX_POINTS) {
+            launch_fused_down(fused_view(K), nullptr, 0, c.fmg_sweeps, c.omega, false, s->stream);
+            std::swap(K.x, K.xb);
+            std::swap(K.base_x, K.base_xb);
+        } else {
+            rc = smooth_operator(s, l + 1, c.fmg_sweeps, false);
+            if (rc != PMG_OK) break;
+        }
+        double *f_l = (l == 0) ? s->f_fmg0 : L.f;
+        analytic_rhs(s, L, f_l);                                                             // :162
+        launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);                               // :161
+        launch_prolong_add(K.x, L.x, K.n, L.n, K.pitch, L.pitch, c.prolong_mode, s->stream);  // :164
+        if (l == 0) L.f = s->f_fmg0;
+        rc = s->fused ? cycle_fused(s, l, false, false, false, nullptr) : cycle_operator(s, l, false, false);  // :167
+        if (l == 0) L.f = user_f;
+        if (rc != PMG_OK) break;
+    }
+    s->lv[0].f = user_f;
+    return rc;
+}
+
+static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
+{
+    pmg_status rc;
+    if (kind == PMG_CYCLE_F) {
+        rc = cycle_f(s);
+        if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
+        return rc;
+    }
+    if (kind != PMG_CYCLE_V && kind != PMG_CYCLE_W) return fail(PMG_ERR_INVALID, "unknown cycle kind");
+    bool w = (kind == PMG_CYCLE_W);
+    if (!s->fused) {
+        rc = cycle_operator(s, 0, w, false);
+        if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
+        return rc;
+    }
+    if ((int)s->lv.size() == 1 || s->lv[0].n <= s->cfg.n_coarse) {
+        rc = cycle_fused(s, 0, w, false, false, nullptr);
+        if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
+        return rc;
+    }
+    // pointer roles are stable across a fused cycle unless the coarsest solve ping-pongs an odd count
+    const Level &Lc = s->lv.back();
+    bool graph_ok = s->cfg.use_graph && (Lc.n * Lc.n <= SMALL_MAX_POINTS || (s->cfg.coarse_sweeps % 2) == 0);
+    cudaGraphExec_t &ge = s->graph[w ? 1 : 0][want_norm ? 1 : 0];
+    int &gk = s->graph_kernels[w ? 1 : 0][want_norm ? 1 : 0];
+    if (graph_ok && ge != nullptr) {
+        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+        count_launch(gk);
+        return PMG_OK;
+    }
+    unsigned long long before = launches_so_far();
+    if (graph_ok) PMG_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    int n_partials = 0;
+    rc = cycle_fused(s, 0, w, false, want_norm, &n_partials);
+    if (rc == PMG_OK && want_norm) launch_final_sum(s->d_partials, n_partials, s->d_scalar, s->stream);
+    if (graph_ok) {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        if (rc != PMG_OK) {
+            cudaGraphDestroy(g);
+            return rc;
+        }
+        // the launches counted during capture are the ones the first replay below executes
+        gk = (int)(launches_so_far() - before);
+        PMG_CUDA(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+    }
+    return rc;
+}
+
+}  // namespace pmg
+
+// =========================================================================================================
+//                                                C ABI
+// =========================================================================================================
+extern "C" {
+
+const char *pmg_version(void) { return "pmg-b200 0.1 (sm_100a)"; }
+
+const char *pmg_last_error(void) { return g_last_error.c_str(); }
+
+const char *pmg_status_string(pmg_status s)
+{
+    switch (s) {
+        case PMG_OK: return "ok";
+        case PMG_ERR_INVALID: return "invalid argument";
+        case PMG_ERR_CUDA: return "CUDA error";
+        case PMG_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+        case PMG_ERR_ALLOC: return "allocation failed";
+        case PMG_ERR_COMM: return "communication error";
+        case PMG_ERR_UNSUPPORTED: return "unsupported";
+    }
+    return "unknown";
+}
+
+void pmg_config_default(pmg_config *cfg, int n)
+{
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->n = n;
+    cfg->nu1 = 2;   // reference v1 = 1 -> 2 sweeps (MultiGrid.hpp:15, Smoother.hpp:59)
+    cfg->nu2 = 2;
+    cfg->omega = 1.0;
+    cfg->gamma = 3;  // 2_part_MG/main.cpp:15 alpha = 3
+    cfg->n_coarse = 5;
+    cfg->coarse_sweeps = 11;
+    cfg->fmg_sweeps = 4;
+    cfg->prolong_mode = PMG_PROLONG_REFERENCE;
+    cfg->engine = PMG_ENGINE_FUSED;
+    cfg->smoother_eps = 0.0;
+    cfg->device = -1;
+    cfg->use_graph = 1;
+    cfg->rank = 0;
+    cfg->n_ranks = 1;
+    cfg->agglomerate_below = 2049;
+}
+
+unsigned long long pmg_kernel_launches(void) { return launches_so_far(); }
+
+int pmg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
+{
+    if (!cfg || !out) return fail(PMG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (!is_pow2_plus_1(cfg->n)) return fail(PMG_ERR_INVALID, "n must be 2^k + 1 (k >= 1)");
+    if (cfg->n > 46340) return fail(PMG_ERR_INVALID, "n too large");
+    if (cfg->nu1 < 0 || cfg->nu2 < 0 || cfg->coarse_sweeps < 0 || cfg->fmg_sweeps < 0 || cfg->gamma < 1)
+        return fail(PMG_ERR_INVALID, "negative sweep count or gamma < 1");
+    if (!is_pow2_plus_1(cfg->n_coarse)) return fail(PMG_ERR_INVALID, "n_coarse must be 2^k + 1");
+    if (!(cfg->omega > 0.0)) return fail(PMG_ERR_INVALID, "omega must be positive");
+    if (cfg->n_ranks > 1) return fail(PMG_ERR_UNSUPPORTED, "multi-GPU solver handles are created with pmg_dist_create");
+    int ndev = pmg_device_count();
+    if (ndev <= 0) return fail(PMG_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    int dev = cfg->device;
+    if (dev < 0) PMG_CUDA(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(PMG_ERR_INVALID, "device ordinal out of range");
+    PMG_CUDA(cudaSetDevice(dev));
+    int major = 0;
+    PMG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10)
+        return fail(PMG_ERR_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+
+    pmg_solver *s = new (std::nothrow) pmg_solver();
+    if (!s) return fail(PMG_ERR_ALLOC, "host allocation failed");
+    s->cfg = *cfg;
+    s->device = dev;
+    s->fused = (cfg->engine == PMG_ENGINE_FUSED) && fused_supported(cfg->nu1) && fused_supported(cfg->nu2) &&
+               !(cfg->smoother_eps > 0.0);
+    pmg_status rc = PMG_OK;
+    auto bail = [&](pmg_status st) {
+        pmg_destroy(s);
+        return st;
+    };
+    (void)fused_max_partials(3);  // warms the cached SM count outside any stream capture
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(PMG_ERR_CUDA, "cudaStreamCreate failed"));
+    cudaEventCreate(&s->ev0);
+    cudaEventCreate(&s->ev1);
+    // level chain N -> (N-1)/2+1 -> ... -> n_coarse (MultiGrid.hpp:74)
+    for (int n = cfg->n;; n = (n - 1) / 2 + 1) {
+        Level L;
+        L.n = n;
+        L.pitch = level_pitch(n);
+        L.h = 1.0 / (n - 1);  // MultiGridTestRunner.hpp:131 with a = 1; coarse levels: 2h (MultiGrid.hpp:83)
+        L.elems = level_elems(n);
+        s->lv.push_back(L);
+        if (n <= cfg->n_coarse || n <= 3) break;
+    }
+    for (size_t l = 0; l < s->lv.size(); ++l) {
+        Level &L = s->lv[l];
+        if ((rc = alloc_zero(&L.base_x, L.elems)) != PMG_OK) return bail(rc);
+        if ((rc = alloc_zero(&L.base_xb, L.elems)) != PMG_OK) return bail(rc);
+        if ((rc = alloc_zero(&L.base_f, L.elems)) != PMG_OK) return bail(rc);
+        size_t o = level_origin(L.n);
+        L.x = L.base_x + o;
+        L.xb = L.base_xb + o;
+        L.f = L.base_f + o;
+        if (!s->fused) {
+            if ((rc = alloc_zero(&L.base_r, L.elems)) != PMG_OK) return bail(rc);
+            L.r = L.base_r + o;
+        }
+    }
+    s->partials_cap = std::max(reduce_partials(), fused_max_partials(cfg->n));
+    if ((rc = alloc_zero(&s->d_partials, (size_t)s->partials_cap)) != PMG_OK) return bail(rc);
+    if ((rc = alloc_zero(&s->d_scalar, 2)) != PMG_OK) return bail(rc);
+    if (cudaMallocHost((void **)&s->h_scalar, 2 * sizeof(double)) != cudaSuccess)
+        return bail(fail(PMG_ERR_ALLOC, "cudaMallocHost failed"));
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(PMG_ERR_CUDA, "device synchronize failed"));
+    *out = s;
+    return PMG_OK;
+}
+
+void pmg_destroy(pmg_solver *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    drop_graphs(s);
+    for (Level &L : s->lv) {
+        cudaFree(L.base_x);
+        cudaFree(L.base_xb);
+        cudaFree(L.base_f);
+        cudaFree(L.base_r);
+        cudaFree(L.d_sin);
+    }
+    cudaFree(s->base_f_fmg0);
+    cudaFree(s->d_partials);
+    cudaFree(s->d_scalar);
+    if (s->h_scalar) cudaFreeHost(s->h_scalar);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static pmg_status copy_in(pmg_solver *s, double *dst_logical, const double *src, pmg_mem where)
+{
+    if (!s || !src) return fail(PMG_ERR_INVALID, "null argument");
+    const Level &L = s->lv[0];
+    PMG_CUDA(cudaSetDevice(s->device));
+    PMG_CUDA(cudaMemcpy2DAsync(dst_logical, (size_t)L.pitch * sizeof(double), src, (size_t)L.n * sizeof(double),
+                               (size_t)L.n * sizeof(double), (size_t)L.n,
+                               where == PMG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s->stream));
+    PMG_CUDA(cudaStreamSynchronize(s->stream));
+    return PMG_OK;
+}
+
+pmg_status pmg_set_rhs(pmg_solver *s, const double *f, pmg_mem where)
+{
+    return copy_in(s, s ? s->lv[0].f : nullptr, f, where);
+}
+
+pmg_status pmg_set_guess(pmg_solver *s, const double *phi, pmg_mem where)
+{
+    return copy_in(s, s ? s->lv[0].x : nullptr, phi, where);
+}
+
+pmg_status pmg_get_solution(pmg_solver *s, double *phi, pmg_mem where)
+{
+    if (!s || !phi) return fail(PMG_ERR_INVALID, "null argument");
+    const Level &L = s->lv[0];
+    PMG_CUDA(cudaSetDevice(s->device));
+    PMG_CUDA(cudaMemcpy2DAsync(phi, (size_t)L.n * sizeof(double), L.x, (size_t)L.pitch * sizeof(double),
+                               (size_t)L.n * sizeof(double), (size_t)L.n,
+                               where == PMG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s->stream));
+    PMG_CUDA(cudaStreamSynchronize(s->stream));
+    return PMG_OK;
+}
+
+pmg_status pmg_zero_guess(pmg_solver *s)
+{
+    if (!s) return fail(PMG_ERR_INVALID, "null argument");
+    PMG_CUDA(cudaSetDevice(s->device));
+    PMG_CUDA(cudaMemsetAsync(s->lv[0].base_x, 0, s->lv[0].elems * sizeof(double), s->stream));
+    PMG_CUDA(cudaStreamSynchronize(s->stream));
+    return PMG_OK;
+}
+
+pmg_status pmg_set_rhs_sine(pmg_solver *s)
+{
+    if (!s) return fail(PMG_ERR_INVALID, "null argument");
+    PMG_CUDA(cudaSetDevice(s->device));
+    pmg_status rc = ensure_fmg(s);
+    if (rc != PMG_OK) return rc;
+    analytic_rhs(s, s->lv[0], s->lv[0].f);
+    PMG_CUDA(cudaStreamSynchronize(s->stream));
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+pmg_status pmg_residual_norm(pmg_solver *s, double *norm_out)
+{
+    if (!s || !norm_out) return fail(PMG_ERR_INVALID, "null argument");
+    PMG_CUDA(cudaSetDevice(s->device));
+    residual_norm2_async(s);
+    double v = 0.0;
+    pmg_status rc = read_scalar(s, &v);
+    if (rc != PMG_OK) return rc;
+    *norm_out = std::sqrt(v);
+    return PMG_OK;
+}
+
+pmg_status pmg_cycle(pmg_solver *s, pmg_cycle_kind kind, double *res_norm_out)
+{
+    if (!s) return fail(PMG_ERR_INVALID, "null argument");
+    PMG_CUDA(cudaSetDevice(s->device));
+    PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    pmg_status rc = run_cycle(s, kind, res_norm_out != nullptr);
+    if (rc != PMG_OK) return rc;
+    PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    if (res_norm_out) {
+        double v = 0.0;
+        rc = read_scalar(s, &v);
+        if (rc != PMG_OK) return rc;
+        *res_norm_out = std::sqrt(v);
+    } else {
+        PMG_CUDA(cudaStreamSynchronize(s->stream));
+        PMG_CUDA(cudaGetLastError());
+    }
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    return PMG_OK;
+}
+
+pmg_status pmg_solve(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max_cycles, double *res_history,
+                     int *n_cycles_out)
+{
+    if (!s || max_cycles < 0) return fail(PMG_ERR_INVALID, "bad argument");
+    PMG_CUDA(cudaSetDevice(s->device));
+    PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    residual_norm2_async(s);
+    double v = 0.0;
+    pmg_status rc = read_scalar(s, &v);
+    if (rc != PMG_OK) return rc;
+    double r0 = std::sqrt(v);
+    if (res_history) res_history[0] = r0;
+    int k = 0;
+    while (k < max_cycles) {
+        rc = run_cycle(s, kind, true);
+        if (rc != PMG_OK) return rc;
+        rc = read_scalar(s, &v);
+        if (rc != PMG_OK) return rc;
+        ++k;
+        double rn = std::sqrt(v);
+        if (res_history) res_history[k] = rn;
+        if (rn < rel_tol * r0) break;
+    }
+    PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    PMG_CUDA(cudaEventSynchronize(s->ev1));
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    if (n_cycles_out) *n_cycles_out = k;
+    return PMG_OK;
+}
+
+pmg_status pmg_last_device_ms(pmg_solver *s, double *ms_out)
+{
+    if (!s || !ms_out) return fail(PMG_ERR_INVALID, "null argument");
+    *ms_out = s->last_ms;
+    return PMG_OK;
+}
+
+void *pmg_stream(pmg_solver *s) { return s ? (void *)s->stream : nullptr; }
+
+/* ---- tuning / benchmarking hooks (not part of the reference surface) ---------------------------------- */
+int pmg_fused_num_variants(void) { return fused_num_variants(); }
+void pmg_fused_set_variant(int v) { fused_set_variant(v); }
+
+/* `sweeps` weighted-Jacobi sweeps on the solver's finest level, `block` sweeps per streaming pass
+ * (block = 1: one HBM pass per sweep, 24 B/point -- the "Jacobi sweep GB/s" sub-metric). */
+pmg_status pmg_smooth(pmg_solver *s, int sweeps, int block)
+{
+    if (!s || sweeps < 0 || !fused_supported(block)) return fail(PMG_ERR_INVALID, "bad argument");
+    PMG_CUDA(cudaSetDevice(s->device));
+    Level &L = s->lv[0];
+    PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    int left = sweeps;
+    while (left > 0) {
+        int b = left < block ? left : block;
+        launch_fused_down(fused_view(L), nullptr, 0, b, s->cfg.omega, false, s->stream);
+        std::swap(L.x, L.xb);
+        std::swap(L.base_x, L.base_xb);
+        left -= b;
+    }
+    PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    PMG_CUDA(cudaEventSynchronize(s->ev1));
+    PMG_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    drop_graphs(s);  // graphs captured earlier hold the old x/xb roles
+    return PMG_OK;
+}
+
+/* Times one fused pass of level `level` in isolation: which = 0 Pass A (sweeps+residual+restriction),
+ * 1 Pass B with the residual norm, 2 Pass B without, 3 Pass A with x == 0 (coarse-level form).  `reps`
+ * launches between two CUDA events on the solver stream; *ms_avg = average per launch.  Clobbers the
+ * iterate (benchmark use only). */
+pmg_status pmg_bench_pass(pmg_solver *s, int which, int level, int reps, double *ms_avg)
+{
+    if (!s || !ms_avg || reps < 1 || level < 0 || level + 1 >= (int)s->lv.size() || !s->fused)
+        return fail(PMG_ERR_INVALID, "bad argument (needs the fused engine and a non-coarsest level)");
+    PMG_CUDA(cudaSetDevice(s->device));
+    Level &L = s->lv[level];
+    Level &K = s->lv[level + 1];
+    const pmg_config &c = s->cfg;
+    int np = 0;
+    auto one = [&]() {
+        if (which == 0 || which == 3)
+            launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, which == 3, s->stream);
+        else
+            launch_fused_up(fused_view(L), K.x, K.pitch, c.nu2, c.omega, c.prolong_mode,
+                            which == 1 ? s->d_partials : nullptr, &np, s->stream);
+    };
+    one();  // warm-up
+    PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    for (int i = 0; i < reps; ++i) one();
+    PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    PMG_CUDA(cudaEventSynchronize(s->ev1));
+    PMG_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    *ms_avg = ms / reps;
+    return PMG_OK;
+}
+
+/* ---- operator level (dense reference layout, device pointers) ------------------------------------------ */
+static std::mutex g_scratch_mu;
+static double *g_scratch_partials = nullptr;  // reduce_partials() + 1 doubles, per process
+
+static pmg_status op_scratch(double **partials)
+{
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (!g_scratch_partials) {
+        if (cudaMalloc((void **)&g_scratch_partials, (reduce_partials() + 2) * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(PMG_ERR_ALLOC, "cudaMalloc failed");
+        }
+    }
+    *partials = g_scratch_partials;
+    return PMG_OK;
+}
+
+static pmg_status require_device()
+{
+    if (pmg_device_count() <= 0) return fail(PMG_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    return PMG_OK;
+}
+
+pmg_status pmg_jacobi(double *x, const double *f, int width, int height, double h, double omega, int sweeps,
+                      double *scratch, void *stream)
+{
+    if (!x || !f || width < 3 || height < 3 || sweeps < 0) return fail(PMG_ERR_INVALID, "bad argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *tmp = scratch;
+    size_t bytes = (size_t)width * height * sizeof(double);
+    if (!tmp && cudaMalloc((void **)&tmp, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PMG_ERR_ALLOC, "cudaMalloc failed");
+    }
+    double *a = x, *b = tmp;
+    for (int it = 0; it < sweeps; ++it) {
+        launch_jacobi_sweep(b, a, f, width, height, width, width, h, omega, st);
+        std::swap(a, b);
+    }
+    cudaError_t e = cudaSuccess;
+    if (a != x) e = cudaMemcpyAsync(x, a, bytes, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (!scratch) cudaFree(tmp);
+    if (e != cudaSuccess) return fail(PMG_ERR_CUDA, cudaGetErrorString(e));
+    return PMG_OK;
+}
+
+pmg_status pmg_residual(double *r, const double *x, const double *f, int width, int height, double h,
+                        double *norm2_out, void *stream)
+{
+    if (!x || !f || (!r && !norm2_out) || width < 3 || height < 3) return fail(PMG_ERR_INVALID, "bad argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (r) launch_residual(r, x, f, width, height, width, width, width, h, st);
+    if (norm2_out) {
+        double *part = nullptr;
+        if ((rc = op_scratch(&part)) != PMG_OK) return rc;
+        launch_residual_norm2(x, f, width, height, width, width, h, part, part + reduce_partials(), st);
+        PMG_CUDA(cudaMemcpyAsync(norm2_out, part + reduce_partials(), sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    PMG_CUDA(cudaStreamSynchronize(st));
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+pmg_status pmg_restrict_fw(const double *fine, double *coarse, int nf, int nc, void *stream)
+{
+    if (!fine || !coarse || nf < 3 || nc != (nf - 1) / 2 + 1) return fail(PMG_ERR_INVALID, "bad argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_restrict(fine, coarse, nf, nc, nf, nc, st);
+    PMG_CUDA(cudaStreamSynchronize(st));
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+pmg_status pmg_prolong_add(const double *coarse, double *fine, int nc, int nf, int mode, void *stream)
+{
+    if (!fine || !coarse || nf < 3 || nc != (nf - 1) / 2 + 1) return fail(PMG_ERR_INVALID, "bad argument");
+    if (mode != PMG_PROLONG_REFERENCE && mode != PMG_PROLONG_FULL) return fail(PMG_ERR_INVALID, "bad prolong mode");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_prolong_add(coarse, fine, nc, nf, nc, nf, mode, st);
+    PMG_CUDA(cudaStreamSynchronize(st));
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+pmg_status pmg_norm2(const double *v, size_t l, double *norm2_out, void *stream)
+{
+    if (!v || !norm2_out) return fail(PMG_ERR_INVALID, "null argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *part = nullptr;
+    if ((rc = op_scratch(&part)) != PMG_OK) return rc;
+    launch_norm2(v, l, part, part + reduce_partials(), st);
+    PMG_CUDA(cudaMemcpyAsync(norm2_out, part + reduce_partials(), sizeof(double), cudaMemcpyDeviceToHost, st));
+    PMG_CUDA(cudaStreamSynchronize(st));
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+/* ---- memory helpers ------------------------------------------------------------------------------------- */
+pmg_status pmg_device_alloc(void **p, size_t bytes)
+{
+    if (!p) return fail(PMG_ERR_INVALID, "null argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    if (cudaMalloc(p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PMG_ERR_ALLOC, "cudaMalloc failed");
+    }
+    return PMG_OK;
+}
+
+pmg_status pmg_device_free(void *p)
+{
+    PMG_CUDA(cudaFree(p));
+    return PMG_OK;
+}
+
+pmg_status pmg_host_alloc_pinned(void **p, size_t bytes)
+{
+    if (!p) return fail(PMG_ERR_INVALID, "null argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    if (cudaMallocHost(p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PMG_ERR_ALLOC, "cudaMallocHost failed");
+    }
+    return PMG_OK;
+}
+
+pmg_status pmg_host_free_pinned(void *p)
+{
+    PMG_CUDA(cudaFreeHost(p));
+    return PMG_OK;
+}
+
+pmg_status pmg_memcpy(void *dst, const void *src, size_t bytes, int dst_is_device, int src_is_device)
+{
+    cudaMemcpyKind k = dst_is_device ? (src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                                     : (src_is_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    PMG_CUDA(cudaMemcpy(dst, src, bytes, k));
+    return PMG_OK;
+}
+
+pmg_status pmg_device_synchronize(void)
+{
+    PMG_CUDA(cudaDeviceSynchronize());
+    return PMG_OK;
+}
+
+/* rows [y0, y1) of an n-row level owned by `rank`: even-aligned splits so that coarse row jc lives where
+ * fine row 2jc lives; the last rank also takes the odd final row. */
+pmg_status pmg_partition_rows(int n, int n_ranks, int rank, int *y0, int *y1)
+{
+    if (n < 3 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !y0 || !y1) return fail(PMG_ERR_INVALID, "bad argument");
+    long pairs = (n - 1) / 2;  // fine row pairs (2j, 2j+1); the final row n-1 is appended to the last rank
+    long a = pairs * rank / n_ranks, b = pairs * (rank + 1) / n_ranks;
+    *y0 = (int)(2 * a);
+    *y1 = (rank == n_ranks - 1) ? n : (int)(2 * b);
+    return PMG_OK;
+}
+
+}  // extern "C"
