@@ -58,6 +58,15 @@ typedef enum pmg_prolong_mode { PMG_PROLONG_REFERENCE = 0, PMG_PROLONG_FULL = 1 
 
 typedef enum pmg_mem { PMG_MEM_HOST = 0, PMG_MEM_DEVICE = 1 } pmg_mem;
 
+/* DynamicGridUtils::norm (DynamicGridUtils.hpp:21-27) adds the squares left to right.  On smooth fields
+ * that running sum drifts: at N = 16385 it differs from the exactly rounded sum by up to ~1e-9 relative.
+ * PMG_NORM_TREE (default) is a deterministic parallel tree sum fused into the last pass (accurate to
+ * ~1e-15, agrees with the reference to <= 1e-10 up to N = 4097 and to 2e-9 at N = 16385).
+ * PMG_NORM_SEQUENTIAL reproduces the reference's summation order on the device, one element at a time,
+ * so every per-cycle norm is BIT-IDENTICAL to the CPU path at any size; it costs ~4 ns per grid point
+ * per norm and exists for validation. */
+typedef enum pmg_norm_mode { PMG_NORM_TREE = 0, PMG_NORM_SEQUENTIAL = 1 } pmg_norm_mode;
+
 typedef enum pmg_engine {
     PMG_ENGINE_FUSED = 0,   /* temporally blocked streaming kernels (2 HBM passes per level visit)  */
     PMG_ENGINE_OPERATOR = 1 /* one kernel per reference operator (Parallel::Compute* granularity)  */
@@ -81,7 +90,8 @@ typedef struct pmg_config {
     /* ---- multi-GPU (row-slab decomposition, one process per GPU); leave zeroed for 1 GPU ---- */
     int rank, n_ranks;
     int agglomerate_below; /* levels with n <= this run on rank 0 only                              */
-    int reserved[8];
+    int norm_mode;       /* pmg_norm_mode: how the per-cycle residual norm is summed                */
+    int reserved[7];
 } pmg_config;
 
 typedef struct pmg_solver pmg_solver; /* opaque */

@@ -24,6 +24,7 @@ V, W, F = 0, 1, 2
 PROLONG_REFERENCE, PROLONG_FULL = 0, 1
 ENGINE_FUSED, ENGINE_OPERATOR = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
+NORM_TREE, NORM_SEQUENTIAL = 0, 1
 OK = 0
 STATUS_NAMES = {0: "PMG_OK", 1: "PMG_ERR_INVALID", 2: "PMG_ERR_CUDA", 3: "PMG_ERR_NO_DEVICE",
                 4: "PMG_ERR_ALLOC", 5: "PMG_ERR_COMM", 6: "PMG_ERR_UNSUPPORTED"}
@@ -42,7 +43,7 @@ class Config(ctypes.Structure):
                 ("prolong_mode", ctypes.c_int), ("engine", ctypes.c_int),
                 ("smoother_eps", ctypes.c_double), ("device", ctypes.c_int), ("use_graph", ctypes.c_int),
                 ("rank", ctypes.c_int), ("n_ranks", ctypes.c_int), ("agglomerate_below", ctypes.c_int),
-                ("reserved", ctypes.c_int * 8)]
+                ("norm_mode", ctypes.c_int), ("reserved", ctypes.c_int * 7)]
 
 
 # every symbol include/pmg.h declares (tests/test_abi.py checks the library exports all of them)
@@ -111,6 +112,7 @@ def lib():
     L.pmg_bench_pass.argtypes = [vp, i, i, i, pd]
     L.pmg_fused_set_variant.restype = None
     L.pmg_fused_set_variant.argtypes = [i]
+    L.pmg_fused_num_variants.restype = i
     _lib = L
     return L
 
@@ -299,5 +301,10 @@ def norm2(v):
     return out.value
 
 
-def set_fused_variant(v):
-    lib().pmg_fused_set_variant(v)
+def set_fused_variant(down, up=None):
+    """Tuning: pick the kernel instantiation of the nu == 2 passes (Pass A, Pass B)."""
+    lib().pmg_fused_set_variant(down if up is None else (down | (up << 8) | 0x10000))
+
+
+def num_fused_variants():
+    return lib().pmg_fused_num_variants()

@@ -129,6 +129,50 @@ __global__ void __launch_bounds__(RED_THREADS)
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
+// The reference's summation ORDER (DynamicGridUtils.hpp:21-27: sum += r[i]*r[i], i ascending over the
+// row-major array; ring entries are zero and leave the running sum unchanged).  All threads of one CTA
+// compute the squares of the next 2048 interior points into shared memory while thread 0 adds the
+// previous 2048 one at a time -- the result is bit-identical to the CPU loop.  Validation only.
+constexpr int SEQ_CHUNK = 2048;
+__global__ void __launch_bounds__(1024)
+    k_residual_norm2_seq(const double *__restrict__ xg, const double *__restrict__ f, int nx, int ny,
+                         int pitch_x, int pitch_f, double inv_h2, double *__restrict__ out)
+{
+    __shared__ double buf[2][SEQ_CHUNK];
+    const int per_row = (nx - 2 + SEQ_CHUNK - 1) / SEQ_CHUNK;
+    const long chunks = (long)per_row * (ny - 2);
+    double acc = 0.0;
+    for (long c = 0; c <= chunks; ++c) {
+        if (c < chunks) {
+            int y = 1 + (int)(c / per_row);
+            int x0 = 1 + (int)(c - (long)(y - 1) * per_row) * SEQ_CHUNK;
+            double *dst = buf[c & 1];
+            for (int k = threadIdx.x; k < SEQ_CHUNK; k += blockDim.x) {
+                int x = x0 + k;
+                double sq = 0.0;
+                if (x < nx - 1) {
+                    size_t i = (size_t)y * pitch_x + x;
+                    double r = residual_point(inv_h2, f[(size_t)y * pitch_f + x], xg[i], xg[i - 1], xg[i + 1],
+                                              xg[i - pitch_x], xg[i + pitch_x]);
+                    sq = dmul(r, r);
+                }
+                dst[k] = sq;
+            }
+        }
+        if (threadIdx.x == 0 && c > 0) {
+            long p = c - 1;
+            int y = 1 + (int)(p / per_row);
+            int x0 = 1 + (int)(p - (long)(y - 1) * per_row) * SEQ_CHUNK;
+            int cnt = min(SEQ_CHUNK, nx - 1 - x0);
+            const double *src = buf[p & 1];
+#pragma unroll 8
+            for (int k = 0; k < cnt; ++k) acc = dadd(acc, src[k]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = acc;
+}
+
 __global__ void __launch_bounds__(RED_THREADS)
     k_norm2(const double *__restrict__ v, size_t l, double *__restrict__ partials)
 {
@@ -267,6 +311,13 @@ void launch_residual_norm2(const double *x, const double *f, int nx, int ny, int
     k_residual_norm2<<<blocks, RED_THREADS, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, 1.0 / (h * h), d_partials);
     count_launch();
     launch_final_sum(d_partials, blocks, d_out, st);
+}
+
+void launch_residual_norm2_sequential(const double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f,
+                                      double h, double *d_out, cudaStream_t st)
+{
+    k_residual_norm2_seq<<<1, 1024, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, 1.0 / (h * h), d_out);
+    count_launch();
 }
 
 void launch_norm2(const double *v, size_t l, double *d_partials, double *d_out, cudaStream_t st)

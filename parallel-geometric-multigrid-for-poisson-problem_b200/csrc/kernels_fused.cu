@@ -17,7 +17,10 @@
 // two warp shuffles per stage per row; vertical neighbours are the register window.  Strips overlap
 // by HALO columns on each side (the temporally blocked stages eat one column per stage), chunks
 // overlap by the pipeline depth in rows; overlapped data is re-read from L2, not HBM.  Rows are
-// prefetched PF rows ahead into registers, so each warp keeps 2*PF KB in flight (x and f).
+// prefetched PF rows ahead, either into registers (RegFeed) or -- the default -- with cp.async into a
+// per-warp shared-memory ring (SmemFeed: each lane's 16-byte pieces land in its own slots, so the ring
+// is a private FIFO that needs no barrier; it also holds the delay line of f rows the later stages
+// read, which is what frees enough registers for 4 CTAs per SM with nothing spilled).
 //
 // Arithmetic is the reference's, operation for operation and in its order (pmg_internal.h), with no
 // FMA contraction: every value written is bit-identical to the CPU path.  Partial sums
@@ -31,8 +34,9 @@ namespace {
 
 // Tunables (template parameters of the kernels; `Variant` picks a combination at run time):
 //   C     columns per lane (4: two 128-bit accesses per row per array, strip = 128; 2: one, strip = 64)
-//   PF    rows prefetched ahead into registers (even)
+//   PF    rows prefetched ahead
 //   MINB  CTAs per SM promised to the compiler (register budget = 65536 / (128*MINB))
+//   SM    stage rows through shared memory with cp.async (true) or through registers (false)
 constexpr int WARPS_PER_CTA = 4;
 
 __host__ __device__ constexpr int halo_for(int stages) { return stages <= 4 ? 4 : 8; }
@@ -167,13 +171,146 @@ __device__ __forceinline__ void strip_setup(const StripGeom &g, int wid, int lan
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Row feeds: how rows of x and f travel from HBM to the pipeline, and where the delay line of f rows
+// (f of row j-d, needed by stage d) lives.
+// ---------------------------------------------------------------------------------------------------
+template <int C, int PF, int S, bool USE_X>
+struct RegFeed {
+    static constexpr int UNROLL = PF;  // slot index must be static: the row loop is unrolled by PF
+    static constexpr int SMEM_PER_WARP = 0;
+    Row<C> xbuf[PF], fbuf[PF], fq[S + 2];
+    const double *x, *f;
+    int pitch, last_row;
+    __device__ __forceinline__ void init(const double *x_, const double *f_, int pitch_, int col, int j_start,
+                                         int last_row_, int /*lane*/, int /*warp_in_cta*/)
+    {
+        x = x_ + col;
+        f = f_ + col;
+        pitch = pitch_;
+        last_row = last_row_;
+#pragma unroll
+        for (int d = 0; d < PF; ++d) {
+            xbuf[d] = USE_X ? load_row<C>(x + (ptrdiff_t)(j_start + d) * pitch) : zero_row<C>();
+            fbuf[d] = load_row<C>(f + (ptrdiff_t)(j_start + d) * pitch);
+        }
+#pragma unroll
+        for (int d = 0; d < S + 2; ++d) fq[d] = zero_row<C>();
+    }
+    // start of the step whose input row is jj (u = unrolled slot index); returns x row jj
+    __device__ __forceinline__ Row<C> begin(int u, int jj)
+    {
+        Row<C> cur = xbuf[u];
+#pragma unroll
+        for (int d = S + 1; d > 0; --d) fq[d] = fq[d - 1];
+        fq[0] = fbuf[u];
+        int nr = min(jj + PF, last_row);
+        if (USE_X) xbuf[u] = load_row<C>(x + (ptrdiff_t)nr * pitch);
+        fbuf[u] = load_row<C>(f + (ptrdiff_t)nr * pitch);
+        return cur;
+    }
+    __device__ __forceinline__ Row<C> f_row(int d) const { return fq[d]; }  // f of row jj - d
+    __device__ __forceinline__ void end() {}
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+extern __shared__ __align__(16) unsigned char g_dyn_smem[];
+
+template <int C, int PF, int S, bool USE_X>
+struct SmemFeed {
+    static constexpr int UNROLL = 2;
+    static constexpr int NF = 8;                       // f ring slots  (>= PF + S + 2)
+    static constexpr int NX = USE_X ? 4 : 0;           // x ring slots  (>= PF + 1)
+    static constexpr int PLANES = C / 2;               // 16-byte pieces per lane per row
+    static constexpr int ROW_BYTES = PLANES * 512;     // plane p of a row: 32 lanes x 16 B, conflict free
+    static constexpr int SMEM_PER_WARP = (NF + NX) * ROW_BYTES;
+    static_assert(PF + S + 2 <= NF && PF + 1 <= 4, "ring too small");
+    uint32_t fbase, xbase;  // shared-window addresses of this lane's first piece in slot 0
+    const double *x, *f;
+    int pitch, last_row, t;
+    __device__ __forceinline__ void issue(int row, int slot_t)
+    {
+        const double *fr = f + (ptrdiff_t)row * pitch;
+        uint32_t fa = fbase + (uint32_t)(slot_t & (NF - 1)) * ROW_BYTES;
+#pragma unroll
+        for (int p = 0; p < PLANES; ++p) cp_async16(fa + p * 512, fr + 2 * p);
+        if (USE_X) {
+            const double *xr = x + (ptrdiff_t)row * pitch;
+            uint32_t xa = xbase + (uint32_t)(slot_t & 3) * ROW_BYTES;
+#pragma unroll
+            for (int p = 0; p < PLANES; ++p) cp_async16(xa + p * 512, xr + 2 * p);
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ static Row<C> lds_row(uint32_t a)
+    {
+        Row<C> r;
+#pragma unroll
+        for (int p = 0; p < PLANES; ++p)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(r.v[2 * p]), "=d"(r.v[2 * p + 1]) : "r"(a + p * 512));
+        return r;
+    }
+    __device__ __forceinline__ void init(const double *x_, const double *f_, int pitch_, int col, int j_start,
+                                         int last_row_, int lane, int warp_in_cta)
+    {
+        x = x_ + col;
+        f = f_ + col;
+        pitch = pitch_;
+        last_row = last_row_;
+        t = 0;
+        uint32_t base = (uint32_t)__cvta_generic_to_shared(g_dyn_smem) + warp_in_cta * SMEM_PER_WARP;
+        // zero this lane's pieces (warm-up steps read slots that were never filled)
+#pragma unroll
+        for (int sl = 0; sl < NF + NX; ++sl)
+#pragma unroll
+            for (int p = 0; p < PLANES; ++p)
+                asm volatile("st.shared.v2.f64 [%0], {%1, %1};\n" ::"r"(base + sl * ROW_BYTES + p * 512 + lane * 16), "d"(0.0) : "memory");
+        fbase = base + lane * 16;
+        xbase = base + NF * ROW_BYTES + lane * 16;
+#pragma unroll
+        for (int d = 0; d < PF; ++d) issue(j_start + d, d);
+    }
+    __device__ __forceinline__ Row<C> begin(int /*u*/, int jj)
+    {
+        cp_async_wait<PF - 1>();  // all but the newest PF-1 groups have landed => row jj is in its slot
+        Row<C> cur = USE_X ? lds_row(xbase + (uint32_t)(t & 3) * ROW_BYTES) : zero_row<C>();
+        issue(min(jj + PF, last_row), t + PF);
+        return cur;
+    }
+    __device__ __forceinline__ Row<C> f_row(int d) const
+    {
+        return lds_row(fbase + (uint32_t)((t - d) & (NF - 1)) * ROW_BYTES);
+    }
+    __device__ __forceinline__ void end() { ++t; }
+};
+
+template <int C, int PF, int S, bool USE_X, bool SM>
+struct FeedSelect {
+    using type = RegFeed<C, PF, S, USE_X>;
+};
+template <int C, int PF, int S, bool USE_X>
+struct FeedSelect<C, PF, S, USE_X, true> {
+    using type = SmemFeed<C, PF, S, USE_X>;
+};
+
+// ---------------------------------------------------------------------------------------------------
 // Pass A.  S sweeps; RESID adds residual + full weighting into the coarse RHS; ZEROX: x == 0 on entry.
 // ---------------------------------------------------------------------------------------------------
-template <int C, int PF, int MINB, int S, bool ZEROX, bool RESID>
+template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_down(const double *__restrict__ x, double *__restrict__ xo, const double *__restrict__ f,
            double *__restrict__ cf, StripGeom g, int pitch_c, int nc, JacobiCoef coef, double inv_h2)
 {
+    using Feed = typename FeedSelect<C, PF, S, !ZEROX, SM>::type;
     constexpr int NP = C / 2;  // coarse points per lane (fine columns v0, v2, ...)
     const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -191,47 +328,31 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
     for (int k = 0; k < S; ++k) st[k].init();
     rs.init();
-    Row<C> fq[S + 2];  // fq[d] = f of row j-d
-#pragma unroll
-    for (int d = 0; d < S + 2; ++d) fq[d] = zero_row<C>();
     // full-weighting state per coarse point of this lane:
     //   south row 2jc-1: s_mid (centre value), s_cor = SW + SE;  centre row 2jc: c_mid, c_ew = E + W
     double s_mid[NP], s_cor[NP], c_mid[NP], c_ew[NP];
 #pragma unroll
     for (int q = 0; q < NP; ++q) s_mid[q] = s_cor[q] = c_mid[q] = c_ew[q] = 0.0;
 
-    Row<C> xbuf[PF], fbuf[PF];
-#pragma unroll
-    for (int d = 0; d < PF; ++d) {
-        xbuf[d] = ZEROX ? zero_row<C>() : load_row<C>(x + (ptrdiff_t)(j_start + d) * g.pitch + col);
-        fbuf[d] = load_row<C>(f + (ptrdiff_t)(j_start + d) * g.pitch + col);
-    }
-    const int last_row = g.n + PADY - 1;  // last row that exists in the allocation
+    Feed feed;
+    feed.init(x, f, g.pitch, col, j_start, g.n + PADY - 1, lane, threadIdx.x >> 5);
 
-    for (int j = j_start; j <= j_end; j += PF) {
+    for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
+        for (int u = 0; u < Feed::UNROLL; ++u) {
             const int jj = j + u;  // input row of this step (steps past j_end are harmless: stores are masked)
-            Row<C> cur = xbuf[u];
-#pragma unroll
-            for (int d = S + 1; d > 0; --d) fq[d] = fq[d - 1];
-            fq[0] = fbuf[u];
-            {   // refill the slot with row jj + PF (clamped to the allocation)
-                int nr = min(jj + PF, last_row);
-                if (!ZEROX) xbuf[u] = load_row<C>(x + (ptrdiff_t)nr * g.pitch + col);
-                fbuf[u] = load_row<C>(f + (ptrdiff_t)nr * g.pitch + col);
-            }
+            Row<C> cur = feed.begin(u, jj);
             // sweeps: stage k consumes x_k row jj-k and finishes x_{k+1} row jj-k-1
 #pragma unroll
             for (int k = 0; k < S; ++k) {
                 const int out_row = jj - k - 1;
-                cur = st[k].step(cur, fq[k], coef, out_row > 0 && out_row < g.n - 1, cin);
+                cur = st[k].step(cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
             }
             // cur = x_S row jj - S
             const int xrow = jj - S;
             if (owner && xrow >= r0 && xrow < r1) store_row<C>(xo + (ptrdiff_t)xrow * g.pitch + col, cur);
             if (RESID) {
-                Row<C> r = rs.step(cur, fq[S + 1], inv_h2);  // r of row jj - S - 1
+                Row<C> r = rs.step(cur, feed.f_row(S + 1), inv_h2);  // r of row jj - S - 1
                 const int rrow = jj - S - 1;
                 double left = __shfl_up_sync(0xffffffffu, r.v[C - 1], 1);
                 if (rrow & 1) {
@@ -266,8 +387,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                     }
                 }
             }
+            feed.end();
         }
     }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -293,13 +416,14 @@ __device__ __forceinline__ CoarseRow<C> load_coarse(const double *__restrict__ p
     return r;
 }
 
-template <int C, int PF, int MINB, int S, bool PROLONG, bool NORM>
+template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_up(const double *__restrict__ xb, double *__restrict__ xo, const double *__restrict__ f,
          const double *__restrict__ e, StripGeom g, int pitch_c, int lo, JacobiCoef coef, double inv_h2,
          double *__restrict__ partials)
 {
-    static_assert(PF % 2 == 0, "rows are processed in (even, odd) pairs");
+    using Feed = typename FeedSelect<C, PF, S, true, SM>::type;
+    static_assert(Feed::UNROLL % 2 == 0, "rows are processed in (even, odd) pairs");
     constexpr int NP = C / 2;
     const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -318,22 +442,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
     for (int k = 0; k < S; ++k) st[k].init();
     rs.init();
-    Row<C> fq[S + 2];
-#pragma unroll
-    for (int d = 0; d < S + 2; ++d) fq[d] = zero_row<C>();
     double acc = 0.0;
 
     bool cprol[C];  // columns that receive a correction
 #pragma unroll
     for (int k = 0; k < C; ++k) cprol[k] = (col + k >= lo) && (col + k <= g.n - 2);
 
-    Row<C> xbuf[PF], fbuf[PF];
-#pragma unroll
-    for (int d = 0; d < PF; ++d) {
-        xbuf[d] = load_row<C>(xb + (ptrdiff_t)(j_start + d) * g.pitch + col);
-        fbuf[d] = load_row<C>(f + (ptrdiff_t)(j_start + d) * g.pitch + col);
-    }
-    const int last_row = g.n + PADY - 1;
+    Feed feed;
+    feed.init(xb, f, g.pitch, col, j_start, g.n + PADY - 1, lane, threadIdx.x >> 5);
 
     // coarse rows: ec = row jc, en = row jc+1, eb = prefetch of row jc+2 (raw, before the shuffle)
     const int cc = col >> 1;
@@ -348,19 +464,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
         eb = load_coarse<C>(e + (ptrdiff_t)(jc0 + 1) * pitch_c + cc);
     }
 
-    for (int j = j_start; j <= j_end; j += PF) {
+    for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
+        for (int u = 0; u < Feed::UNROLL; ++u) {
             const int jj = j + u;  // u even: fine row 2jc, u odd: fine row 2jc+1
-            Row<C> cur = xbuf[u];
-#pragma unroll
-            for (int d = S + 1; d > 0; --d) fq[d] = fq[d - 1];
-            fq[0] = fbuf[u];
-            {
-                int nr = min(jj + PF, last_row);
-                xbuf[u] = load_row<C>(xb + (ptrdiff_t)nr * g.pitch + col);
-                fbuf[u] = load_row<C>(f + (ptrdiff_t)nr * g.pitch + col);
-            }
+            Row<C> cur = feed.begin(u, jj);
             if (PROLONG) {
                 const bool rowp = (jj >= lo) && (jj <= g.n - 2);
                 double corr[C];
@@ -391,12 +499,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
             for (int k = 0; k < S; ++k) {
                 const int out_row = jj - k - 1;
-                cur = st[k].step(cur, fq[k], coef, out_row > 0 && out_row < g.n - 1, cin);
+                cur = st[k].step(cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
             }
             const int xrow = jj - S;
             if (owner && xrow >= r0 && xrow < r1) store_row<C>(xo + (ptrdiff_t)xrow * g.pitch + col, cur);
             if (NORM) {
-                Row<C> r = rs.step(cur, fq[S + 1], inv_h2);
+                Row<C> r = rs.step(cur, feed.f_row(S + 1), inv_h2);
                 const int rrow = jj - S - 1;
                 if (owner && rrow >= r0 && rrow < r1 && rrow > 0 && rrow < g.n - 1) {
 #pragma unroll
@@ -404,8 +512,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                         if (cin[k]) acc = dadd(acc, dmul(r.v[k], r.v[k]));
                 }
             }
+            feed.end();
         }
     }
+    cp_async_wait<0>();
     if (NORM) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc = dadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
@@ -415,11 +525,20 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 
 // ---- run-time variant table ---------------------------------------------------------------------
 struct VariantDesc {
-    int c, pf, minb;
+    int c, pf, minb, sm;
 };
-constexpr int NUM_VARIANTS = 4;
-constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {{4, 2, 3}, {4, 2, 2}, {2, 2, 5}, {2, 4, 4}};
-int g_variant = 0;
+constexpr int NUM_VARIANTS = 8;
+constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {
+    {4, 3, 4, 1},  // 0: shared-memory staged, 16 warps/SM            (default)
+    {4, 3, 3, 1},  // 1: shared-memory staged, 12 warps/SM
+    {4, 2, 3, 0},  // 2: register staged
+    {4, 2, 2, 0},  // 3
+    {2, 2, 5, 0},  // 4
+    {2, 4, 4, 0},  // 5
+    {2, 3, 6, 1},  // 6: shared-memory staged, 2 columns per lane, 24 warps/SM
+    {2, 3, 4, 1},  // 7
+};
+int g_variant_down = 0, g_variant_up = 0;
 
 int g_num_sms = 0;
 int num_sms()
@@ -459,44 +578,71 @@ inline int grid_for(const StripGeom &g)
     return (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 }
 
-template <int C, int PF, int MINB, int S>
+template <typename K>
+void set_smem(K kernel, int bytes)
+{
+    if (bytes > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+template <int C, int PF, int MINB, bool SM, int S>
 void down_launch(const FusedLevel &lv, double *cf, int pitch_c, double omega, bool x_is_zero, bool resid,
                  cudaStream_t st)
 {
-    StripGeom g = make_geom(lv.n, lv.pitch, S + (resid ? 2 : 0), VariantDesc{C, PF, MINB});
+    StripGeom g = make_geom(lv.n, lv.pitch, S + (resid ? 2 : 0), VariantDesc{C, PF, MINB, SM});
     JacobiCoef c = jacobi_coef(lv.h, omega);
     double inv = 1.0 / (lv.h * lv.h);
     int nc = (lv.n - 1) / 2 + 1;
     dim3 grid(grid_for(g)), block(32 * WARPS_PER_CTA);
-    if (resid) {
-        if (x_is_zero)
-            k_down<C, PF, MINB, S, true, true><<<grid, block, 0, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv);
-        else
-            k_down<C, PF, MINB, S, false, true><<<grid, block, 0, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv);
+    if (resid && x_is_zero) {
+        auto k = k_down<C, PF, MINB, SM, S, true, true>;
+        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
+        static bool once = (set_smem(k, sm), true);
+        (void)once;
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv);
+    } else if (resid) {
+        auto k = k_down<C, PF, MINB, SM, S, false, true>;
+        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
+        static bool once = (set_smem(k, sm), true);
+        (void)once;
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv);
     } else {
-        k_down<C, PF, MINB, S, false, false><<<grid, block, 0, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv);
+        auto k = k_down<C, PF, MINB, SM, S, false, false>;
+        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
+        static bool once = (set_smem(k, sm), true);
+        (void)once;
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv);
     }
     count_launch();
 }
 
-template <int C, int PF, int MINB, int S>
+template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM>
+void up_launch_one(const FusedLevel &lv, const double *e, int pitch_c, const StripGeom &g, int lo,
+                   const JacobiCoef &c, double inv, double *d_partials, cudaStream_t st)
+{
+    auto k = k_up<C, PF, MINB, SM, S, PROLONG, NORM>;
+    int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
+    static bool once = (set_smem(k, sm), true);
+    (void)once;
+    k<<<dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+}
+
+template <int C, int PF, int MINB, bool SM, int S>
 void up_launch(const FusedLevel &lv, const double *e, int pitch_c, double omega, int lo, bool norm,
                double *d_partials, int *n_partials, cudaStream_t st)
 {
-    StripGeom g = make_geom(lv.n, lv.pitch, S + (norm ? 2 : 1), VariantDesc{C, PF, MINB});
+    StripGeom g = make_geom(lv.n, lv.pitch, S + (norm ? 2 : 1), VariantDesc{C, PF, MINB, SM});
     JacobiCoef c = jacobi_coef(lv.h, omega);
     double inv = 1.0 / (lv.h * lv.h);
-    dim3 grid(grid_for(g)), block(32 * WARPS_PER_CTA);
     if (e != nullptr) {
         if (norm)
-            k_up<C, PF, MINB, S, true, true><<<grid, block, 0, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+            up_launch_one<C, PF, MINB, SM, S, true, true>(lv, e, pitch_c, g, lo, c, inv, d_partials, st);
         else
-            k_up<C, PF, MINB, S, true, false><<<grid, block, 0, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+            up_launch_one<C, PF, MINB, SM, S, true, false>(lv, e, pitch_c, g, lo, c, inv, d_partials, st);
     } else {
         if (norm)
-            k_up<C, PF, MINB, S, false, true><<<grid, block, 0, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+            up_launch_one<C, PF, MINB, SM, S, false, true>(lv, e, pitch_c, g, lo, c, inv, d_partials, st);
         else
-            k_up<C, PF, MINB, S, false, false><<<grid, block, 0, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+            up_launch_one<C, PF, MINB, SM, S, false, false>(lv, e, pitch_c, g, lo, c, inv, d_partials, st);
     }
     count_launch();
     if (n_partials) *n_partials = norm ? g.n_strips * g.n_chunks : 0;
@@ -507,8 +653,15 @@ void up_launch(const FusedLevel &lv, const double *e, int pitch_c, double omega,
 bool fused_supported(int nu) { return nu >= 1 && nu <= 4; }
 
 int fused_num_variants() { return NUM_VARIANTS; }
-void fused_set_variant(int v) { g_variant = (v >= 0 && v < NUM_VARIANTS) ? v : 0; }
-int fused_get_variant() { return g_variant; }
+void fused_set_variant(int v)
+{
+    // bit 16 clear: one variant for both passes; set: low byte = Pass A variant, next byte = Pass B variant
+    int d = v & 0xff, u = (v >> 8) & 0xff;
+    if (!(v & 0x10000)) u = d;
+    g_variant_down = (d >= 0 && d < NUM_VARIANTS) ? d : 0;
+    g_variant_up = (u >= 0 && u < NUM_VARIANTS) ? u : 0;
+}
+int fused_get_variant() { return g_variant_down | (g_variant_up << 8); }
 
 int fused_max_partials(int n)
 {
@@ -524,12 +677,16 @@ int fused_max_partials(int n)
 }
 
 // The tuning variants exist for the headline V(2,2) configuration only; other sweep counts use variant 0.
-#define PMG_DISPATCH_S2(FN, ...)                                          \
-    switch (g_variant) {                                                  \
-        case 1: FN<4, 2, 2, 2>(__VA_ARGS__); break;                       \
-        case 2: FN<2, 2, 5, 2>(__VA_ARGS__); break;                       \
-        case 3: FN<2, 4, 4, 2>(__VA_ARGS__); break;                       \
-        default: FN<4, 2, 3, 2>(__VA_ARGS__); break;                      \
+#define PMG_DISPATCH_S2(VAR, FN, ...)                                       \
+    switch (VAR) {                                                          \
+        case 1: FN<4, 3, 3, true, 2>(__VA_ARGS__); break;                   \
+        case 2: FN<4, 2, 3, false, 2>(__VA_ARGS__); break;                  \
+        case 3: FN<4, 2, 2, false, 2>(__VA_ARGS__); break;                  \
+        case 4: FN<2, 2, 5, false, 2>(__VA_ARGS__); break;                  \
+        case 5: FN<2, 4, 4, false, 2>(__VA_ARGS__); break;                  \
+        case 6: FN<2, 3, 6, true, 2>(__VA_ARGS__); break;                   \
+        case 7: FN<2, 3, 4, true, 2>(__VA_ARGS__); break;                   \
+        default: FN<4, 3, 4, true, 2>(__VA_ARGS__); break;                  \
     }
 
 void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int nu1, double omega,
@@ -537,10 +694,10 @@ void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int 
 {
     bool resid = coarse_f != nullptr;
     switch (nu1) {
-        case 1: down_launch<4, 2, 3, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
-        case 2: PMG_DISPATCH_S2(down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
-        case 3: down_launch<4, 2, 3, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
-        case 4: down_launch<4, 2, 3, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 1: down_launch<4, 3, 4, true, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 2: PMG_DISPATCH_S2(g_variant_down, down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 3: down_launch<4, 3, 3, true, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 4: down_launch<4, 2, 3, true, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
         default: break;
     }
 }
@@ -551,10 +708,10 @@ void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, 
     bool norm = d_partials != nullptr;
     int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
     switch (nu2) {
-        case 1: up_launch<4, 2, 3, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
-        case 2: PMG_DISPATCH_S2(up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
-        case 3: up_launch<4, 2, 3, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
-        case 4: up_launch<4, 2, 3, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 1: up_launch<4, 3, 4, true, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 2: PMG_DISPATCH_S2(g_variant_up, up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 3: up_launch<4, 3, 3, true, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 4: up_launch<4, 2, 3, true, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
         default: break;
     }
 }

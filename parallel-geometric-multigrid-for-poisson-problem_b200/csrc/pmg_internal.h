@@ -85,6 +85,9 @@ void launch_residual(double *r, const double *x, const double *f, int nx, int ny
 int reduce_partials();
 void launch_residual_norm2(const double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f,
                            double h, double *d_partials, double *d_out, cudaStream_t st);
+// same quantity summed in the reference's left-to-right order (bit-identical to the CPU loop; slow)
+void launch_residual_norm2_sequential(const double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f,
+                                      double h, double *d_out, cudaStream_t st);
 void launch_norm2(const double *v, size_t l, double *d_partials, double *d_out, cudaStream_t st);
 // fixed-order sum of `count` partials -> *d_out
 void launch_final_sum(const double *d_partials, int count, double *d_out, cudaStream_t st);

@@ -174,7 +174,10 @@ static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero,
 static pmg_status residual_norm2_async(pmg_solver *s)
 {
     Level &L = s->lv[0];
-    launch_residual_norm2(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
+    if (s->cfg.norm_mode == PMG_NORM_SEQUENTIAL)
+        launch_residual_norm2_sequential(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_scalar, s->stream);
+    else
+        launch_residual_norm2(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
     return PMG_OK;
 }
 
@@ -272,6 +275,11 @@ static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
     }
     if (kind != PMG_CYCLE_V && kind != PMG_CYCLE_W) return fail(PMG_ERR_INVALID, "unknown cycle kind");
     bool w = (kind == PMG_CYCLE_W);
+    if (s->fused && want_norm && s->cfg.norm_mode == PMG_NORM_SEQUENTIAL) {
+        rc = run_cycle(s, kind, false);
+        if (rc == PMG_OK) rc = residual_norm2_async(s);
+        return rc;
+    }
     if (!s->fused) {
         rc = cycle_operator(s, 0, w, false);
         if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
@@ -358,6 +366,7 @@ void pmg_config_default(pmg_config *cfg, int n)
     cfg->rank = 0;
     cfg->n_ranks = 1;
     cfg->agglomerate_below = 2049;
+    cfg->norm_mode = PMG_NORM_TREE;
 }
 
 unsigned long long pmg_kernel_launches(void) { return launches_so_far(); }
@@ -382,6 +391,8 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         return fail(PMG_ERR_INVALID, "negative sweep count or gamma < 1");
     if (!is_pow2_plus_1(cfg->n_coarse)) return fail(PMG_ERR_INVALID, "n_coarse must be 2^k + 1");
     if (!(cfg->omega > 0.0)) return fail(PMG_ERR_INVALID, "omega must be positive");
+    if (cfg->norm_mode != PMG_NORM_TREE && cfg->norm_mode != PMG_NORM_SEQUENTIAL)
+        return fail(PMG_ERR_INVALID, "bad norm_mode");
     if (cfg->n_ranks > 1) return fail(PMG_ERR_UNSUPPORTED, "multi-GPU solver handles are created with pmg_dist_create");
     int ndev = pmg_device_count();
     if (ndev <= 0) return fail(PMG_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");

@@ -1,9 +1,14 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed goldens.
 
 Tolerances.  Every operator output and every iterate is compared BIT-EXACTLY (np.array_equal): the
-kernels evaluate the reference's expressions in its order without FMA contraction.  Residual NORMS are
-compared to 1e-10 relative per cycle (north-star tolerance); the only difference is the summation order
-(parallel tree on the GPU, left-to-right in DynamicGridUtils::norm), observed ~1e-15.
+kernels evaluate the reference's expressions in its order without FMA contraction.  Residual NORMS:
+  * norm_mode = SEQUENTIAL (the reference's left-to-right summation order reproduced on the device):
+    compared with `==` -- every per-cycle norm is bit-identical to the CPU path, at every size up to
+    the full N = 16385 history.
+  * norm_mode = TREE (default, fused parallel sum): <= 1e-10 relative per cycle (north-star tolerance)
+    up to N = 4097.  At N = 16385 the REFERENCE's running sum of 2.7e8 squares has itself drifted by
+    up to 8.5e-10 from the exactly rounded sum (smooth fields give correlated rounding), so the tree sum
+    is held to 2e-9 there; the SEQUENTIAL run shows the iterates are identical.
 """
 import numpy as np
 import pytest
@@ -23,11 +28,11 @@ def _rand(shape, seed):
     return np.random.default_rng(seed).standard_normal(shape)
 
 
-def _hist_close(a, b):
+def _hist_close(a, b, rtol=NORM_RTOL):
     a, b = np.asarray(a), np.asarray(b)
     assert a.shape == b.shape
     rel = np.abs(a - b) / np.abs(b)
-    assert rel.max() <= NORM_RTOL, "max relative deviation %.3e" % rel.max()
+    assert rel.max() <= rtol, "max relative deviation %.3e" % rel.max()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -84,10 +89,6 @@ def test_operator_known_answers(golden):
     for g in golden["operators"]:
         n = g["n"]
         h, m = 1.0 / (n - 1), n // 2
-        with pmg.Solver(n) as s:
-            s.set_rhs_sine()
-            f = np.empty((n, n))
-            # read f back through a zero guess + residual: r = f - A*0 = f on the interior
         orc = cc.load("orc")
         f = orc.rhs(n)
         dx, df = pmg.DeviceArray.from_numpy(np.zeros((n, n))), pmg.DeviceArray.from_numpy(f)
@@ -133,6 +134,9 @@ def test_rhs_sine_bit_exact(orc):
 # ---------------------------------------------------------------------------------------------------
 # cycle level: residual histories and iterates against the goldens generated from the reference
 # ---------------------------------------------------------------------------------------------------
+TREE_RTOL_16385 = 2e-9
+
+
 def _gpu_history(h, engine, **extra):
     n = h["n"]
     f = cc.load("orc").rhs(n) if h["rhs"] == "sine" else cc.random_rhs(n)
@@ -155,6 +159,9 @@ def test_history_matches_reference_golden(golden, engine, idx):
     _hist_close(hist, h["hist"])
     if h["field"]:
         assert np.array_equal(phi, golden["fields"][h["field"]]), "iterate is not bit-identical"
+    # the same run with the reference's summation order: the whole history is bit-identical
+    k, hist, _ = _gpu_history(h, engine, norm_mode=pmg.NORM_SEQUENTIAL)
+    assert k == h["cycles"] and list(hist) == h["hist"]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -261,7 +268,7 @@ def test_n16385_history_against_survey(golden):
     s.zero_guess()
     k, hist = s.solve(pmg.V, rel_tol=1e-8, max_cycles=60)
     assert k == 39
-    _hist_close(hist[1:], sv["V_n16385"])
+    _hist_close(hist[1:], sv["V_n16385"], TREE_RTOL_16385)
     s.close()
     s = pmg.Solver(16385, omega=2.0 / 3.0, prolong_mode=pmg.PROLONG_FULL)
     s.set_rhs_sine()
@@ -269,7 +276,20 @@ def test_n16385_history_against_survey(golden):
     k, hist = s.solve(pmg.V, rel_tol=1e-8, max_cycles=60)
     s.close()
     assert k == 13
-    _hist_close(hist[1:], sv["V_n16385_full_prolong"])
+    _hist_close(hist[1:], sv["V_n16385_full_prolong"], TREE_RTOL_16385)
+
+
+def test_n16385_history_bit_identical_with_reference_summation_order(golden):
+    """BASELINE config 3 with norm_mode = SEQUENTIAL: all 39 residual norms of the reference CPU run
+    (20 min, 13 GB on the host) reproduced BIT FOR BIT -- i.e. every iterate is identical."""
+    sv = golden["survey"]
+    s = pmg.Solver(16385, omega=2.0 / 3.0, norm_mode=pmg.NORM_SEQUENTIAL)
+    s.set_rhs_sine()
+    s.zero_guess()
+    k, hist = s.solve(pmg.V, rel_tol=1e-8, max_cycles=60)
+    s.close()
+    assert k == 39
+    assert list(hist[1:]) == sv["V_n16385"]
 
 
 def test_n16385_w_cycle_against_survey(golden):
@@ -280,7 +300,7 @@ def test_n16385_w_cycle_against_survey(golden):
     k, hist = s.solve(pmg.W, rel_tol=1e-8, max_cycles=40)
     s.close()
     assert k == 19
-    _hist_close(hist[1:], sv["W_alpha2_n16385"])
+    _hist_close(hist[1:], sv["W_alpha2_n16385"], TREE_RTOL_16385)
 
 
 @pytest.mark.parametrize("n", [2049, 4097])
@@ -289,8 +309,8 @@ def test_engines_and_variants_agree_bitwise(n):
     variants of the fused kernels give the same bits on a random RHS."""
     f = cc.random_rhs(n, seed=41)
     out = []
-    for engine, variant, graph in [(pmg.ENGINE_OPERATOR, 0, 0), (pmg.ENGINE_FUSED, 0, 1), (pmg.ENGINE_FUSED, 1, 0),
-                                   (pmg.ENGINE_FUSED, 2, 1), (pmg.ENGINE_FUSED, 3, 0)]:
+    runs = [(pmg.ENGINE_OPERATOR, 0, 0)] + [(pmg.ENGINE_FUSED, v, v % 2) for v in range(pmg.num_fused_variants())]
+    for engine, variant, graph in runs:
         pmg.set_fused_variant(variant)
         s = pmg.Solver(n, omega=2.0 / 3.0, gamma=2, engine=engine, use_graph=graph)
         s.set_rhs(f)

@@ -13,7 +13,7 @@ sizes = [int(a) for a in sys.argv[1:]] or [4097, 16385]
 names = {0: ("passA", 26.0), 3: ("passA_zero", 18.0), 1: ("passB_norm", 26.0), 2: ("passB", 26.0)}
 rows = []
 for n in sizes:
-    for v in range(pmg.lib().pmg_fused_num_variants()):
+    for v in range(pmg.num_fused_variants()):
         pmg.set_fused_variant(v)
         s = pmg.Solver(n, omega=2.0 / 3.0, use_graph=0)
         s.set_rhs_sine()
