@@ -113,6 +113,8 @@ def lib():
     L.pmg_fused_set_variant.restype = None
     L.pmg_fused_set_variant.argtypes = [i]
     L.pmg_fused_num_variants.restype = i
+    L.pmg_fused_set_min_chunk_rows.restype = None
+    L.pmg_fused_set_min_chunk_rows.argtypes = [i]
     _lib = L
     return L
 

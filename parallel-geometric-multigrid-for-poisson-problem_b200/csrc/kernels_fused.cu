@@ -527,18 +527,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 struct VariantDesc {
     int c, pf, minb, sm;
 };
-constexpr int NUM_VARIANTS = 8;
+constexpr int NUM_VARIANTS = 6;
 constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {
-    {4, 3, 4, 1},  // 0: shared-memory staged, 16 warps/SM            (default)
-    {4, 3, 3, 1},  // 1: shared-memory staged, 12 warps/SM
-    {4, 2, 3, 0},  // 2: register staged
-    {4, 2, 2, 0},  // 3
-    {2, 2, 5, 0},  // 4
-    {2, 4, 4, 0},  // 5
-    {2, 3, 6, 1},  // 6: shared-memory staged, 2 columns per lane, 24 warps/SM
-    {2, 3, 4, 1},  // 7
+    {2, 3, 4, 1},  // 0: shared-memory staged, 2 columns per lane, 16 warps/SM   (default; measured best)
+    {2, 3, 6, 1},  // 1: same, 24 warps/SM
+    {2, 3, 5, 1},  // 2: same, 20 warps/SM
+    {2, 2, 4, 1},  // 3: prefetch depth 2
+    {4, 2, 3, 0},  // 4: register staged, 4 columns per lane
+    {2, 4, 4, 0},  // 5: register staged, 2 columns per lane
 };
 int g_variant_down = 0, g_variant_up = 0;
+int g_min_chunk_rows = 8;  // even; the pipeline warm-up (4..8 rows) is paid once per chunk
 
 int g_num_sms = 0;
 int num_sms()
@@ -566,7 +565,7 @@ StripGeom make_geom(int n, int pitch, int stages, const VariantDesc &v)
     if (chunks < 1) chunks = 1;
     int rows = (n + chunks - 1) / chunks;
     rows += rows & 1;
-    if (rows < 16) rows = 16;
+    if (rows < g_min_chunk_rows) rows = g_min_chunk_rows;
     g.chunk_rows = rows;
     g.n_chunks = (n + rows - 1) / rows;
     return g;
@@ -662,6 +661,7 @@ void fused_set_variant(int v)
     g_variant_up = (u >= 0 && u < NUM_VARIANTS) ? u : 0;
 }
 int fused_get_variant() { return g_variant_down | (g_variant_up << 8); }
+void fused_set_min_chunk_rows(int r) { g_min_chunk_rows = (r >= 2) ? (r + (r & 1)) : 2; }
 
 int fused_max_partials(int n)
 {
@@ -679,14 +679,12 @@ int fused_max_partials(int n)
 // The tuning variants exist for the headline V(2,2) configuration only; other sweep counts use variant 0.
 #define PMG_DISPATCH_S2(VAR, FN, ...)                                       \
     switch (VAR) {                                                          \
-        case 1: FN<4, 3, 3, true, 2>(__VA_ARGS__); break;                   \
-        case 2: FN<4, 2, 3, false, 2>(__VA_ARGS__); break;                  \
-        case 3: FN<4, 2, 2, false, 2>(__VA_ARGS__); break;                  \
-        case 4: FN<2, 2, 5, false, 2>(__VA_ARGS__); break;                  \
+        case 1: FN<2, 3, 6, true, 2>(__VA_ARGS__); break;                   \
+        case 2: FN<2, 3, 5, true, 2>(__VA_ARGS__); break;                   \
+        case 3: FN<2, 2, 4, true, 2>(__VA_ARGS__); break;                   \
+        case 4: FN<4, 2, 3, false, 2>(__VA_ARGS__); break;                  \
         case 5: FN<2, 4, 4, false, 2>(__VA_ARGS__); break;                  \
-        case 6: FN<2, 3, 6, true, 2>(__VA_ARGS__); break;                   \
-        case 7: FN<2, 3, 4, true, 2>(__VA_ARGS__); break;                   \
-        default: FN<4, 3, 4, true, 2>(__VA_ARGS__); break;                  \
+        default: FN<2, 3, 4, true, 2>(__VA_ARGS__); break;                  \
     }
 
 void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int nu1, double omega,
@@ -694,10 +692,10 @@ void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int 
 {
     bool resid = coarse_f != nullptr;
     switch (nu1) {
-        case 1: down_launch<4, 3, 4, true, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 1: down_launch<2, 3, 4, true, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
         case 2: PMG_DISPATCH_S2(g_variant_down, down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
-        case 3: down_launch<4, 3, 3, true, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
-        case 4: down_launch<4, 2, 3, true, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 3: down_launch<2, 3, 4, true, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 4: down_launch<2, 2, 4, true, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
         default: break;
     }
 }
@@ -708,10 +706,10 @@ void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, 
     bool norm = d_partials != nullptr;
     int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
     switch (nu2) {
-        case 1: up_launch<4, 3, 4, true, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 1: up_launch<2, 3, 4, true, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
         case 2: PMG_DISPATCH_S2(g_variant_up, up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
-        case 3: up_launch<4, 3, 3, true, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
-        case 4: up_launch<4, 2, 3, true, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 3: up_launch<2, 3, 4, true, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 4: up_launch<2, 2, 4, true, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
         default: break;
     }
 }

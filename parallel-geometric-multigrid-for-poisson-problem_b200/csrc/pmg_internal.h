@@ -125,5 +125,6 @@ int fused_max_partials(int n);
 int fused_num_variants();
 void fused_set_variant(int v);
 int fused_get_variant();
+void fused_set_min_chunk_rows(int r);
 
 }  // namespace pmg

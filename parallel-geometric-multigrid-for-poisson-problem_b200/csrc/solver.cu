@@ -612,6 +612,7 @@ void *pmg_stream(pmg_solver *s) { return s ? (void *)s->stream : nullptr; }
 /* ---- tuning / benchmarking hooks (not part of the reference surface) ---------------------------------- */
 int pmg_fused_num_variants(void) { return fused_num_variants(); }
 void pmg_fused_set_variant(int v) { fused_set_variant(v); }
+void pmg_fused_set_min_chunk_rows(int r) { fused_set_min_chunk_rows(r); }
 
 /* `sweeps` weighted-Jacobi sweeps on the solver's finest level, `block` sweeps per streaming pass
  * (block = 1: one HBM pass per sweep, 24 B/point -- the "Jacobi sweep GB/s" sub-metric). */
