@@ -537,7 +537,7 @@ constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {
     {2, 4, 4, 0},  // 5: register staged, 2 columns per lane
 };
 int g_variant_down = 0, g_variant_up = 0;
-int g_min_chunk_rows = 8;  // even; the pipeline warm-up (4..8 rows) is paid once per chunk
+int g_min_chunk_rows = 4;  // even; the pipeline warm-up (4..8 rows) is paid once per chunk
 
 int g_num_sms = 0;
 int num_sms()
