@@ -42,9 +42,10 @@ __global__ void __launch_bounds__(BX *BY)
 // ---- all sweeps of a small level inside one CTA (coarsest-grid solve, MultiGrid.hpp:59-63) ---------
 __global__ void __launch_bounds__(1024)
     k_jacobi_small(double *__restrict__ xg, const double *__restrict__ fg, int nx, int ny, int pitch_x,
-                   int pitch_f, JacobiCoef c, int sweeps, int x_is_zero)
+                   int pitch_f, JacobiCoef c, int sweeps, int x_is_zero, const int *__restrict__ done)
 {
     __shared__ double a[SMALL_MAX_POINTS], b[SMALL_MAX_POINTS], fs[SMALL_MAX_POINTS];
+    if (done != nullptr && *done) return;
     int l = nx * ny;
     for (int i = threadIdx.x; i < l; i += blockDim.x) {
         int y = i / nx, x = i - y * nx;
@@ -195,6 +196,33 @@ __global__ void __launch_bounds__(1024) k_final_sum(const double *__restrict__ p
     if (threadIdx.x == 0) *out = acc;
 }
 
+__global__ void k_solve_begin(const double *__restrict__ norm2, SolveCtrl *ctrl, double *__restrict__ hist2,
+                              double rel_tol, int max_cycles)
+{
+    hist2[0] = *norm2;
+    ctrl->r0 = sqrt(*norm2);
+    ctrl->rel_tol = rel_tol;
+    ctrl->cycles = 0;
+    ctrl->max_cycles = max_cycles;
+    ctrl->done = (max_cycles <= 0) ? 1 : 0;
+}
+
+// Last kernel of a cycle (MultiGridTestRunner.hpp:210-211 + the relative stopping test the reference lacks)
+__global__ void __launch_bounds__(1024)
+    k_cycle_finish(const double *__restrict__ partials, int count, SolveCtrl *ctrl, double *__restrict__ hist2)
+{
+    if (ctrl->done) return;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) acc = dadd(acc, partials[i]);
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) {
+        int c = ctrl->cycles + 1;
+        ctrl->cycles = c;
+        hist2[c] = acc;
+        if (sqrt(acc) < dmul(ctrl->rel_tol, ctrl->r0) || c >= ctrl->max_cycles) ctrl->done = 1;
+    }
+}
+
 // ---- full-weighting restriction: MultiGrid.hpp:187-205 (replaces restriction_kernel_full_weighting,
 //      Parallel_Method.cu:48-78) ---------------------------------------------------------------------
 __global__ void __launch_bounds__(BX *BY)
@@ -278,11 +306,11 @@ void launch_jacobi_sweep(double *out, const double *in, const double *f, int nx,
 }
 
 void launch_jacobi_small(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h,
-                         double omega, int sweeps, bool x_is_zero, cudaStream_t st)
+                         double omega, int sweeps, bool x_is_zero, cudaStream_t st, const int *done)
 {
     int l = nx * ny;
     int threads = l >= 1024 ? 1024 : ((l + 31) / 32) * 32;
-    k_jacobi_small<<<1, threads, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, make_coef(h, omega), sweeps, x_is_zero ? 1 : 0);
+    k_jacobi_small<<<1, threads, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, make_coef(h, omega), sweeps, x_is_zero ? 1 : 0, done);
     count_launch();
 }
 
@@ -299,6 +327,19 @@ int reduce_partials() { return RED_BLOCKS; }
 void launch_final_sum(const double *d_partials, int count, double *d_out, cudaStream_t st)
 {
     k_final_sum<<<1, 1024, 0, st>>>(d_partials, count, d_out);
+    count_launch();
+}
+
+void launch_solve_begin(const double *d_norm2, SolveCtrl *ctrl, double *hist2, double rel_tol, int max_cycles,
+                        cudaStream_t st)
+{
+    k_solve_begin<<<1, 1, 0, st>>>(d_norm2, ctrl, hist2, rel_tol, max_cycles);
+    count_launch();
+}
+
+void launch_cycle_finish(const double *d_partials, int count, SolveCtrl *ctrl, double *hist2, cudaStream_t st)
+{
+    k_cycle_finish<<<1, 1024, 0, st>>>(d_partials, count, ctrl, hist2);
     count_launch();
 }
 

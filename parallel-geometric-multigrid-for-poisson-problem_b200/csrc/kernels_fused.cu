@@ -308,9 +308,11 @@ struct FeedSelect<C, PF, S, USE_X, true> {
 template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_down(const double *__restrict__ x, double *__restrict__ xo, const double *__restrict__ f,
-           double *__restrict__ cf, StripGeom g, int pitch_c, int nc, JacobiCoef coef, double inv_h2)
+           double *__restrict__ cf, StripGeom g, int pitch_c, int nc, JacobiCoef coef, double inv_h2,
+           const int *__restrict__ done)
 {
     using Feed = typename FeedSelect<C, PF, S, !ZEROX, SM>::type;
+    if (done != nullptr && *done) return;  // device-side convergence control: the solve already stopped
     constexpr int NP = C / 2;  // coarse points per lane (fine columns v0, v2, ...)
     const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -420,9 +422,10 @@ template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_up(const double *__restrict__ xb, double *__restrict__ xo, const double *__restrict__ f,
          const double *__restrict__ e, StripGeom g, int pitch_c, int lo, JacobiCoef coef, double inv_h2,
-         double *__restrict__ partials)
+         double *__restrict__ partials, const int *__restrict__ done)
 {
     using Feed = typename FeedSelect<C, PF, S, true, SM>::type;
+    if (done != nullptr && *done) return;
     static_assert(Feed::UNROLL % 2 == 0, "rows are processed in (even, odd) pairs");
     constexpr int NP = C / 2;
     const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -585,7 +588,7 @@ void set_smem(K kernel, int bytes)
 
 template <int C, int PF, int MINB, bool SM, int S>
 void down_launch(const FusedLevel &lv, double *cf, int pitch_c, double omega, bool x_is_zero, bool resid,
-                 cudaStream_t st)
+                 const int *done, cudaStream_t st)
 {
     StripGeom g = make_geom(lv.n, lv.pitch, S + (resid ? 2 : 0), VariantDesc{C, PF, MINB, SM});
     JacobiCoef c = jacobi_coef(lv.h, omega);
@@ -597,51 +600,51 @@ void down_launch(const FusedLevel &lv, double *cf, int pitch_c, double omega, bo
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv);
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done);
     } else if (resid) {
         auto k = k_down<C, PF, MINB, SM, S, false, true>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv);
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done);
     } else {
         auto k = k_down<C, PF, MINB, SM, S, false, false>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv);
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv, done);
     }
     count_launch();
 }
 
 template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM>
 void up_launch_one(const FusedLevel &lv, const double *e, int pitch_c, const StripGeom &g, int lo,
-                   const JacobiCoef &c, double inv, double *d_partials, cudaStream_t st)
+                   const JacobiCoef &c, double inv, double *d_partials, const int *done, cudaStream_t st)
 {
     auto k = k_up<C, PF, MINB, SM, S, PROLONG, NORM>;
     int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
     static bool once = (set_smem(k, sm), true);
     (void)once;
-    k<<<dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials);
+    k<<<dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials, done);
 }
 
 template <int C, int PF, int MINB, bool SM, int S>
 void up_launch(const FusedLevel &lv, const double *e, int pitch_c, double omega, int lo, bool norm,
-               double *d_partials, int *n_partials, cudaStream_t st)
+               double *d_partials, int *n_partials, const int *done, cudaStream_t st)
 {
     StripGeom g = make_geom(lv.n, lv.pitch, S + (norm ? 2 : 1), VariantDesc{C, PF, MINB, SM});
     JacobiCoef c = jacobi_coef(lv.h, omega);
     double inv = 1.0 / (lv.h * lv.h);
     if (e != nullptr) {
         if (norm)
-            up_launch_one<C, PF, MINB, SM, S, true, true>(lv, e, pitch_c, g, lo, c, inv, d_partials, st);
+            up_launch_one<C, PF, MINB, SM, S, true, true>(lv, e, pitch_c, g, lo, c, inv, d_partials, done, st);
         else
-            up_launch_one<C, PF, MINB, SM, S, true, false>(lv, e, pitch_c, g, lo, c, inv, d_partials, st);
+            up_launch_one<C, PF, MINB, SM, S, true, false>(lv, e, pitch_c, g, lo, c, inv, d_partials, done, st);
     } else {
         if (norm)
-            up_launch_one<C, PF, MINB, SM, S, false, true>(lv, e, pitch_c, g, lo, c, inv, d_partials, st);
+            up_launch_one<C, PF, MINB, SM, S, false, true>(lv, e, pitch_c, g, lo, c, inv, d_partials, done, st);
         else
-            up_launch_one<C, PF, MINB, SM, S, false, false>(lv, e, pitch_c, g, lo, c, inv, d_partials, st);
+            up_launch_one<C, PF, MINB, SM, S, false, false>(lv, e, pitch_c, g, lo, c, inv, d_partials, done, st);
     }
     count_launch();
     if (n_partials) *n_partials = norm ? g.n_strips * g.n_chunks : 0;
@@ -688,28 +691,28 @@ int fused_max_partials(int n)
     }
 
 void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int nu1, double omega,
-                       bool x_is_zero, cudaStream_t st)
+                       bool x_is_zero, cudaStream_t st, const int *done)
 {
     bool resid = coarse_f != nullptr;
     switch (nu1) {
-        case 1: down_launch<2, 3, 4, true, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
-        case 2: PMG_DISPATCH_S2(g_variant_down, down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
-        case 3: down_launch<2, 3, 4, true, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
-        case 4: down_launch<2, 2, 4, true, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, st); break;
+        case 1: down_launch<2, 3, 4, true, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
+        case 2: PMG_DISPATCH_S2(g_variant_down, down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
+        case 3: down_launch<2, 3, 4, true, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
+        case 4: down_launch<2, 2, 4, true, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         default: break;
     }
 }
 
 void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, int nu2, double omega,
-                     int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st)
+                     int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st, const int *done)
 {
     bool norm = d_partials != nullptr;
     int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
     switch (nu2) {
-        case 1: up_launch<2, 3, 4, true, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
-        case 2: PMG_DISPATCH_S2(g_variant_up, up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
-        case 3: up_launch<2, 3, 4, true, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
-        case 4: up_launch<2, 2, 4, true, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, st); break;
+        case 1: up_launch<2, 3, 4, true, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
+        case 2: PMG_DISPATCH_S2(g_variant_up, up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
+        case 3: up_launch<2, 3, 4, true, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
+        case 4: up_launch<2, 2, 4, true, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
         default: break;
     }
 }

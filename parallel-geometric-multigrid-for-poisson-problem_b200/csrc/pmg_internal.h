@@ -78,7 +78,7 @@ void launch_jacobi_sweep(double *out, const double *in, const double *f, int nx,
 constexpr int SMALL_MAX_POINTS = 33 * 33;
 // x_is_zero: start from x == 0 without reading x (first visit of a coarse level)
 void launch_jacobi_small(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h,
-                         double omega, int sweeps, bool x_is_zero, cudaStream_t st);
+                         double omega, int sweeps, bool x_is_zero, cudaStream_t st, const int *done = nullptr);
 void launch_residual(double *r, const double *x, const double *f, int nx, int ny, int pitch_r,
                      int pitch_x, int pitch_f, double h, cudaStream_t st);
 // sum over the interior of (f - A x)^2 -> *d_out (device double); `d_partials` >= reduce_partials() doubles
@@ -91,6 +91,23 @@ void launch_residual_norm2_sequential(const double *x, const double *f, int nx, 
 void launch_norm2(const double *v, size_t l, double *d_partials, double *d_out, cudaStream_t st);
 // fixed-order sum of `count` partials -> *d_out
 void launch_final_sum(const double *d_partials, int count, double *d_out, cudaStream_t st);
+
+// Device-side control block of an asynchronous solve: the last kernel of every cycle appends the residual
+// norm to the history and raises `done` when ||r|| < rel_tol * ||r0|| or the cycle budget is used up; all
+// later kernels see `done` and return immediately, so the host can queue cycles ahead without waiting.
+struct SolveCtrl {
+    double r0;        // ||r0||
+    double rel_tol;
+    int done;
+    int cycles;       // cycles completed
+    int max_cycles;
+    int pad;
+};
+// hist2[0] = *d_norm2 ; ctrl initialised
+void launch_solve_begin(const double *d_norm2, SolveCtrl *ctrl, double *hist2, double rel_tol, int max_cycles,
+                        cudaStream_t st);
+// hist2[++cycles] = fixed-order sum of the partials; convergence test (skipped when already done)
+void launch_cycle_finish(const double *d_partials, int count, SolveCtrl *ctrl, double *hist2, cudaStream_t st);
 void launch_restrict(const double *fine, double *coarse, int nf, int nc, int pitch_f, int pitch_c,
                      cudaStream_t st);
 void launch_prolong_add(const double *coarse, double *fine, int nc, int nf, int pitch_c, int pitch_f,
@@ -114,12 +131,14 @@ struct FusedLevel {
 // Pass A (down): xb = S^nu1(x);  coarse_f(interior) = R(f - A xb).  x_is_zero: the iterate is known to
 // be identically zero on entry (coarse levels of a V-cycle) so x is not read.
 bool fused_supported(int nu);
+// `done` (nullable): device flag; when set the kernel returns at once (device-side convergence control)
 void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int nu1, double omega,
-                       bool x_is_zero, cudaStream_t st);
+                       bool x_is_zero, cudaStream_t st, const int *done = nullptr);
 // Pass B (up): x = S^nu2(xb + P coarse_x); optionally sum (f - A x)^2 over the interior into partials
 // (count returned through *n_partials; reduce with launch_final_sum)
 void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, int nu2, double omega,
-                     int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st);
+                     int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st,
+                     const int *done = nullptr);
 int fused_max_partials(int n);
 // tuning: which (columns per lane, prefetch depth, CTAs per SM) instantiation the nu == 2 passes use
 int fused_num_variants();

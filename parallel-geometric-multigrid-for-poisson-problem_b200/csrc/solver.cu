@@ -60,10 +60,17 @@ struct pmg_solver {
     // F-cycle: level-0 analytic RHS lives in its own array so the caller's f survives
     double *base_f_fmg0 = nullptr, *f_fmg0 = nullptr;
     bool fmg_ready = false;
-    // CUDA graphs of one fused cycle, keyed by [kind V/W][with norm]
-    cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    int graph_kernels[2][2] = {{0, 0}, {0, 0}};  // kernel nodes per replay (launch bookkeeping)
+    // CUDA graphs of one fused cycle, keyed by [kind V/W][0: no norm, 1: norm -> d_scalar,
+    // 2: norm -> device-side solve control (asynchronous solve)]
+    cudaGraphExec_t graph[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    int graph_kernels[2][3] = {{0, 0, 0}, {0, 0, 0}};  // kernel nodes per replay (launch bookkeeping)
     bool fused = false;
+    // asynchronous solve: device control block + history of squared norms, pinned mirrors, batch events
+    SolveCtrl *d_ctrl = nullptr;
+    double *d_hist2 = nullptr;
+    int hist_cap = 0;
+    SolveCtrl *h_ctrl = nullptr;  // 2 pinned slots
+    cudaEvent_t ev_batch[2] = {nullptr, nullptr};
 };
 
 namespace pmg {
@@ -102,7 +109,7 @@ static pmg_status alloc_zero(double **p, size_t elems)
 
 // ---- smoothing on one level (Smoother::smooth, Smoother.hpp:38-116) -----------------------------------
 // Operator-granular: ping-pong sweeps; with smoother_eps > 0 the reference's per-sweep absolute-norm exit.
-static pmg_status smooth_operator(pmg_solver *s, int l, int sweeps, bool x_is_zero)
+static pmg_status smooth_operator(pmg_solver *s, int l, int sweeps, bool x_is_zero, const int *done = nullptr)
 {
     Level &L = s->lv[l];
     const pmg_config &c = s->cfg;
@@ -121,7 +128,7 @@ static pmg_status smooth_operator(pmg_solver *s, int l, int sweeps, bool x_is_ze
         return PMG_OK;
     }
     if (L.n * L.n <= SMALL_MAX_POINTS) {
-        launch_jacobi_small(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, sweeps, x_is_zero, s->stream);
+        launch_jacobi_small(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, sweeps, x_is_zero, s->stream, done);
         return PMG_OK;
     }
     for (int it = 0; it < sweeps; ++it) {
@@ -154,20 +161,22 @@ static pmg_status cycle_operator(pmg_solver *s, int l, bool w_form, bool x_is_ze
 }
 
 // The same cycle on the fused engine: two streaming passes per level visit.
-static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero, bool want_norm, int *n_partials)
+static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero, bool want_norm, int *n_partials,
+                              const int *done = nullptr)
 {
     const pmg_config &c = s->cfg;
     Level &L = s->lv[l];
-    if (L.n <= c.n_coarse || l + 1 == (int)s->lv.size()) return smooth_operator(s, l, c.coarse_sweeps, x_is_zero);
+    if (L.n <= c.n_coarse || l + 1 == (int)s->lv.size())
+        return smooth_operator(s, l, c.coarse_sweeps, x_is_zero, done);
     Level &K = s->lv[l + 1];
-    launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream);
+    launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, done);
     int reps = w_form ? c.gamma : 1;
     for (int k = 0; k < reps; ++k) {
-        pmg_status rc = cycle_fused(s, l + 1, w_form, k == 0, false, nullptr);
+        pmg_status rc = cycle_fused(s, l + 1, w_form, k == 0, false, nullptr, done);
         if (rc != PMG_OK) return rc;
     }
     launch_fused_up(fused_view(L), K.x, K.pitch, c.nu2, c.omega, c.prolong_mode,
-                    want_norm ? s->d_partials : nullptr, n_partials, s->stream);
+                    want_norm ? s->d_partials : nullptr, n_partials, s->stream, done);
     return PMG_OK;
 }
 
@@ -265,6 +274,49 @@ static pmg_status cycle_f(pmg_solver *s)
     return rc;
 }
 
+// One fused V/W cycle, replayed from a CUDA graph when allowed.  mode 0: no norm, 1: norm -> d_scalar,
+// 2: norm -> device-side solve control (k_cycle_finish) with every kernel honouring ctrl->done.
+static bool fused_graph_ok(const pmg_solver *s)
+{
+    // pointer roles are stable across a fused cycle unless the coarsest solve ping-pongs an odd count
+    const Level &Lc = s->lv.back();
+    return s->cfg.use_graph && (Lc.n * Lc.n <= SMALL_MAX_POINTS || (s->cfg.coarse_sweeps % 2) == 0);
+}
+
+static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
+{
+    bool graph_ok = fused_graph_ok(s);
+    cudaGraphExec_t &ge = s->graph[w ? 1 : 0][mode];
+    int &gk = s->graph_kernels[w ? 1 : 0][mode];
+    if (graph_ok && ge != nullptr) {
+        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+        count_launch(gk);
+        return PMG_OK;
+    }
+    unsigned long long before = launches_so_far();
+    if (graph_ok) PMG_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    int n_partials = 0;
+    const int *done = (mode == 2) ? &s->d_ctrl->done : nullptr;
+    pmg_status rc = cycle_fused(s, 0, w, false, mode != 0, &n_partials, done);
+    if (rc == PMG_OK && mode == 1) launch_final_sum(s->d_partials, n_partials, s->d_scalar, s->stream);
+    if (rc == PMG_OK && mode == 2) launch_cycle_finish(s->d_partials, n_partials, s->d_ctrl, s->d_hist2, s->stream);
+    if (graph_ok) {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        if (rc != PMG_OK) {
+            cudaGraphDestroy(g);
+            return rc;
+        }
+        // the launches counted during capture are the ones the first replay below executes
+        gk = (int)(launches_so_far() - before);
+        PMG_CUDA(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+    }
+    return rc;
+}
+
 static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
 {
     pmg_status rc;
@@ -290,36 +342,7 @@ static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
         if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
         return rc;
     }
-    // pointer roles are stable across a fused cycle unless the coarsest solve ping-pongs an odd count
-    const Level &Lc = s->lv.back();
-    bool graph_ok = s->cfg.use_graph && (Lc.n * Lc.n <= SMALL_MAX_POINTS || (s->cfg.coarse_sweeps % 2) == 0);
-    cudaGraphExec_t &ge = s->graph[w ? 1 : 0][want_norm ? 1 : 0];
-    int &gk = s->graph_kernels[w ? 1 : 0][want_norm ? 1 : 0];
-    if (graph_ok && ge != nullptr) {
-        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
-        count_launch(gk);
-        return PMG_OK;
-    }
-    unsigned long long before = launches_so_far();
-    if (graph_ok) PMG_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    int n_partials = 0;
-    rc = cycle_fused(s, 0, w, false, want_norm, &n_partials);
-    if (rc == PMG_OK && want_norm) launch_final_sum(s->d_partials, n_partials, s->d_scalar, s->stream);
-    if (graph_ok) {
-        cudaGraph_t g = nullptr;
-        cudaError_t e = cudaStreamEndCapture(s->stream, &g);
-        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-        if (rc != PMG_OK) {
-            cudaGraphDestroy(g);
-            return rc;
-        }
-        // the launches counted during capture are the ones the first replay below executes
-        gk = (int)(launches_so_far() - before);
-        PMG_CUDA(cudaGraphInstantiate(&ge, g, 0));
-        cudaGraphDestroy(g);
-        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
-    }
-    return rc;
+    return run_fused_graph(s, w, want_norm ? 1 : 0);
 }
 
 }  // namespace pmg
@@ -450,6 +473,14 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     if ((rc = alloc_zero(&s->d_scalar, 2)) != PMG_OK) return bail(rc);
     if (cudaMallocHost((void **)&s->h_scalar, 2 * sizeof(double)) != cudaSuccess)
         return bail(fail(PMG_ERR_ALLOC, "cudaMallocHost failed"));
+    if (cudaMalloc((void **)&s->d_ctrl, sizeof(SolveCtrl)) != cudaSuccess ||
+        cudaMemset(s->d_ctrl, 0, sizeof(SolveCtrl)) != cudaSuccess ||
+        cudaMallocHost((void **)&s->h_ctrl, 2 * sizeof(SolveCtrl)) != cudaSuccess)
+        return bail(fail(PMG_ERR_ALLOC, "solve-control allocation failed"));
+    s->hist_cap = 256;
+    if ((rc = alloc_zero(&s->d_hist2, (size_t)s->hist_cap)) != PMG_OK) return bail(rc);
+    cudaEventCreateWithFlags(&s->ev_batch[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_batch[1], cudaEventDisableTiming);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(PMG_ERR_CUDA, "device synchronize failed"));
     *out = s;
     return PMG_OK;
@@ -472,6 +503,11 @@ void pmg_destroy(pmg_solver *s)
     cudaFree(s->d_partials);
     cudaFree(s->d_scalar);
     if (s->h_scalar) cudaFreeHost(s->h_scalar);
+    cudaFree(s->d_ctrl);
+    cudaFree(s->d_hist2);
+    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    for (auto &e : s->ev_batch)
+        if (e) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -568,11 +604,73 @@ pmg_status pmg_cycle(pmg_solver *s, pmg_cycle_kind kind, double *res_norm_out)
     return PMG_OK;
 }
 
+/* Fused V/W solve with device-side convergence control: cycles are queued one batch ahead of the host's
+ * knowledge of the residual, the last kernel of each cycle records ||r||^2 and raises `done`, and every
+ * kernel queued after that returns at once.  The GPU never waits for the host between cycles. */
+static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int max_cycles, double *res_history,
+                                    int *n_cycles_out)
+{
+    if (max_cycles + 1 > s->hist_cap) {
+        if (s->d_hist2) cudaFree(s->d_hist2);
+        s->d_hist2 = nullptr;
+        s->hist_cap = max_cycles + 1 + 64;
+        pmg_status rc = alloc_zero(&s->d_hist2, (size_t)s->hist_cap);
+        if (rc != PMG_OK) return rc;
+        drop_graphs(s);  // the captured graphs hold the old history pointer
+    }
+    Level &L = s->lv[0];
+    PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    launch_residual_norm2(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
+    launch_solve_begin(s->d_scalar, s->d_ctrl, s->d_hist2, rel_tol, max_cycles, s->stream);
+    // enough queued work to cover a host round trip: one cycle on big grids, a few on small ones
+    const int batch = L.n >= 2049 ? 1 : (L.n >= 513 ? 2 : 4);
+    int queued = 0, slot = 0;
+    bool pending[2] = {false, false};
+    bool finished = false;
+    while (!finished) {
+        int b = std::min(batch, max_cycles - queued);
+        for (int i = 0; i < b; ++i) {
+            pmg_status rc = run_fused_graph(s, w, 2);
+            if (rc != PMG_OK) return rc;
+        }
+        queued += b;
+        PMG_CUDA(cudaMemcpyAsync(&s->h_ctrl[slot], s->d_ctrl, sizeof(SolveCtrl), cudaMemcpyDeviceToHost, s->stream));
+        PMG_CUDA(cudaEventRecord(s->ev_batch[slot], s->stream));
+        pending[slot] = true;
+        int prev = slot ^ 1;
+        if (pending[prev]) {  // look at the batch before this one while this one runs
+            PMG_CUDA(cudaEventSynchronize(s->ev_batch[prev]));
+            pending[prev] = false;
+            if (s->h_ctrl[prev].done) finished = true;
+        }
+        if (queued >= max_cycles || b == 0) finished = true;
+        slot ^= 1;
+    }
+    PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    PMG_CUDA(cudaMemcpyAsync(&s->h_ctrl[0], s->d_ctrl, sizeof(SolveCtrl), cudaMemcpyDeviceToHost, s->stream));
+    PMG_CUDA(cudaStreamSynchronize(s->stream));
+    PMG_CUDA(cudaGetLastError());
+    int k = s->h_ctrl[0].cycles;
+    if (res_history) {
+        std::vector<double> h2((size_t)k + 1);
+        PMG_CUDA(cudaMemcpy(h2.data(), s->d_hist2, ((size_t)k + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i <= k; ++i) res_history[i] = std::sqrt(h2[i]);
+    }
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    if (n_cycles_out) *n_cycles_out = k;
+    return PMG_OK;
+}
+
 pmg_status pmg_solve(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max_cycles, double *res_history,
                      int *n_cycles_out)
 {
     if (!s || max_cycles < 0) return fail(PMG_ERR_INVALID, "bad argument");
     PMG_CUDA(cudaSetDevice(s->device));
+    if (s->fused && (kind == PMG_CYCLE_V || kind == PMG_CYCLE_W) && s->cfg.norm_mode == PMG_NORM_TREE &&
+        s->lv.size() > 1 && s->lv[0].n > s->cfg.n_coarse && fused_graph_ok(s))
+        return solve_fused_async(s, kind == PMG_CYCLE_W, rel_tol, max_cycles, res_history, n_cycles_out);
     PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
     residual_norm2_async(s);
     double v = 0.0;
