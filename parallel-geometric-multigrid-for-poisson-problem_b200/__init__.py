@@ -108,6 +108,8 @@ def lib():
     L.pmg_host_free_pinned.argtypes = [vp]
     L.pmg_memcpy.argtypes = [vp, vp, sz, i, i]
     L.pmg_partition_rows.argtypes = [i, i, i, pi, pi]
+    L.pmg_comm_unique_id.argtypes = [ctypes.c_char_p]
+    L.pmg_comm_init.argtypes = [ctypes.c_char_p, i, i, i]
     L.pmg_smooth.argtypes = [vp, i, i]
     L.pmg_bench_pass.argtypes = [vp, i, i, i, pd]
     L.pmg_fused_set_variant.restype = None
@@ -146,6 +148,40 @@ def partition_rows(n, n_ranks, rank):
     y0, y1 = ctypes.c_int(), ctypes.c_int()
     check(lib().pmg_partition_rows(n, n_ranks, rank, ctypes.byref(y0), ctypes.byref(y1)))
     return y0.value, y1.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """128 opaque bytes made by one rank; ship them to the others (e.g. torch.distributed.broadcast)."""
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    check(lib().pmg_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(unique_id, rank, n_ranks, device):
+    """Collective: creates this process's NCCL communicator (one process per GPU)."""
+    assert len(unique_id) == COMM_ID_BYTES
+    check(lib().pmg_comm_init(ctypes.create_string_buffer(unique_id, COMM_ID_BYTES), rank, n_ranks, device))
+
+
+def comm_finalize():
+    lib().pmg_comm_finalize()
+
+
+def init_distributed_from_torch(device=None):
+    """Bootstrap from an initialised torch.distributed process group (the plumbing only: the id travels
+    over it once; all solver traffic then goes through libpmg's own NCCL communicator)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", rank))
+    ids = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm_init(ids[0], rank, world, device)
+    return rank, world, device
 
 
 class DeviceArray:
@@ -232,9 +268,17 @@ class Solver:
     def zero_guess(self):
         check(lib().pmg_zero_guess(self._h))
 
+    @property
+    def local_rows(self):
+        """(y0, y1): the rows of the finest level this rank owns (the whole grid on one GPU)."""
+        if self.cfg.n_ranks > 1:
+            return partition_rows(self.n, self.cfg.n_ranks, self.cfg.rank)
+        return 0, self.n
+
     def get_solution(self, out=None):
         if out is None:
-            out = np.empty((self.n, self.n))
+            y0, y1 = self.local_rows
+            out = np.empty((y1 - y0, self.n))
         p, m = _ptr_and_mem(out)
         check(lib().pmg_get_solution(self._h, p, m))
         return out

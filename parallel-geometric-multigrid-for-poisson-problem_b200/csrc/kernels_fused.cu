@@ -42,7 +42,11 @@ constexpr int WARPS_PER_CTA = 4;
 __host__ __device__ constexpr int halo_for(int stages) { return stages <= 4 ? 4 : 8; }
 
 struct StripGeom {
-    int n;           // logical points per side
+    int n;           // GLOBAL points per side (columns of this slab; rows of the whole level)
+    int ny;          // rows of this slab that the rank owns (== n on one GPU)
+    int yoff;        // global row index of local row 0 (even; 0 on one GPU)
+    int ext_lo;      // the iterate is also written for local rows [-ext_lo, 0) and [ny, ny + ext_hi):
+    int ext_hi;      //   redundant work on halo rows that saves a halo exchange (even; 0 on one GPU)
     int pitch;       // row pitch of x / xb / f (doubles)
     int n_strips;    // strips across
     int n_chunks;    // row chunks
@@ -162,8 +166,8 @@ __device__ __forceinline__ void strip_setup(const StripGeom &g, int wid, int lan
     int chunk = wid / g.n_strips;
     int strip = wid - chunk * g.n_strips;
     col = -g.halo + strip * g.stride + C * lane;
-    r0 = chunk * g.chunk_rows;
-    r1 = min(r0 + g.chunk_rows, g.n);
+    r0 = -g.ext_lo + chunk * g.chunk_rows;
+    r1 = min(r0 + g.chunk_rows, g.ny + g.ext_hi);
     int first_owner = g.halo / C;
     owner = (lane >= first_owner) && (lane < first_owner + g.stride / C);
 #pragma unroll
@@ -321,9 +325,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     bool owner, cin[C];
     strip_setup<C>(g, wid, lane, col, r0, r1, owner, cin);
 
-    const int lead = RESID ? 2 : 0;  // extra finished rows needed above the chunk
-    const int j_start = r0 - lead - S;
-    const int j_end = r1 - 1 + (RESID ? 1 : 0) + S;  // inclusive
+    // Rows this chunk must finish: x_S on [r0, r1) and, for the coarse rows it owns (fine row 2jc inside
+    // the chunk AND inside the slab), r on [2jc-1, 2jc+1], i.e. x_S two rows earlier and one row later.
+    const int lead = RESID ? 2 : 0;
+    const int j_start = min(r0, max(r0, 0) - lead) - S;
+    const int j_end = max(r1 - 1, min(r1, g.ny) - 1 + (RESID ? 1 : 0)) + S;  // inclusive
 
     SweepStage<C> st[S];
     ResidualStage<C> rs;
@@ -337,7 +343,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     for (int q = 0; q < NP; ++q) s_mid[q] = s_cor[q] = c_mid[q] = c_ew[q] = 0.0;
 
     Feed feed;
-    feed.init(x, f, g.pitch, col, j_start, g.n + PADY - 1, lane, threadIdx.x >> 5);
+    feed.init(x, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5);
+    const int ycoarse = g.yoff >> 1;  // global coarse row of local coarse row 0
 
     for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
 #pragma unroll
@@ -347,7 +354,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             // sweeps: stage k consumes x_k row jj-k and finishes x_{k+1} row jj-k-1
 #pragma unroll
             for (int k = 0; k < S; ++k) {
-                const int out_row = jj - k - 1;
+                const int out_row = jj - k - 1 + g.yoff;  // global row
                 cur = st[k].step(cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
             }
             // cur = x_S row jj - S
@@ -373,7 +380,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                         s_mid[q] = r.v[2 * q];
                         s_cor[q] = dadd(west, r.v[2 * q + 1]);
                     }
-                    if (owner && jc >= 1 && jc < nc - 1 && 2 * jc >= r0 && 2 * jc < r1) {
+                    // stored by the chunk and the rank that own fine row 2jc; coarse ring rows stay zero
+                    if (owner && jc + ycoarse >= 1 && jc + ycoarse < nc - 1 && 2 * jc >= r0 && 2 * jc < r1 &&
+                        jc >= 0 && 2 * jc < g.ny) {
                         double *dst = cf + (ptrdiff_t)jc * pitch_c + ic;
                         if (NP == 2)
                             *reinterpret_cast<double2 *>(dst) = make_double2(o[0], o[NP - 1]);
@@ -452,11 +461,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     for (int k = 0; k < C; ++k) cprol[k] = (col + k >= lo) && (col + k <= g.n - 2);
 
     Feed feed;
-    feed.init(xb, f, g.pitch, col, j_start, g.n + PADY - 1, lane, threadIdx.x >> 5);
+    feed.init(xb, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5);
 
     // coarse rows: ec = row jc, en = row jc+1, eb = prefetch of row jc+2 (raw, before the shuffle)
     const int cc = col >> 1;
-    const int nc_last_row = ((g.n - 1) >> 1) + PADY;  // last coarse row in the allocation
+    const int nc_last_row = ((g.ny - 1) >> 1) + PADY;  // last local coarse row in the allocation
     CoarseRow<C> ec, en, eb;
 #pragma unroll
     for (int q = 0; q <= NP; ++q) ec.v[q] = en.v[q] = eb.v[q] = 0.0;
@@ -473,7 +482,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             const int jj = j + u;  // u even: fine row 2jc, u odd: fine row 2jc+1
             Row<C> cur = feed.begin(u, jj);
             if (PROLONG) {
-                const bool rowp = (jj >= lo) && (jj <= g.n - 2);
+                const bool rowp = (jj + g.yoff >= lo) && (jj + g.yoff <= g.n - 2);
                 double corr[C];
                 if ((u & 1) == 0) {
                     // coarse row jc+1 arrives (loaded one pair ago); fetch jc+2 for the next pair
@@ -501,7 +510,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             }
 #pragma unroll
             for (int k = 0; k < S; ++k) {
-                const int out_row = jj - k - 1;
+                const int out_row = jj - k - 1 + g.yoff;
                 cur = st[k].step(cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
             }
             const int xrow = jj - S;
@@ -509,7 +518,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             if (NORM) {
                 Row<C> r = rs.step(cur, feed.f_row(S + 1), inv_h2);
                 const int rrow = jj - S - 1;
-                if (owner && rrow >= r0 && rrow < r1 && rrow > 0 && rrow < g.n - 1) {
+                if (owner && rrow >= r0 && rrow < r1 && rrow >= 0 && rrow < g.ny && rrow + g.yoff > 0 &&
+                    rrow + g.yoff < g.n - 1) {
 #pragma unroll
                     for (int k = 0; k < C; ++k)
                         if (cin[k]) acc = dadd(acc, dmul(r.v[k], r.v[k]));
@@ -554,11 +564,16 @@ int num_sms()
     return g_num_sms;
 }
 
-StripGeom make_geom(int n, int pitch, int stages, const VariantDesc &v)
+StripGeom make_geom(const FusedLevel &lv, int stages, const VariantDesc &v, int ext_lo, int ext_hi)
 {
+    const int n = lv.n;
     StripGeom g;
     g.n = n;
-    g.pitch = pitch;
+    g.ny = lv.ny > 0 ? lv.ny : n;
+    g.yoff = lv.ny > 0 ? lv.yoff : 0;
+    g.ext_lo = ext_lo;
+    g.ext_hi = ext_hi;
+    g.pitch = lv.pitch;
     g.halo = halo_for(stages);
     g.stride = 32 * v.c - 2 * g.halo;
     g.n_strips = (n + g.stride - 1) / g.stride;
@@ -566,11 +581,12 @@ StripGeom make_geom(int n, int pitch, int stages, const VariantDesc &v)
     int resident = num_sms() * v.minb * WARPS_PER_CTA;
     int chunks = resident / g.n_strips;
     if (chunks < 1) chunks = 1;
-    int rows = (n + chunks - 1) / chunks;
+    const int span = g.ny + ext_lo + ext_hi;  // rows the pass writes
+    int rows = (span + chunks - 1) / chunks;
     rows += rows & 1;
     if (rows < g_min_chunk_rows) rows = g_min_chunk_rows;
     g.chunk_rows = rows;
-    g.n_chunks = (n + rows - 1) / rows;
+    g.n_chunks = (span + rows - 1) / rows;
     return g;
 }
 
@@ -590,7 +606,7 @@ template <int C, int PF, int MINB, bool SM, int S>
 void down_launch(const FusedLevel &lv, double *cf, int pitch_c, double omega, bool x_is_zero, bool resid,
                  const int *done, cudaStream_t st)
 {
-    StripGeom g = make_geom(lv.n, lv.pitch, S + (resid ? 2 : 0), VariantDesc{C, PF, MINB, SM});
+    StripGeom g = make_geom(lv, S + (resid ? 2 : 0), VariantDesc{C, PF, MINB, SM}, lv.ext_lo, lv.ext_hi);
     JacobiCoef c = jacobi_coef(lv.h, omega);
     double inv = 1.0 / (lv.h * lv.h);
     int nc = (lv.n - 1) / 2 + 1;
@@ -632,7 +648,7 @@ template <int C, int PF, int MINB, bool SM, int S>
 void up_launch(const FusedLevel &lv, const double *e, int pitch_c, double omega, int lo, bool norm,
                double *d_partials, int *n_partials, const int *done, cudaStream_t st)
 {
-    StripGeom g = make_geom(lv.n, lv.pitch, S + (norm ? 2 : 1), VariantDesc{C, PF, MINB, SM});
+    StripGeom g = make_geom(lv, S + (norm ? 2 : 1), VariantDesc{C, PF, MINB, SM}, lv.ext_lo, lv.ext_hi);
     JacobiCoef c = jacobi_coef(lv.h, omega);
     double inv = 1.0 / (lv.h * lv.h);
     if (e != nullptr) {
@@ -669,10 +685,13 @@ void fused_set_min_chunk_rows(int r) { g_min_chunk_rows = (r >= 2) ? (r + (r & 1
 int fused_max_partials(int n)
 {
     int best = 0;
+    FusedLevel lv{};
+    lv.n = n;
+    lv.pitch = level_pitch(n);
     for (int v = 0; v < NUM_VARIANTS; ++v) {
-        StripGeom g = make_geom(n, level_pitch(n), 8, VARIANTS[v]);
+        StripGeom g = make_geom(lv, 8, VARIANTS[v], 8, 8);
         int c = g.n_strips * g.n_chunks;
-        g = make_geom(n, level_pitch(n), 4, VARIANTS[v]);
+        g = make_geom(lv, 4, VARIANTS[v], 8, 8);
         if (g.n_strips * g.n_chunks > c) c = g.n_strips * g.n_chunks;
         if (c > best) best = c;
     }

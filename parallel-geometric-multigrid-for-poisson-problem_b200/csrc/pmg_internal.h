@@ -127,6 +127,9 @@ struct FusedLevel {
     const double *f;
     int n, pitch;
     double h;
+    // row slab of a level partitioned over ranks (all zero on one GPU): the arrays hold local rows
+    // [-PADY, ny + PADY); local row 0 is global row yoff.  ext_lo/ext_hi: see StripGeom.
+    int ny, yoff, ext_lo, ext_hi;
 };
 // Pass A (down): xb = S^nu1(x);  coarse_f(interior) = R(f - A xb).  x_is_zero: the iterate is known to
 // be identically zero on entry (coarse levels of a V-cycle) so x is not read.
@@ -145,5 +148,16 @@ int fused_num_variants();
 void fused_set_variant(int v);
 int fused_get_variant();
 void fused_set_min_chunk_rows(int r);
+
+// ---- multi-GPU plumbing (comm.cu): no-ops returning PMG_OK while no communicator exists ---------------
+bool comm_ready();
+int comm_rank();
+int comm_size();
+pmg_status comm_halo_exchange(double *p, int ny, int pitch, int depth, cudaStream_t st);
+pmg_status comm_gather_rows(const double *slab, double *full, int pitch, const int *y0s, const int *y1s,
+                            cudaStream_t st);
+pmg_status comm_scatter_rows(const double *full, double *slab, int n_rows, int pitch, const int *y0s,
+                             const int *y1s, int halo, cudaStream_t st);
+pmg_status comm_allgather_double(const double *d_mine, double *d_all, cudaStream_t st);
 
 }  // namespace pmg

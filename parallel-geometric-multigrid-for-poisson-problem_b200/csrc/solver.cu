@@ -35,6 +35,7 @@ static bool is_pow2_plus_1(int n) { return n >= 3 && ((n - 1) & (n - 2)) == 0; }
 
 struct Level {
     int n = 0, pitch = 0;
+    int ny = 0, y0 = 0;  // row slab [y0, y0 + ny) of a level partitioned over ranks; ny == 0: whole level
     double h = 0.0;
     size_t elems = 0;
     double *base_x = nullptr, *base_xb = nullptr, *base_f = nullptr, *base_r = nullptr;
@@ -71,6 +72,15 @@ struct pmg_solver {
     int hist_cap = 0;
     SolveCtrl *h_ctrl = nullptr;  // 2 pinned slots
     cudaEvent_t ev_batch[2] = {nullptr, nullptr};
+    // ---- row-slab decomposition over ranks (one process per GPU) ----
+    // lv[l] for l < agg_level are SLABS (ny > 0); lv[l] for l >= agg_level are whole levels that only rank 0
+    // works on ("agglomerated"); `aslab` is the slab-shaped window of level agg_level the finest
+    // agglomerated level is gathered from / scattered to.
+    bool dist = false;
+    int rank = 0, n_ranks = 1, agg_level = 0;
+    Level aslab;
+    std::vector<std::vector<int>> y0s, y1s;  // [level <= agg_level][rank]
+    double *d_gather = nullptr;              // one double per rank (norm all-gather)
 };
 
 namespace pmg {
@@ -94,6 +104,9 @@ static FusedLevel fused_view(const Level &L)
     v.n = L.n;
     v.pitch = L.pitch;
     v.h = L.h;
+    v.ny = L.ny;
+    v.yoff = L.y0;
+    v.ext_lo = v.ext_hi = 0;
     return v;
 }
 
@@ -180,8 +193,68 @@ static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero,
     return PMG_OK;
 }
 
+// Row extension of a pass on a slab: ranks recompute `e` halo rows next to each neighbour instead of
+// exchanging them (none at the global top / bottom, where the zero padding rows play that role).
+static FusedLevel slab_view(const pmg_solver *s, const Level &L, int e)
+{
+    FusedLevel v = fused_view(L);
+    v.ext_lo = (s->rank > 0) ? e : 0;
+    v.ext_hi = (s->rank < s->n_ranks - 1) ? e : 0;
+    return v;
+}
+
+// The fused cycle on row slabs.  Per level visit: ONE halo exchange of PADY rows on
+// the way down (the iterate on the finest level / on repeated W visits, the restricted right-hand side on a
+// first visit) and none on the way up -- Pass A also finishes 6 halo rows of xb, Pass B 4 halo rows of x,
+// which is exactly what the parent's prolongation and this level's second pass read.
+static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, bool want_norm, int *n_partials,
+                             const int *done)
+{
+    const pmg_config &c = s->cfg;
+    Level &L = s->lv[l];
+    const bool last_slab = (l + 1 == s->agg_level);
+    Level &K = last_slab ? s->aslab : s->lv[l + 1];
+    pmg_status rc;
+    if (!x_is_zero && (rc = comm_halo_exchange(L.x, L.ny, L.pitch, PADY, s->stream)) != PMG_OK) return rc;
+    if (l > 0 && x_is_zero && (rc = comm_halo_exchange(L.f, L.ny, L.pitch, PADY, s->stream)) != PMG_OK) return rc;
+    launch_fused_down(slab_view(s, L, 6), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, done);
+    int reps = w_form ? c.gamma : 1;
+    if (!last_slab) {
+        for (int k = 0; k < reps; ++k)
+            if ((rc = cycle_dist(s, l + 1, w_form, k == 0, false, nullptr, done)) != PMG_OK) return rc;
+    } else {
+        Level &A = s->lv[s->agg_level];
+        const int *y0 = s->y0s[s->agg_level].data(), *y1 = s->y1s[s->agg_level].data();
+        if ((rc = comm_gather_rows(K.f, A.f, A.pitch, y0, y1, s->stream)) != PMG_OK) return rc;
+        if (s->rank == 0)
+            for (int k = 0; k < reps; ++k)
+                if ((rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, done)) != PMG_OK) return rc;
+        if ((rc = comm_scatter_rows(A.x, K.x, A.n, A.pitch, y0, y1, 4, s->stream)) != PMG_OK) return rc;
+    }
+    launch_fused_up(slab_view(s, L, l == 0 ? 0 : 4), K.x, K.pitch, c.nu2, c.omega, c.prolong_mode,
+                    want_norm ? s->d_partials : nullptr, n_partials, s->stream, done);
+    return PMG_OK;
+}
+
+// sum over this rank's owned interior rows of (f - A x)^2 -> d_scalar[0], then the rank-ordered global sum
+static pmg_status dist_residual_norm2(pmg_solver *s)
+{
+    Level &L = s->lv[0];
+    pmg_status rc = comm_halo_exchange(L.x, L.ny, L.pitch, PADY, s->stream);
+    if (rc != PMG_OK) return rc;
+    int ga = std::max(L.y0, 1), gb = std::min(L.y0 + L.ny, L.n - 1);  // owned interior rows [ga, gb)
+    int a = ga - L.y0, b = gb - L.y0;
+    // a window whose own "ring" rows are local rows a-1 and b
+    launch_residual_norm2(L.x + (ptrdiff_t)(a - 1) * L.pitch, L.f + (ptrdiff_t)(a - 1) * L.pitch, L.n, b - a + 2,
+                          L.pitch, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
+    if ((rc = comm_allgather_double(s->d_scalar, s->d_gather, s->stream)) != PMG_OK) return rc;
+    launch_final_sum(s->d_gather, s->n_ranks, s->d_scalar, s->stream);
+    return PMG_OK;
+}
+
 static pmg_status residual_norm2_async(pmg_solver *s)
 {
+    if (s->dist) return dist_residual_norm2(s);
     Level &L = s->lv[0];
     if (s->cfg.norm_mode == PMG_NORM_SEQUENTIAL)
         launch_residual_norm2_sequential(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_scalar, s->stream);
@@ -285,6 +358,20 @@ static bool fused_graph_ok(const pmg_solver *s)
 
 static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
 {
+    if (s->dist) {
+        // direct launches (NCCL calls sit between the kernels); norms are combined in rank order
+        int np = 0;
+        const int *done = (mode == 2) ? &s->d_ctrl->done : nullptr;
+        pmg_status rc = cycle_dist(s, 0, w, false, mode != 0, &np, done);
+        if (rc != PMG_OK || mode == 0) return rc;
+        launch_final_sum(s->d_partials, np, s->d_scalar, s->stream);
+        if ((rc = comm_allgather_double(s->d_scalar, s->d_gather, s->stream)) != PMG_OK) return rc;
+        if (mode == 1)
+            launch_final_sum(s->d_gather, s->n_ranks, s->d_scalar, s->stream);
+        else
+            launch_cycle_finish(s->d_gather, s->n_ranks, s->d_ctrl, s->d_hist2, s->stream);
+        return PMG_OK;
+    }
     bool graph_ok = fused_graph_ok(s);
     cudaGraphExec_t &ge = s->graph[w ? 1 : 0][mode];
     int &gk = s->graph_kernels[w ? 1 : 0][mode];
@@ -320,6 +407,7 @@ static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
 static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
 {
     pmg_status rc;
+    if (s->dist && kind == PMG_CYCLE_F) return fail(PMG_ERR_UNSUPPORTED, "the F-cycle is single-GPU only");
     if (kind == PMG_CYCLE_F) {
         rc = cycle_f(s);
         if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
@@ -337,7 +425,7 @@ static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
         if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
         return rc;
     }
-    if ((int)s->lv.size() == 1 || s->lv[0].n <= s->cfg.n_coarse) {
+    if (!s->dist && ((int)s->lv.size() == 1 || s->lv[0].n <= s->cfg.n_coarse)) {
         rc = cycle_fused(s, 0, w, false, false, nullptr);
         if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
         return rc;
@@ -416,7 +504,15 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     if (!(cfg->omega > 0.0)) return fail(PMG_ERR_INVALID, "omega must be positive");
     if (cfg->norm_mode != PMG_NORM_TREE && cfg->norm_mode != PMG_NORM_SEQUENTIAL)
         return fail(PMG_ERR_INVALID, "bad norm_mode");
-    if (cfg->n_ranks > 1) return fail(PMG_ERR_UNSUPPORTED, "multi-GPU solver handles are created with pmg_dist_create");
+    const bool dist = cfg->n_ranks > 1;
+    if (dist) {
+        if (!comm_ready() || comm_size() != cfg->n_ranks || comm_rank() != cfg->rank)
+            return fail(PMG_ERR_INVALID, "n_ranks > 1 needs pmg_comm_init with the same rank / n_ranks first");
+        if (cfg->engine != PMG_ENGINE_FUSED || !(cfg->nu1 >= 1 && cfg->nu1 <= 2 && cfg->nu2 >= 1 && cfg->nu2 <= 2) ||
+            cfg->smoother_eps > 0.0 || cfg->norm_mode != PMG_NORM_TREE)
+            return fail(PMG_ERR_UNSUPPORTED,
+                        "multi-GPU: fused engine, 1-2 pre/post sweeps, smoother_eps = 0 and the tree norm only");
+    }
     int ndev = pmg_device_count();
     if (ndev <= 0) return fail(PMG_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
     int dev = cfg->device;
@@ -453,6 +549,43 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         L.elems = level_elems(n);
         s->lv.push_back(L);
         if (n <= cfg->n_coarse || n <= 3) break;
+    }
+    if (dist) {
+        s->dist = true;
+        s->rank = cfg->rank;
+        s->n_ranks = cfg->n_ranks;
+        // levels stay partitioned while every rank keeps >= 4*PADY rows and the level is above the threshold
+        int la = 0;
+        const int nl = (int)s->lv.size();
+        while (la < nl - 1 && s->lv[la].n > cfg->agglomerate_below && ((s->lv[la].n - 1) / 2) / cfg->n_ranks * 2 >= 4 * PADY)
+            ++la;
+        if (la == 0) return bail(fail(PMG_ERR_UNSUPPORTED, "grid too small to partition over n_ranks (or agglomerate_below >= n)"));
+        s->agg_level = la;
+        s->y0s.resize(la + 1);
+        s->y1s.resize(la + 1);
+        for (int l = 0; l <= la; ++l) {
+            s->y0s[l].resize(cfg->n_ranks);
+            s->y1s[l].resize(cfg->n_ranks);
+            for (int r = 0; r < cfg->n_ranks; ++r) pmg_partition_rows(s->lv[l].n, cfg->n_ranks, r, &s->y0s[l][r], &s->y1s[l][r]);
+            if (l > 0)  // the coarse partition must be the fine one halved (coarse row jc lives with fine row 2jc)
+                for (int r = 0; r < cfg->n_ranks; ++r)
+                    if (s->y0s[l][r] * 2 != s->y0s[l - 1][r])
+                        return bail(fail(PMG_ERR_UNSUPPORTED, "row partition does not nest across levels for this n / n_ranks"));
+        }
+        auto slab_shape = [&](Level &L, int l) {
+            L.y0 = s->y0s[l][cfg->rank];
+            L.ny = s->y1s[l][cfg->rank] - L.y0;
+            L.elems = (size_t)L.pitch * (size_t)(L.ny + 2 * PADY);
+        };
+        for (int l = 0; l < la; ++l) slab_shape(s->lv[l], l);
+        s->aslab = s->lv[la];
+        slab_shape(s->aslab, la);
+        Level &A = s->aslab;
+        if ((rc = alloc_zero(&A.base_x, A.elems)) != PMG_OK) return bail(rc);
+        if ((rc = alloc_zero(&A.base_f, A.elems)) != PMG_OK) return bail(rc);
+        A.x = A.base_x + level_origin(A.n);
+        A.f = A.base_f + level_origin(A.n);
+        if ((rc = alloc_zero(&s->d_gather, (size_t)cfg->n_ranks)) != PMG_OK) return bail(rc);
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
@@ -500,6 +633,9 @@ void pmg_destroy(pmg_solver *s)
         cudaFree(L.d_sin);
     }
     cudaFree(s->base_f_fmg0);
+    cudaFree(s->aslab.base_x);
+    cudaFree(s->aslab.base_f);
+    cudaFree(s->d_gather);
     cudaFree(s->d_partials);
     cudaFree(s->d_scalar);
     if (s->h_scalar) cudaFreeHost(s->h_scalar);
@@ -514,14 +650,20 @@ void pmg_destroy(pmg_solver *s)
     delete s;
 }
 
+// With n_ranks > 1 every rank passes ITS OWN ROWS [y0, y1) of the field (ny x n doubles, dense).
 static pmg_status copy_in(pmg_solver *s, double *dst_logical, const double *src, pmg_mem where)
 {
     if (!s || !src) return fail(PMG_ERR_INVALID, "null argument");
     const Level &L = s->lv[0];
+    const int rows = s->dist ? L.ny : L.n;
     PMG_CUDA(cudaSetDevice(s->device));
     PMG_CUDA(cudaMemcpy2DAsync(dst_logical, (size_t)L.pitch * sizeof(double), src, (size_t)L.n * sizeof(double),
-                               (size_t)L.n * sizeof(double), (size_t)L.n,
+                               (size_t)L.n * sizeof(double), (size_t)rows,
                                where == PMG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s->stream));
+    if (s->dist) {
+        pmg_status rc = comm_halo_exchange(dst_logical, L.ny, L.pitch, PADY, s->stream);
+        if (rc != PMG_OK) return rc;
+    }
     PMG_CUDA(cudaStreamSynchronize(s->stream));
     return PMG_OK;
 }
@@ -542,7 +684,7 @@ pmg_status pmg_get_solution(pmg_solver *s, double *phi, pmg_mem where)
     const Level &L = s->lv[0];
     PMG_CUDA(cudaSetDevice(s->device));
     PMG_CUDA(cudaMemcpy2DAsync(phi, (size_t)L.n * sizeof(double), L.x, (size_t)L.pitch * sizeof(double),
-                               (size_t)L.n * sizeof(double), (size_t)L.n,
+                               (size_t)L.n * sizeof(double), (size_t)(s->dist ? L.ny : L.n),
                                where == PMG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s->stream));
     PMG_CUDA(cudaStreamSynchronize(s->stream));
     return PMG_OK;
@@ -563,7 +705,16 @@ pmg_status pmg_set_rhs_sine(pmg_solver *s)
     PMG_CUDA(cudaSetDevice(s->device));
     pmg_status rc = ensure_fmg(s);
     if (rc != PMG_OK) return rc;
-    analytic_rhs(s, s->lv[0], s->lv[0].f);
+    if (s->dist) {
+        const Level &L = s->lv[0];
+        int ga = std::max(L.y0 - PADY, 0), gb = std::min(L.y0 + L.ny + PADY, L.n);  // rows incl. halo
+        const double a = 1.0, p = 1.0, q = 1.0;
+        double factor = (M_PI * M_PI / (a * a)) * (p * p + q * q);
+        launch_rhs_separable(L.f + (ptrdiff_t)(ga - L.y0) * L.pitch, L.pitch, L.n, gb - ga, factor, L.d_sin,
+                             L.d_sin + ga, s->stream);
+    } else {
+        analytic_rhs(s, s->lv[0], s->lv[0].f);
+    }
     PMG_CUDA(cudaStreamSynchronize(s->stream));
     PMG_CUDA(cudaGetLastError());
     return PMG_OK;
@@ -620,7 +771,10 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
     }
     Level &L = s->lv[0];
     PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
-    launch_residual_norm2(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
+    {
+        pmg_status rc0 = residual_norm2_async(s);
+        if (rc0 != PMG_OK) return rc0;
+    }
     launch_solve_begin(s->d_scalar, s->d_ctrl, s->d_hist2, rel_tol, max_cycles, s->stream);
     // enough queued work to cover a host round trip: one cycle on big grids, a few on small ones
     const int batch = L.n >= 2049 ? 1 : (L.n >= 513 ? 2 : 4);
@@ -668,8 +822,9 @@ pmg_status pmg_solve(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max
 {
     if (!s || max_cycles < 0) return fail(PMG_ERR_INVALID, "bad argument");
     PMG_CUDA(cudaSetDevice(s->device));
+    if (s->dist && kind == PMG_CYCLE_F) return fail(PMG_ERR_UNSUPPORTED, "the F-cycle is single-GPU only");
     if (s->fused && (kind == PMG_CYCLE_V || kind == PMG_CYCLE_W) && s->cfg.norm_mode == PMG_NORM_TREE &&
-        s->lv.size() > 1 && s->lv[0].n > s->cfg.n_coarse && fused_graph_ok(s))
+        s->lv.size() > 1 && s->lv[0].n > s->cfg.n_coarse && (s->dist || fused_graph_ok(s)))
         return solve_fused_async(s, kind == PMG_CYCLE_W, rel_tol, max_cycles, res_history, n_cycles_out);
     PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
     residual_norm2_async(s);
