@@ -1,0 +1,128 @@
+"""bench_dist.py -- the N > 1 leg of bench.py: one process per GPU (torchrun), strong scaling of the same
+N = 16385 solve over row slabs.  torch.distributed (NCCL) is plumbing only: rendezvous, the barrier around
+the timed region, the MAX over ranks of the elapsed time.  All solver traffic (halo rows, the agglomerated
+coarse level, the norm all-gather) goes through libpmg's own NCCL communicator inside pmg_solve.
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+import bench
+
+
+def run(args):
+    import torch
+    import torch.distributed as dist
+    import pmg_b200 as pmg
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world, dev = pmg.init_distributed_from_torch(local)
+    n = args.n
+    peak, peak_src = bench.hbm_peak()
+    prolong = pmg.PROLONG_FULL if args.prolong == "full" else pmg.PROLONG_REFERENCE
+    s = pmg.Solver(n, omega=bench.OMEGA, prolong_mode=prolong, device=dev, rank=rank, n_ranks=world,
+                   agglomerate_below=args.agglomerate_below)
+    y0, y1 = s.local_rows
+    ny = y1 - y0
+    s.set_rhs_sine()
+    max_cycles = 100
+
+    def step():
+        s.zero_guess()
+        return s.solve(pmg.V, rel_tol=bench.REL_TOL, max_cycles=max_cycles)
+
+    def fence():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        k, hist = step()
+    fence()
+    clocks = bench.ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = pmg.kernel_launches()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        k, hist = step()
+        dev_ms += s.last_ms
+    fence()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([wall, dev_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, dev_ms = float(t[0]), float(t[1])
+    lt = torch.tensor([pmg.kernel_launches() - launches0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+
+    # dominant kernel on this rank's slab, timed alone (no communication inside)
+    t_down = s.bench_pass(0, 0, 5)
+    t_upn = s.bench_pass(1, 0, 5)
+    tt = torch.tensor([t_down, t_upn], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_down, t_upn = float(tt[0]), float(tt[1])
+
+    # e2e: every rank pushes ITS slab of f and phi0 from pinned host memory and pulls its slab of phi back
+    f_host, pf = bench.pinned(pmg, (ny, n))
+    x_host, px = bench.pinned(pmg, (ny, n))
+    out_host, po = bench.pinned(pmg, (ny, n))
+    h = 1.0 / (n - 1)
+    sx = np.sin(np.pi * (np.arange(n) * h))
+    np.multiply((2.0 * np.pi * np.pi * sx)[None, :], sx[y0:y1, None], out=f_host)
+    x_host[:] = 0.0
+
+    def e2e_step():
+        s.set_rhs(f_host)
+        s.set_guess(x_host)
+        kk, _ = s.solve(pmg.V, rel_tol=bench.REL_TOL, max_cycles=max_cycles)
+        s.get_solution(out_host)
+        return kk
+
+    e2e_step()
+    fence()
+    e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        ke = e2e_step()
+    fence()
+    te = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e_wall = float(te[0])
+    for p in (pf, px, po):
+        pmg.lib().pmg_host_free_pinned(p)
+    s.close()
+    pmg.comm_finalize()
+
+    if rank == 0:
+        alg_bytes = bench.BYTES_PER_POINT_PASS * n * ny
+        dom_ms, dom_name = (t_upn, "k_up<nu2=2,prolong,norm>") if t_upn >= t_down else (t_down, "k_down<nu1=2,resid>")
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+        cycle_gbs = bench.BYTES_PER_DOF_CYCLE * n * n * k / (dev_ms / args.steps * 1e-3) / 1e9
+        line = {"metric": bench.METRIC, "value": n * n / (wall / args.steps) / 1e9, "unit": bench.UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench.workload_config(args, world),
+                "cycles_to_converge": k, "converged": bool(hist[-1] < bench.REL_TOL * hist[0]),
+                "final_rel_residual": float(hist[-1] / hist[0]),
+                "gdof_cycle_per_s": n * n * k / (dev_ms / args.steps * 1e-3) / 1e9,
+                "device_ms_per_step": dev_ms / args.steps,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "kernel": dom_name + " on one rank's slab",
+                             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms, "peak_source": peak_src,
+                             "pass_down_ms": t_down, "pass_up_norm_ms": t_upn,
+                             "vcycle_effective_gbs_at_69.3B_per_dof": cycle_gbs,
+                             "vcycle_frac_of_aggregate_peak": cycle_gbs / (peak * world)},
+                "cpu_baseline": None,
+                "e2e": {"value": n * n / e_wall / 1e9, "unit": bench.UNIT, "h2d_bytes_per_step": 2 * n * n * 8,
+                        "d2h_bytes_per_step": n * n * 8 + (ke + 1) * 8 * world, "ms_per_step": 1e3 * e_wall, "cycles": ke},
+                "gpu_launches": int(lt[0]), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
