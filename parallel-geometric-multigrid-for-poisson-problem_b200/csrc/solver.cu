@@ -5,6 +5,7 @@
 // its GPU twin leaks them, Parallel_Mg.cu:38-54) and no stage ever runs on the CPU.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -193,6 +194,27 @@ static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero,
     return PMG_OK;
 }
 
+// ---- optional phase trace of the distributed cycle (PMG_DIST_TRACE=1): CUDA events between the phases ----
+struct TraceMark {
+    const char *label;
+    int level;
+    cudaEvent_t ev;
+};
+static std::vector<TraceMark> g_trace;
+static int g_trace_on = -1;
+static void trace_mark(pmg_solver *s, const char *label, int level)
+{
+    if (g_trace_on < 0) {
+        const char *e = getenv("PMG_DIST_TRACE");
+        g_trace_on = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!g_trace_on) return;
+    TraceMark m{label, level, nullptr};
+    cudaEventCreate(&m.ev);
+    cudaEventRecord(m.ev, s->stream);
+    g_trace.push_back(m);
+}
+
 // Row extension of a pass on a slab: ranks recompute `e` halo rows next to each neighbour instead of
 // exchanging them (none at the global top / bottom, where the zero padding rows play that role).
 static FusedLevel slab_view(const pmg_solver *s, const Level &L, int e)
@@ -215,9 +237,12 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     const bool last_slab = (l + 1 == s->agg_level);
     Level &K = last_slab ? s->aslab : s->lv[l + 1];
     pmg_status rc;
+    trace_mark(s, "begin", l);
     if (!x_is_zero && (rc = comm_halo_exchange(L.x, L.ny, L.pitch, PADY, s->stream)) != PMG_OK) return rc;
     if (l > 0 && x_is_zero && (rc = comm_halo_exchange(L.f, L.ny, L.pitch, PADY, s->stream)) != PMG_OK) return rc;
+    trace_mark(s, "halo", l);
     launch_fused_down(slab_view(s, L, 6), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, done);
+    trace_mark(s, "passA", l);
     int reps = w_form ? c.gamma : 1;
     if (!last_slab) {
         for (int k = 0; k < reps; ++k)
@@ -226,13 +251,18 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         Level &A = s->lv[s->agg_level];
         const int *y0 = s->y0s[s->agg_level].data(), *y1 = s->y1s[s->agg_level].data();
         if ((rc = comm_gather_rows(K.f, A.f, A.pitch, y0, y1, s->stream)) != PMG_OK) return rc;
+        trace_mark(s, "gather", l + 1);
         if (s->rank == 0)
             for (int k = 0; k < reps; ++k)
                 if ((rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, done)) != PMG_OK) return rc;
+        trace_mark(s, "coarse", l + 1);
         if ((rc = comm_scatter_rows(A.x, K.x, A.n, A.pitch, y0, y1, 4, s->stream)) != PMG_OK) return rc;
+        trace_mark(s, "scatter", l + 1);
     }
+    trace_mark(s, "child", l);
     launch_fused_up(slab_view(s, L, l == 0 ? 0 : 4), K.x, K.pitch, c.nu2, c.omega, c.prolong_mode,
                     want_norm ? s->d_partials : nullptr, n_partials, s->stream, done);
+    trace_mark(s, "passB", l);
     return PMG_OK;
 }
 
@@ -370,6 +400,7 @@ static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
             launch_final_sum(s->d_gather, s->n_ranks, s->d_scalar, s->stream);
         else
             launch_cycle_finish(s->d_gather, s->n_ranks, s->d_ctrl, s->d_hist2, s->stream);
+        trace_mark(s, "norm", 0);
         return PMG_OK;
     }
     bool graph_ok = fused_graph_ok(s);
@@ -863,6 +894,36 @@ pmg_status pmg_last_device_ms(pmg_solver *s, double *ms_out)
 void *pmg_stream(pmg_solver *s) { return s ? (void *)s->stream : nullptr; }
 
 /* ---- tuning / benchmarking hooks (not part of the reference surface) ---------------------------------- */
+/* PMG_DIST_TRACE=1: prints, per phase label and level, the average device time between consecutive marks of
+ * the distributed cycle recorded since the last dump (the stream must be idle). */
+void pmg_dist_trace_dump(int rank_to_print)
+{
+    if (g_trace.empty()) return;
+    cudaDeviceSynchronize();
+    struct Acc { double ms = 0; int n = 0; };
+    std::vector<std::pair<std::string, Acc>> acc;
+    for (size_t i = 1; i < g_trace.size(); ++i) {
+        if (std::strcmp(g_trace[i].label, "begin") == 0 && g_trace[i].level == 0) continue;  // gap between cycles
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_trace[i - 1].ev, g_trace[i].ev);
+        std::string key = std::string(g_trace[i].label) + "@" + std::to_string(g_trace[i].level);
+        size_t k = 0;
+        for (; k < acc.size(); ++k) if (acc[k].first == key) break;
+        if (k == acc.size()) acc.push_back({key, Acc()});
+        acc[k].second.ms += ms;
+        acc[k].second.n += 1;
+    }
+    if (comm_rank() == rank_to_print) {
+        double tot = 0;
+        for (auto &a : acc) tot += a.second.ms / a.second.n;
+        std::printf("[pmg trace rank %d] per-cycle phase times (us), total %.1f\n", comm_rank(), tot * 1e3);
+        for (auto &a : acc) std::printf("   %-12s %8.1f  (x%d)\n", a.first.c_str(), 1e3 * a.second.ms / a.second.n, a.second.n);
+        std::fflush(stdout);
+    }
+    for (auto &m : g_trace) cudaEventDestroy(m.ev);
+    g_trace.clear();
+}
+
 int pmg_fused_num_variants(void) { return fused_num_variants(); }
 void pmg_fused_set_variant(int v) { fused_set_variant(v); }
 void pmg_fused_set_min_chunk_rows(int r) { fused_set_min_chunk_rows(r); }
