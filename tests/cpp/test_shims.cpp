@@ -1,0 +1,140 @@
+// test_shims.cpp -- a reference-style driver written against include/pmg.hpp only.
+// It follows MultigridTestRunner::run_cycle (2_part_MG/MultiGridTestRunner.hpp:127-256): phi = 0, manufactured
+// RHS, JacobiSmoother(eps) injected into MultigridSolver(&smoother, alpha, N), a fixed number of cycles through a
+// member-function pointer, then "Final Relative L2 Error"; and ParallelTestRunner's operator protocol
+// (3_part_parallel/ParallelTestRunner.cu:231-468) through class Parallel on device memory.
+// Output: one JSON object per line, checked by tests/test_cpp_shims.py against the goldens.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "pmg.hpp"
+
+using namespace pmg::compat;
+
+static void rhs(std::vector<double> &f, std::vector<double> &u, int n)
+{
+    double h = 1.0 / (n - 1);
+    double factor = (M_PI * M_PI) * 2.0;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+            double x = i * h, y = j * h;
+            f[(size_t)j * n + i] = factor * std::sin(M_PI * x) * std::sin(M_PI * y);
+            u[(size_t)j * n + i] = std::sin(M_PI * x) * std::sin(M_PI * y);
+        }
+}
+
+static double norm(const std::vector<double> &v)
+{
+    double s = 0;
+    for (double x : v) s += x * x;
+    return std::sqrt(s);
+}
+
+using CycleFunction = void (MultigridSolver::*)(double *, const double *, int, double);  // MultiGridTestRunner.hpp:125
+
+static void run_cycle(const char *name, int n, CycleFunction fn, bool fcycle)
+{
+    std::vector<double> phi((size_t)n * n, 0.0), f(phi.size()), u(phi.size()), err(phi.size());
+    rhs(f, u, n);
+    JacobiSmoother smoother(1e-7);           // 2_part_MG/main.cpp:12
+    MultigridSolver mg(&smoother, 3, n);     // alpha = 3 (:15)
+    double h = 1.0 / (n - 1);
+    if (fcycle)
+        mg.f_cycle_from_fine(phi.data(), f.data(), n);
+    else
+        (mg.*fn)(phi.data(), f.data(), n, h);
+    for (size_t i = 0; i < phi.size(); ++i) err[i] = phi[i] - u[i];
+    std::printf("{\"test\": \"mg_cpu_exec\", \"cycle\": \"%s\", \"n\": %d, \"rel_l2_error\": %.17g}\n", name, n,
+                norm(err) / norm(u));
+}
+
+static void history(int n)
+{
+    std::vector<double> phi((size_t)n * n, 0.0), f(phi.size()), u(phi.size());
+    rhs(f, u, n);
+    pmg_config c;
+    pmg_config_default(&c, n);
+    c.omega = 2.0 / 3.0;
+    pmg::Solver s(c);
+    s.set_rhs(f.data());
+    s.set_guess(phi.data());
+    std::vector<double> hist = s.solve(PMG_CYCLE_V, 1e-8, 100);
+    std::printf("{\"test\": \"history\", \"n\": %d, \"cycles\": %d, \"hist\": [", n, (int)hist.size() - 1);
+    for (size_t i = 0; i < hist.size(); ++i) std::printf("%s%.17g", i ? ", " : "", hist[i]);
+    std::printf("]}\n");
+}
+
+static void parallel_ops(int n)
+{
+    size_t l = (size_t)n * n, bytes = l * sizeof(double);
+    std::vector<double> x(l, 0.0), f(l), u(l), r(l, 0.0);
+    rhs(f, u, n);
+    void *dx, *df, *dr, *dc, *dp;
+    int nc = (n - 1) / 2 + 1;
+    pmg::check(pmg_device_alloc(&dx, bytes));
+    pmg::check(pmg_device_alloc(&df, bytes));
+    pmg::check(pmg_device_alloc(&dr, bytes));
+    pmg::check(pmg_device_alloc(&dc, (size_t)nc * nc * sizeof(double)));
+    pmg::check(pmg_device_alloc(&dp, bytes));
+    pmg::check(pmg_memcpy(dx, x.data(), bytes, 1, 0));
+    pmg::check(pmg_memcpy(df, f.data(), bytes, 1, 0));
+    pmg::check(pmg_memcpy(dr, r.data(), bytes, 1, 0));
+    pmg::check(pmg_memcpy(dp, r.data(), bytes, 1, 0));
+    std::vector<double> zc((size_t)nc * nc, 0.0);
+    pmg::check(pmg_memcpy(dc, zc.data(), zc.size() * sizeof(double), 1, 0));
+    double h = 1.0 / (n - 1);
+    Parallel::ComputeJacobi((double *)dx, (double *)df, n, n, h, 1);  // v = 1 -> 2 sweeps
+    Parallel::ComputeResidual((double *)dr, (double *)dx, (double *)df, n, n, h);
+    Parallel::ComputeRestriction((double *)dr, (double *)dc, n, nc);
+    Parallel::ComputeProlungator((double *)dc, (double *)dp, nc, n);
+    std::vector<double> p(l), rc((size_t)nc * nc);
+    pmg::check(pmg_memcpy(x.data(), dx, bytes, 0, 1));
+    pmg::check(pmg_memcpy(r.data(), dr, bytes, 0, 1));
+    pmg::check(pmg_memcpy(rc.data(), dc, rc.size() * sizeof(double), 0, 1));
+    pmg::check(pmg_memcpy(p.data(), dp, bytes, 0, 1));
+    int m = n / 2, mc = nc / 2;
+    std::printf("{\"test\": \"parallel_ops\", \"n\": %d, \"x_mid\": %.17g, \"x_11\": %.17g, \"r_mid\": %.17g, \"r_11\": %.17g, "
+                "\"rc_mid\": %.17g, \"rc_11\": %.17g, \"p_11\": %.17g, \"p_22\": %.17g, \"p_23\": %.17g, \"p_33\": %.17g}\n",
+                n, x[(size_t)m * n + m], x[(size_t)n + 1], r[(size_t)m * n + m], r[(size_t)n + 1],
+                rc[(size_t)mc * nc + mc], rc[(size_t)nc + 1], p[(size_t)n + 1], p[(size_t)2 * n + 2],
+                p[(size_t)2 * n + 3], p[(size_t)3 * n + 3]);
+    // ParallelMultiGridSolver::v_cycle on device memory (ParallelTestRunner.cu:152-186 protocol, 3 cycles)
+    std::vector<double> z(l, 0.0);
+    pmg::check(pmg_memcpy(dx, z.data(), bytes, 1, 0));
+    ParallelMultiGridSolver pm(3);
+    for (int it = 0; it < 3; ++it) pm.v_cycle((double *)dx, (double *)df, n, h);
+    pmg::check(pmg_memcpy(x.data(), dx, bytes, 0, 1));
+    std::vector<double> err(l);
+    for (size_t i = 0; i < l; ++i) err[i] = x[i] - u[i];
+    std::printf("{\"test\": \"gpu_exec_v3\", \"n\": %d, \"rel_l2_error\": %.17g}\n", n, norm(err) / norm(u));
+    pmg_device_free(dx); pmg_device_free(df); pmg_device_free(dr); pmg_device_free(dc); pmg_device_free(dp);
+}
+
+int main()
+{
+    try {
+        for (int n : {129, 257}) {
+            run_cycle("V", n, &MultigridSolver::v_cycle, false);
+            run_cycle("W", n, &MultigridSolver::w_cycle, false);
+            run_cycle("F", n, nullptr, true);
+        }
+        history(257);
+        for (int n : {9, 33, 257}) parallel_ops(n);
+        // Smoother interface: residuals vector, num_iter + 1 sweeps
+        {
+            int n = 33;
+            std::vector<double> x((size_t)n * n, 0.0), f(x.size()), u(x.size());
+            rhs(f, u, n);
+            JacobiSmoother sm(0.0);
+            std::vector<double> res;
+            sm.smooth(x.data(), f.data(), n, n, 1.0 / (n - 1), 1, nullptr, &res);
+            std::printf("{\"test\": \"smoother\", \"n\": %d, \"sweeps\": %d, \"res0\": %.17g, \"res1\": %.17g, \"x_mid\": %.17g}\n",
+                        n, (int)res.size(), res[0], res[1], x[(size_t)(n / 2) * n + n / 2]);
+        }
+    } catch (const pmg::Error &e) {
+        std::printf("{\"test\": \"error\", \"status\": %d, \"what\": \"%s\"}\n", (int)e.status, e.what());
+        return 3;
+    }
+    return 0;
+}
