@@ -124,6 +124,26 @@ def cpu_reference_sample(n_sample, cycles, n_target, cycles_target):
     return n_target * n_target / t_target / 1e9, dt, kind
 
 
+def reference_cuda_build(sizes=((4097, 3), (16385, 2))):
+    """The reference's own CUDA multigrid (3_part_parallel, unmodified, compiled for sm_100a into
+    oracle/_ref/ref_gpu_exec) timed on this GPU, ParallelTestRunner::run_v_cycle protocol, data prefetched.
+    Time per V-cycle only: it has no convergence test, no omega, a racy in-place smoother, and leaks ~16 N^2
+    bytes of managed memory per cycle (hence the small cycle counts)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_exec")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_gpu_exec not built"}
+    out = {}
+    for n, cycles in sizes:
+        try:
+            p = subprocess.run([exe, str(n), str(cycles), "1"], capture_output=True, text=True, timeout=180)
+            rec = json.loads(p.stdout.strip().splitlines()[-1])
+            out[str(n)] = {"cycle_ms": rec["cycle_ms"], "best_cycle_ms": min(rec["cycle_ms"]),
+                           "gdof_cycle_per_s": n * n / (min(rec["cycle_ms"]) * 1e-3) / 1e9}
+        except Exception as e:  # noqa: BLE001
+            out[str(n)] = {"error": repr(e)[:200]}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores.  Each step
     is a bounded sample (one V(2,2) cycle at N = 4097, ~2 s) scaled by DOF*cycles to the 39-cycle solve at
@@ -247,6 +267,11 @@ def run_single(args):
                          "reference is single-threaded" % (secs, k, n),
                "host_cores_available": os.cpu_count()}
 
+    ref_cuda = None if args.no_ref_cuda else reference_cuda_build()
+    if ref_cuda and str(n) in ref_cuda and "best_cycle_ms" in ref_cuda[str(n)]:
+        ref_cuda["ours_cycle_ms_same_n"] = dev_ms / args.steps / k
+        ref_cuda["speedup_per_cycle_same_n"] = ref_cuda[str(n)]["best_cycle_ms"] / (dev_ms / args.steps / k)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
@@ -260,7 +285,8 @@ def run_single(args):
                          "vcycle_effective_gbs_at_69.3B_per_dof": cycle_gbs, "vcycle_frac": cycle_gbs / peak},
             "jacobi_sweep": {"gbs_24B_per_point": jac_gbs, "frac": jac_gbs / peak,
                              "blocked4_effective_gbs": jac_blocked_gbs},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+            "cpu_baseline": cpu, "reference_cuda_build": ref_cuda, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk}
     print(json.dumps(line))
     return 0
 
@@ -275,6 +301,7 @@ def main():
     ap.add_argument("--prolong", default="reference", choices=["reference", "full"])
     ap.add_argument("--cycles-expected", type=int, default=39, dest="cycles_expected")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA build")
     ap.add_argument("--agglomerate-below", type=int, default=2049, dest="agglomerate_below",
                     help="multi-GPU: levels with n <= this run on rank 0 only")
     args = ap.parse_args()
