@@ -104,32 +104,36 @@ __device__ __forceinline__ void neighbours(const Row<C> &c, Row<C> &w, Row<C> &e
     }
 }
 
-// One weighted-Jacobi stage of the row pipeline.  `cen` = input row i-1, `part` = the partial sum
-// ((h^2 f + W) + E) + S of row i-1.  Given input row i (`in`) and f of row i it returns the finished
-// output row i-1 and advances the state to row i.
+// One weighted-Jacobi stage of the row pipeline.  `cen[p]` = input row i-1 (p = parity of the step; the two
+// slots ping-pong so that no register has to be copied at the loop back-edge), `part` = the partial sum
+// ((h^2 f + W) + E) + S of row i-1.  Given input row i (`in`) and f of row i it returns the finished output
+// row i-1 and advances the state to row i.
 template <int C>
 struct SweepStage {
-    Row<C> cen, part;
+    Row<C> cen[2], part;
     __device__ __forceinline__ void init()
     {
-        cen = zero_row<C>();
+        cen[0] = zero_row<C>();
+        cen[1] = zero_row<C>();
         part = zero_row<C>();
     }
-    __device__ __forceinline__ Row<C> step(const Row<C> &in, const Row<C> &f_row, const JacobiCoef &c,
+    template <bool WEIGHTED>
+    __device__ __forceinline__ Row<C> step(const int p, const Row<C> &in, const Row<C> &f_row, const JacobiCoef &c,
                                            bool out_row_interior, const bool (&col_interior)[C])
     {
         Row<C> out, w, e;
+        const Row<C> &prev = cen[p];
 #pragma unroll
         for (int k = 0; k < C; ++k) {
             double jac = dmul(0.25, dadd(part.v[k], in.v[k]));
-            double val = c.weighted ? dadd(dmul(c.om1, cen.v[k]), dmul(c.omega, jac)) : jac;
-            out.v[k] = (out_row_interior && col_interior[k]) ? val : cen.v[k];
+            double val = WEIGHTED ? dadd(dmul(c.om1, prev.v[k]), dmul(c.omega, jac)) : jac;
+            out.v[k] = (out_row_interior && col_interior[k]) ? val : prev.v[k];
         }
         neighbours<C>(in, w, e);
 #pragma unroll
         for (int k = 0; k < C; ++k)
-            part.v[k] = dadd(dadd(dadd(dmul(c.h2, f_row.v[k]), w.v[k]), e.v[k]), cen.v[k]);
-        cen = in;
+            part.v[k] = dadd(dadd(dadd(dmul(c.h2, f_row.v[k]), w.v[k]), e.v[k]), prev.v[k]);
+        cen[p ^ 1] = in;
         return out;
     }
 };
@@ -137,14 +141,15 @@ struct SweepStage {
 // Residual stage: same pipeline shape; returns r of row i-1 given x row i.
 template <int C>
 struct ResidualStage {
-    Row<C> part;  // ((4x - W) - E) - S of row i-1
-    Row<C> cen;   // x row i-1
+    Row<C> part;    // ((4x - W) - E) - S of row i-1
+    Row<C> cen[2];  // x row i-1 (ping-pong on the step parity)
     __device__ __forceinline__ void init()
     {
-        cen = zero_row<C>();
+        cen[0] = zero_row<C>();
+        cen[1] = zero_row<C>();
         part = zero_row<C>();
     }
-    __device__ __forceinline__ Row<C> step(const Row<C> &in, const Row<C> &f_prev, double inv_h2)
+    __device__ __forceinline__ Row<C> step(const int p, const Row<C> &in, const Row<C> &f_prev, double inv_h2)
     {
         Row<C> r, w, e;
 #pragma unroll
@@ -153,8 +158,8 @@ struct ResidualStage {
         neighbours<C>(in, w, e);
 #pragma unroll
         for (int k = 0; k < C; ++k)
-            part.v[k] = dsub(dsub(dsub(dmul(4.0, in.v[k]), w.v[k]), e.v[k]), cen.v[k]);
-        cen = in;
+            part.v[k] = dsub(dsub(dsub(dmul(4.0, in.v[k]), w.v[k]), e.v[k]), cen[p].v[k]);
+        cen[p ^ 1] = in;
         return r;
     }
 };
@@ -309,7 +314,7 @@ struct FeedSelect<C, PF, S, USE_X, true> {
 // ---------------------------------------------------------------------------------------------------
 // Pass A.  S sweeps; RESID adds residual + full weighting into the coarse RHS; ZEROX: x == 0 on entry.
 // ---------------------------------------------------------------------------------------------------
-template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID>
+template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID, bool WEIGHTED>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_down(const double *__restrict__ x, double *__restrict__ xo, const double *__restrict__ f,
            double *__restrict__ cf, StripGeom g, int pitch_c, int nc, JacobiCoef coef, double inv_h2,
@@ -318,7 +323,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     using Feed = typename FeedSelect<C, PF, S, !ZEROX, SM>::type;
     if (done != nullptr && *done) return;  // device-side convergence control: the solve already stopped
     constexpr int NP = C / 2;  // coarse points per lane (fine columns v0, v2, ...)
-    const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    // broadcast from lane 0 so the compiler KNOWS the warp index (hence every loop bound below) is warp-uniform:
+    // the row loop then needs no divergence guards around its shuffles
+    const int wid = __shfl_sync(0xffffffffu, (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), 0);
     const int lane = threadIdx.x & 31;
     if (wid >= g.n_strips * g.n_chunks) return;
     int col, r0, r1;
@@ -355,13 +362,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
             for (int k = 0; k < S; ++k) {
                 const int out_row = jj - k - 1 + g.yoff;  // global row
-                cur = st[k].step(cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
+                cur = st[k].template step<WEIGHTED>(u & 1, cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
             }
             // cur = x_S row jj - S
             const int xrow = jj - S;
             if (owner && xrow >= r0 && xrow < r1) store_row<C>(xo + (ptrdiff_t)xrow * g.pitch + col, cur);
             if (RESID) {
-                Row<C> r = rs.step(cur, feed.f_row(S + 1), inv_h2);  // r of row jj - S - 1
+                Row<C> r = rs.step(u & 1, cur, feed.f_row(S + 1), inv_h2);  // r of row jj - S - 1
                 const int rrow = jj - S - 1;
                 double left = __shfl_up_sync(0xffffffffu, r.v[C - 1], 1);
                 if (rrow & 1) {
@@ -427,7 +434,7 @@ __device__ __forceinline__ CoarseRow<C> load_coarse(const double *__restrict__ p
     return r;
 }
 
-template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM>
+template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM, bool WEIGHTED>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_up(const double *__restrict__ xb, double *__restrict__ xo, const double *__restrict__ f,
          const double *__restrict__ e, StripGeom g, int pitch_c, int lo, JacobiCoef coef, double inv_h2,
@@ -437,7 +444,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     if (done != nullptr && *done) return;
     static_assert(Feed::UNROLL % 2 == 0, "rows are processed in (even, odd) pairs");
     constexpr int NP = C / 2;
-    const int wid = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    // broadcast from lane 0 so the compiler KNOWS the warp index (hence every loop bound below) is warp-uniform:
+    // the row loop then needs no divergence guards around its shuffles
+    const int wid = __shfl_sync(0xffffffffu, (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), 0);
     const int lane = threadIdx.x & 31;
     if (wid >= g.n_strips * g.n_chunks) return;
     int col, r0, r1;
@@ -511,12 +520,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
             for (int k = 0; k < S; ++k) {
                 const int out_row = jj - k - 1 + g.yoff;
-                cur = st[k].step(cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
+                cur = st[k].template step<WEIGHTED>(u & 1, cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
             }
             const int xrow = jj - S;
             if (owner && xrow >= r0 && xrow < r1) store_row<C>(xo + (ptrdiff_t)xrow * g.pitch + col, cur);
             if (NORM) {
-                Row<C> r = rs.step(cur, feed.f_row(S + 1), inv_h2);
+                Row<C> r = rs.step(u & 1, cur, feed.f_row(S + 1), inv_h2);
                 const int rrow = jj - S - 1;
                 if (owner && rrow >= r0 && rrow < r1 && rrow >= 0 && rrow < g.ny && rrow + g.yoff > 0 &&
                     rrow + g.yoff < g.n - 1) {
@@ -540,14 +549,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 struct VariantDesc {
     int c, pf, minb, sm;
 };
-constexpr int NUM_VARIANTS = 6;
+constexpr int NUM_VARIANTS = 3;
 constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {
     {2, 3, 4, 1},  // 0: shared-memory staged, 2 columns per lane, 16 warps/SM   (default; measured best)
-    {2, 3, 6, 1},  // 1: same, 24 warps/SM
-    {2, 3, 5, 1},  // 2: same, 20 warps/SM
-    {2, 2, 4, 1},  // 3: prefetch depth 2
-    {4, 2, 3, 0},  // 4: register staged, 4 columns per lane
-    {2, 4, 4, 0},  // 5: register staged, 2 columns per lane
+    {2, 3, 5, 1},  // 1: same, 20 warps/SM
+    {2, 4, 4, 0},  // 2: register staged, 2 columns per lane
 };
 int g_variant_down = 0, g_variant_up = 0;
 int g_min_chunk_rows = 4;  // even; the pipeline warm-up (4..8 rows) is paid once per chunk
@@ -602,6 +608,31 @@ void set_smem(K kernel, int bytes)
     if (bytes > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
+template <int C, int PF, int MINB, bool SM, int S, bool WEIGHTED>
+void down_launch_w(const FusedLevel &lv, double *cf, int pitch_c, bool x_is_zero, bool resid, const StripGeom &g,
+                   int nc, const JacobiCoef &c, double inv, dim3 grid, dim3 block, const int *done, cudaStream_t st)
+{
+    if (resid && x_is_zero) {
+        auto k = k_down<C, PF, MINB, SM, S, true, true, WEIGHTED>;
+        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
+        static bool once = (set_smem(k, sm), true);
+        (void)once;
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done);
+    } else if (resid) {
+        auto k = k_down<C, PF, MINB, SM, S, false, true, WEIGHTED>;
+        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
+        static bool once = (set_smem(k, sm), true);
+        (void)once;
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done);
+    } else {
+        auto k = k_down<C, PF, MINB, SM, S, false, false, WEIGHTED>;
+        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
+        static bool once = (set_smem(k, sm), true);
+        (void)once;
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv, done);
+    }
+}
+
 template <int C, int PF, int MINB, bool SM, int S>
 void down_launch(const FusedLevel &lv, double *cf, int pitch_c, double omega, bool x_is_zero, bool resid,
                  const int *done, cudaStream_t st)
@@ -611,37 +642,33 @@ void down_launch(const FusedLevel &lv, double *cf, int pitch_c, double omega, bo
     double inv = 1.0 / (lv.h * lv.h);
     int nc = (lv.n - 1) / 2 + 1;
     dim3 grid(grid_for(g)), block(32 * WARPS_PER_CTA);
-    if (resid && x_is_zero) {
-        auto k = k_down<C, PF, MINB, SM, S, true, true>;
-        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
-        static bool once = (set_smem(k, sm), true);
-        (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done);
-    } else if (resid) {
-        auto k = k_down<C, PF, MINB, SM, S, false, true>;
-        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
-        static bool once = (set_smem(k, sm), true);
-        (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done);
+    if (c.weighted) {
+        down_launch_w<C, PF, MINB, SM, S, true>(lv, cf, pitch_c, x_is_zero, resid, g, nc, c, inv, grid, block, done, st);
     } else {
-        auto k = k_down<C, PF, MINB, SM, S, false, false>;
-        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
-        static bool once = (set_smem(k, sm), true);
-        (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv, done);
+        down_launch_w<C, PF, MINB, SM, S, false>(lv, cf, pitch_c, x_is_zero, resid, g, nc, c, inv, grid, block, done, st);
     }
     count_launch();
+}
+
+template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM, bool WEIGHTED>
+void up_launch_k(const FusedLevel &lv, const double *e, int pitch_c, const StripGeom &g, int lo,
+                 const JacobiCoef &c, double inv, double *d_partials, const int *done, cudaStream_t st)
+{
+    auto k = k_up<C, PF, MINB, SM, S, PROLONG, NORM, WEIGHTED>;
+    int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
+    static bool once = (set_smem(k, sm), true);
+    (void)once;
+    k<<<dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials, done);
 }
 
 template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM>
 void up_launch_one(const FusedLevel &lv, const double *e, int pitch_c, const StripGeom &g, int lo,
                    const JacobiCoef &c, double inv, double *d_partials, const int *done, cudaStream_t st)
 {
-    auto k = k_up<C, PF, MINB, SM, S, PROLONG, NORM>;
-    int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
-    static bool once = (set_smem(k, sm), true);
-    (void)once;
-    k<<<dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials, done);
+    if (c.weighted)
+        up_launch_k<C, PF, MINB, SM, S, PROLONG, NORM, true>(lv, e, pitch_c, g, lo, c, inv, d_partials, done, st);
+    else
+        up_launch_k<C, PF, MINB, SM, S, PROLONG, NORM, false>(lv, e, pitch_c, g, lo, c, inv, d_partials, done, st);
 }
 
 template <int C, int PF, int MINB, bool SM, int S>
@@ -701,11 +728,8 @@ int fused_max_partials(int n)
 // The tuning variants exist for the headline V(2,2) configuration only; other sweep counts use variant 0.
 #define PMG_DISPATCH_S2(VAR, FN, ...)                                       \
     switch (VAR) {                                                          \
-        case 1: FN<2, 3, 6, true, 2>(__VA_ARGS__); break;                   \
-        case 2: FN<2, 3, 5, true, 2>(__VA_ARGS__); break;                   \
-        case 3: FN<2, 2, 4, true, 2>(__VA_ARGS__); break;                   \
-        case 4: FN<4, 2, 3, false, 2>(__VA_ARGS__); break;                  \
-        case 5: FN<2, 4, 4, false, 2>(__VA_ARGS__); break;                  \
+        case 1: FN<2, 3, 5, true, 2>(__VA_ARGS__); break;                   \
+        case 2: FN<2, 4, 4, false, 2>(__VA_ARGS__); break;                  \
         default: FN<2, 3, 4, true, 2>(__VA_ARGS__); break;                  \
     }
 
