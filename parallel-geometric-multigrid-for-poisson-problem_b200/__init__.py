@@ -14,6 +14,7 @@ Reference surface mirrored here (see include/pmg.hpp for the C++ twin):
 import ctypes
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -212,6 +213,9 @@ class DeviceArray:
             self.ptr = None
 
     def __del__(self):
+        # never call into CUDA while the interpreter is being torn down (the runtime may already be gone)
+        if sys.is_finalizing():
+            return
         try:
             self.free()
         except Exception:
@@ -246,7 +250,10 @@ class Solver:
             lib().pmg_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        if sys.is_finalizing():
+            return
+        self.close()
 
     def __enter__(self):
         return self

@@ -14,7 +14,38 @@
 
 #include "pmg_internal.h"
 
+#include <execinfo.h>
+#include <fcntl.h>
+#include <signal.h>
+#include <unistd.h>
+
 namespace pmg {
+
+// PMG_DEBUG_SIGNALS=<file>: append a native backtrace to <file> on SIGSEGV / SIGABRT (debug aid; off by default)
+static int g_debug_fd = -1;
+static void pmg_signal_handler(int sig)
+{
+    void *frames[64];
+    int n = backtrace(frames, 64);
+    const char msg[] = "\n[libpmg] fatal signal, native backtrace:\n";
+    (void)!write(g_debug_fd, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, g_debug_fd);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+static int install_debug_signals()
+{
+    const char *e = getenv("PMG_DEBUG_SIGNALS");
+    if (e && e[0]) {
+        g_debug_fd = open(e, O_WRONLY | O_CREAT | O_APPEND, 0644);
+        if (g_debug_fd >= 0) {
+            signal(SIGSEGV, pmg_signal_handler);
+            signal(SIGABRT, pmg_signal_handler);
+        }
+    }
+    return 0;
+}
+static int g_debug_signals = install_debug_signals();
 
 thread_local std::string g_last_error;
 
@@ -836,6 +867,8 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
     PMG_CUDA(cudaStreamSynchronize(s->stream));
     PMG_CUDA(cudaGetLastError());
     int k = s->h_ctrl[0].cycles;
+    if (k < 0 || k > max_cycles)
+        return fail(PMG_ERR_CUDA, "solve control block corrupted (cycles = " + std::to_string(k) + ")");
     if (res_history) {
         std::vector<double> h2((size_t)k + 1);
         PMG_CUDA(cudaMemcpy(h2.data(), s->d_hist2, ((size_t)k + 1) * sizeof(double), cudaMemcpyDeviceToHost));
@@ -848,8 +881,21 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
     return PMG_OK;
 }
 
+static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max_cycles, double *res_history,
+                             int *n_cycles_out);
+
 pmg_status pmg_solve(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max_cycles, double *res_history,
                      int *n_cycles_out)
+{
+    try {  // no C++ exception may cross the C ABI
+        return solve_impl(s, kind, rel_tol, max_cycles, res_history, n_cycles_out);
+    } catch (const std::exception &e) {
+        return fail(PMG_ERR_ALLOC, std::string("exception in pmg_solve: ") + e.what());
+    }
+}
+
+static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max_cycles, double *res_history,
+                             int *n_cycles_out)
 {
     if (!s || max_cycles < 0) return fail(PMG_ERR_INVALID, "bad argument");
     PMG_CUDA(cudaSetDevice(s->device));
