@@ -186,6 +186,13 @@ pmg_status comm_scatter_rows(const double *full, double *slab, int n_rows, int p
     return PMG_OK;
 }
 
+pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int pitch, cudaStream_t st)
+{
+    if (!g_comm) return PMG_OK;
+    PMG_NCCL(g_nccl.AllGather(slab - PADX, full - PADX, (size_t)rows * pitch, ncclFloat64, g_comm, st));
+    return PMG_OK;
+}
+
 // every rank receives every rank's double, in rank order
 pmg_status comm_allgather_double(const double *d_mine, double *d_all, cudaStream_t st)
 {

@@ -45,8 +45,9 @@ struct StripGeom {
     int n;           // GLOBAL points per side (columns of this slab; rows of the whole level)
     int ny;          // rows of this slab that the rank owns (== n on one GPU)
     int yoff;        // global row index of local row 0 (even; 0 on one GPU)
-    int ext_lo;      // the iterate is also written for local rows [-ext_lo, 0) and [ny, ny + ext_hi):
-    int ext_hi;      //   redundant work on halo rows that saves a halo exchange (even; 0 on one GPU)
+    int row_lo;      // the pass writes the iterate for local rows [row_lo, row_hi) (row_lo even).  One GPU:
+    int row_hi;      //   [0, n).  Slabs: up to [-6, ny + 6) -- halo rows recomputed instead of exchanged -- or a
+                     //   sub-range when interior and boundary rows are launched separately (comm overlap)
     int pitch;       // row pitch of x / xb / f (doubles)
     int n_strips;    // strips across
     int n_chunks;    // row chunks
@@ -171,8 +172,8 @@ __device__ __forceinline__ void strip_setup(const StripGeom &g, int wid, int lan
     int chunk = wid / g.n_strips;
     int strip = wid - chunk * g.n_strips;
     col = -g.halo + strip * g.stride + C * lane;
-    r0 = -g.ext_lo + chunk * g.chunk_rows;
-    r1 = min(r0 + g.chunk_rows, g.ny + g.ext_hi);
+    r0 = g.row_lo + chunk * g.chunk_rows;
+    r1 = min(r0 + g.chunk_rows, g.row_hi);
     int first_owner = g.halo / C;
     owner = (lane >= first_owner) && (lane < first_owner + g.stride / C);
 #pragma unroll
@@ -549,13 +550,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 struct VariantDesc {
     int c, pf, minb, sm;
 };
-constexpr int NUM_VARIANTS = 3;
+constexpr int NUM_VARIANTS = 4;
 constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {
-    {2, 3, 4, 1},  // 0: shared-memory staged, 2 columns per lane, 16 warps/SM   (default; measured best)
-    {2, 3, 5, 1},  // 1: same, 20 warps/SM
+    {2, 3, 4, 1},  // 0: shared-memory staged, 2 columns per lane, 16 warps/SM   (default for Pass A)
+    {2, 3, 5, 1},  // 1: same, 20 warps/SM                                       (default for Pass B)
     {2, 4, 4, 0},  // 2: register staged, 2 columns per lane
+    {2, 3, 6, 1},  // 3: shared-memory staged, 24 warps/SM
 };
-int g_variant_down = 0, g_variant_up = 0;
+int g_variant_down = 0, g_variant_up = 1;  // measured best per pass (tools/tune_fused.py)
 int g_min_chunk_rows = 4;  // even; the pipeline warm-up (4..8 rows) is paid once per chunk
 
 int g_num_sms = 0;
@@ -577,8 +579,12 @@ StripGeom make_geom(const FusedLevel &lv, int stages, const VariantDesc &v, int 
     g.n = n;
     g.ny = lv.ny > 0 ? lv.ny : n;
     g.yoff = lv.ny > 0 ? lv.yoff : 0;
-    g.ext_lo = ext_lo;
-    g.ext_hi = ext_hi;
+    g.row_lo = -ext_lo;
+    g.row_hi = g.ny + ext_hi;
+    if (lv.span_hi > lv.span_lo) {  // explicit row range (interior / boundary split)
+        g.row_lo = lv.span_lo;
+        g.row_hi = lv.span_hi;
+    }
     g.pitch = lv.pitch;
     g.halo = halo_for(stages);
     g.stride = 32 * v.c - 2 * g.halo;
@@ -587,7 +593,7 @@ StripGeom make_geom(const FusedLevel &lv, int stages, const VariantDesc &v, int 
     int resident = num_sms() * v.minb * WARPS_PER_CTA;
     int chunks = resident / g.n_strips;
     if (chunks < 1) chunks = 1;
-    const int span = g.ny + ext_lo + ext_hi;  // rows the pass writes
+    const int span = g.row_hi - g.row_lo;  // rows the pass writes
     int rows = (span + chunks - 1) / chunks;
     rows += rows & 1;
     if (rows < g_min_chunk_rows) rows = g_min_chunk_rows;
@@ -730,6 +736,7 @@ int fused_max_partials(int n)
     switch (VAR) {                                                          \
         case 1: FN<2, 3, 5, true, 2>(__VA_ARGS__); break;                   \
         case 2: FN<2, 4, 4, false, 2>(__VA_ARGS__); break;                  \
+        case 3: FN<2, 3, 6, true, 2>(__VA_ARGS__); break;                   \
         default: FN<2, 3, 4, true, 2>(__VA_ARGS__); break;                  \
     }
 

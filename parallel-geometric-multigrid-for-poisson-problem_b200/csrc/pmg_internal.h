@@ -130,6 +130,7 @@ struct FusedLevel {
     // row slab of a level partitioned over ranks (all zero on one GPU): the arrays hold local rows
     // [-PADY, ny + PADY); local row 0 is global row yoff.  ext_lo/ext_hi: see StripGeom.
     int ny, yoff, ext_lo, ext_hi;
+    int span_lo, span_hi;  // if span_hi > span_lo: write only local rows [span_lo, span_hi) (span_lo even)
 };
 // Pass A (down): xb = S^nu1(x);  coarse_f(interior) = R(f - A xb).  x_is_zero: the iterate is known to
 // be identically zero on entry (coarse levels of a V-cycle) so x is not read.
@@ -159,5 +160,8 @@ pmg_status comm_gather_rows(const double *slab, double *full, int pitch, const i
 pmg_status comm_scatter_rows(const double *full, double *slab, int n_rows, int pitch, const int *y0s,
                              const int *y1s, int halo, cudaStream_t st);
 pmg_status comm_allgather_double(const double *d_mine, double *d_all, cudaStream_t st);
+// every rank contributes `rows` owned rows of its slab; all ranks receive the whole level (rank r's block at
+// row r*rows of `full`).  Needs equally sized slabs (the extra last row of the last rank is the zero ring).
+pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int pitch, cudaStream_t st);
 
 }  // namespace pmg

@@ -113,6 +113,10 @@ struct pmg_solver {
     Level aslab;
     std::vector<std::vector<int>> y0s, y1s;  // [level <= agg_level][rank]
     double *d_gather = nullptr;              // one double per rank (norm all-gather)
+    cudaStream_t comm_stream = nullptr;      // halo exchanges and the norm all-gather run here, beside compute
+    cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_passb = nullptr, ev_norm = nullptr;
+    bool norm_pending = false;               // an ev_norm has been recorded that the next Pass B(0) must wait for
+    bool coarse_redundant = false;           // every rank solves the agglomerated levels (all-gather, no scatter)
 };
 
 namespace pmg {
@@ -139,6 +143,7 @@ static FusedLevel fused_view(const Level &L)
     v.ny = L.ny;
     v.yoff = L.y0;
     v.ext_lo = v.ext_hi = 0;
+    v.span_lo = v.span_hi = 0;
     return v;
 }
 
@@ -246,20 +251,12 @@ static void trace_mark(pmg_solver *s, const char *label, int level)
     g_trace.push_back(m);
 }
 
-// Row extension of a pass on a slab: ranks recompute `e` halo rows next to each neighbour instead of
-// exchanging them (none at the global top / bottom, where the zero padding rows play that role).
-static FusedLevel slab_view(const pmg_solver *s, const Level &L, int e)
-{
-    FusedLevel v = fused_view(L);
-    v.ext_lo = (s->rank > 0) ? e : 0;
-    v.ext_hi = (s->rank < s->n_ranks - 1) ? e : 0;
-    return v;
-}
-
 // The fused cycle on row slabs.  Per level visit: ONE halo exchange of PADY rows on
 // the way down (the iterate on the finest level / on repeated W visits, the restricted right-hand side on a
 // first visit) and none on the way up -- Pass A also finishes 6 halo rows of xb, Pass B 4 halo rows of x,
 // which is exactly what the parent's prolongation and this level's second pass read.
+// The exchange runs on `comm_stream` WHILE Pass A works on the interior rows [8, ny-8), which need no halo;
+// the two boundary strips [-6, 8) and [ny-8, ny+6) follow once the halo has landed.
 static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, bool want_norm, int *n_partials,
                              const int *done)
 {
@@ -267,13 +264,41 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     Level &L = s->lv[l];
     const bool last_slab = (l + 1 == s->agg_level);
     Level &K = last_slab ? s->aslab : s->lv[l + 1];
+    const bool up_nb = s->rank > 0, dn_nb = s->rank < s->n_ranks - 1;
     pmg_status rc;
     trace_mark(s, "begin", l);
-    if (!x_is_zero && (rc = comm_halo_exchange(L.x, L.ny, L.pitch, PADY, s->stream)) != PMG_OK) return rc;
-    if (l > 0 && x_is_zero && (rc = comm_halo_exchange(L.f, L.ny, L.pitch, PADY, s->stream)) != PMG_OK) return rc;
-    trace_mark(s, "halo", l);
-    launch_fused_down(slab_view(s, L, 6), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, done);
-    trace_mark(s, "passA", l);
+    // (1) halo exchange on the communication stream, behind everything the compute stream has queued so far
+    double *halo_field = !x_is_zero ? L.x : (l > 0 ? L.f : nullptr);
+    if (halo_field) {
+        PMG_CUDA(cudaEventRecord(s->ev_ready, s->stream));
+        PMG_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
+        if ((rc = comm_halo_exchange(halo_field, L.ny, L.pitch, PADY, s->comm_stream)) != PMG_OK) return rc;
+        PMG_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
+    }
+    // (2) Pass A: interior rows first, boundary strips after the halo
+    {
+        FusedLevel v = fused_view(L);
+        const int lo_i = (halo_field && up_nb) ? PADY : (up_nb ? -6 : 0);
+        const int hi_i = (halo_field && dn_nb) ? L.ny - PADY : (dn_nb ? L.ny + 6 : L.ny);
+        v.span_lo = lo_i;
+        v.span_hi = hi_i;
+        launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
+        trace_mark(s, "passA_in", l);
+        if (halo_field) {
+            PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+            if (up_nb) {
+                v.span_lo = -6;
+                v.span_hi = PADY;
+                launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
+            }
+            if (dn_nb) {
+                v.span_lo = L.ny - PADY;
+                v.span_hi = L.ny + 6;
+                launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
+            }
+            trace_mark(s, "passA_bd", l);
+        }
+    }
     int reps = w_form ? c.gamma : 1;
     if (!last_slab) {
         for (int k = 0; k < reps; ++k)
@@ -281,18 +306,43 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     } else {
         Level &A = s->lv[s->agg_level];
         const int *y0 = s->y0s[s->agg_level].data(), *y1 = s->y1s[s->agg_level].data();
-        if ((rc = comm_gather_rows(K.f, A.f, A.pitch, y0, y1, s->stream)) != PMG_OK) return rc;
-        trace_mark(s, "gather", l + 1);
-        if (s->rank == 0)
+        if (s->coarse_redundant) {
+            // every rank receives the whole first agglomerated level and solves it: no scatter, no idle ranks
+            if ((rc = comm_allgather_rows(K.f, A.f, y1[0] - y0[0], A.pitch, s->stream)) != PMG_OK) return rc;
+            trace_mark(s, "allgather", l + 1);
             for (int k = 0; k < reps; ++k)
-                if ((rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, done)) != PMG_OK) return rc;
-        trace_mark(s, "coarse", l + 1);
-        if ((rc = comm_scatter_rows(A.x, K.x, A.n, A.pitch, y0, y1, 4, s->stream)) != PMG_OK) return rc;
+                if ((rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, nullptr)) != PMG_OK) return rc;
+            trace_mark(s, "coarse", l + 1);
+            int a = std::max(0, y0[s->rank] - 4), b = std::min(A.n, y1[s->rank] + 4);
+            PMG_CUDA(cudaMemcpyAsync(K.x - PADX + (ptrdiff_t)(a - y0[s->rank]) * K.pitch, A.x - PADX + (ptrdiff_t)a * A.pitch,
+                                     (size_t)(b - a) * A.pitch * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        } else {
+            if ((rc = comm_gather_rows(K.f, A.f, A.pitch, y0, y1, s->stream)) != PMG_OK) return rc;
+            trace_mark(s, "gather", l + 1);
+            if (s->rank == 0)
+                for (int k = 0; k < reps; ++k)
+                    if ((rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, nullptr)) != PMG_OK) return rc;
+            trace_mark(s, "coarse", l + 1);
+            if ((rc = comm_scatter_rows(A.x, K.x, A.n, A.pitch, y0, y1, 4, s->stream)) != PMG_OK) return rc;
+        }
         trace_mark(s, "scatter", l + 1);
     }
     trace_mark(s, "child", l);
-    launch_fused_up(slab_view(s, L, l == 0 ? 0 : 4), K.x, K.pitch, c.nu2, c.omega, c.prolong_mode,
-                    want_norm ? s->d_partials : nullptr, n_partials, s->stream, done);
+    // (3) Pass B.  Only the finest level's Pass B changes state that outlives the cycle (x_0), so it alone
+    // honours the device-side `done` flag -- after waiting for the previous cycle's norm, which was combined
+    // on the communication stream while this cycle was already running.
+    if (l == 0 && s->norm_pending) {
+        PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_norm, 0));
+        s->norm_pending = false;
+    }
+    {
+        FusedLevel v = fused_view(L);
+        const int e = (l == 0) ? 0 : 4;
+        v.ext_lo = up_nb ? e : 0;
+        v.ext_hi = dn_nb ? e : 0;
+        launch_fused_up(v, K.x, K.pitch, c.nu2, c.omega, c.prolong_mode, want_norm ? s->d_partials : nullptr,
+                        n_partials, s->stream, l == 0 ? done : nullptr);
+    }
     trace_mark(s, "passB", l);
     return PMG_OK;
 }
@@ -425,12 +475,21 @@ static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
         const int *done = (mode == 2) ? &s->d_ctrl->done : nullptr;
         pmg_status rc = cycle_dist(s, 0, w, false, mode != 0, &np, done);
         if (rc != PMG_OK || mode == 0) return rc;
-        launch_final_sum(s->d_partials, np, s->d_scalar, s->stream);
-        if ((rc = comm_allgather_double(s->d_scalar, s->d_gather, s->stream)) != PMG_OK) return rc;
-        if (mode == 1)
-            launch_final_sum(s->d_gather, s->n_ranks, s->d_scalar, s->stream);
-        else
-            launch_cycle_finish(s->d_gather, s->n_ranks, s->d_ctrl, s->d_hist2, s->stream);
+        // the norm is combined on the communication stream; only the NEXT cycle's last pass waits for it
+        cudaStream_t ns = (mode == 2) ? s->comm_stream : s->stream;
+        if (mode == 2) {
+            PMG_CUDA(cudaEventRecord(s->ev_passb, s->stream));
+            PMG_CUDA(cudaStreamWaitEvent(ns, s->ev_passb, 0));
+        }
+        launch_final_sum(s->d_partials, np, s->d_scalar, ns);
+        if ((rc = comm_allgather_double(s->d_scalar, s->d_gather, ns)) != PMG_OK) return rc;
+        if (mode == 1) {
+            launch_final_sum(s->d_gather, s->n_ranks, s->d_scalar, ns);
+        } else {
+            launch_cycle_finish(s->d_gather, s->n_ranks, s->d_ctrl, s->d_hist2, ns);
+            PMG_CUDA(cudaEventRecord(s->ev_norm, ns));
+            s->norm_pending = true;
+        }
         trace_mark(s, "norm", 0);
         return PMG_OK;
     }
@@ -648,6 +707,19 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         A.x = A.base_x + level_origin(A.n);
         A.f = A.base_f + level_origin(A.n);
         if ((rc = alloc_zero(&s->d_gather, (size_t)cfg->n_ranks)) != PMG_OK) return bail(rc);
+        if (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess)
+            return bail(fail(PMG_ERR_CUDA, "cudaStreamCreate failed"));
+        cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->ev_passb, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->ev_norm, cudaEventDisableTiming);
+        // all-gather + redundant coarse solve needs equally sized slabs (the last rank's extra row is the ring)
+        bool equal = true;
+        for (int r = 0; r + 1 < cfg->n_ranks; ++r)
+            equal = equal && (s->y1s[la][r] - s->y0s[la][r] == s->y1s[la][0] - s->y0s[la][0]);
+        equal = equal && (s->y1s[la][cfg->n_ranks - 1] - s->y0s[la][cfg->n_ranks - 1] == s->y1s[la][0] - s->y0s[la][0] + 1);
+        const char *env = getenv("PMG_COARSE_GATHER");
+        s->coarse_redundant = equal && !(env && env[0] == '1');
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
@@ -698,6 +770,12 @@ void pmg_destroy(pmg_solver *s)
     cudaFree(s->aslab.base_x);
     cudaFree(s->aslab.base_f);
     cudaFree(s->d_gather);
+    if (s->comm_stream) {
+        cudaStreamSynchronize(s->comm_stream);
+        cudaStreamDestroy(s->comm_stream);
+    }
+    for (cudaEvent_t e : {s->ev_ready, s->ev_halo, s->ev_passb, s->ev_norm})
+        if (e) cudaEventDestroy(e);
     cudaFree(s->d_partials);
     cudaFree(s->d_scalar);
     if (s->h_scalar) cudaFreeHost(s->h_scalar);
@@ -850,8 +928,9 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
             if (rc != PMG_OK) return rc;
         }
         queued += b;
-        PMG_CUDA(cudaMemcpyAsync(&s->h_ctrl[slot], s->d_ctrl, sizeof(SolveCtrl), cudaMemcpyDeviceToHost, s->stream));
-        PMG_CUDA(cudaEventRecord(s->ev_batch[slot], s->stream));
+        cudaStream_t cs = s->dist ? s->comm_stream : s->stream;  // the stream whose last kernel wrote the control block
+        PMG_CUDA(cudaMemcpyAsync(&s->h_ctrl[slot], s->d_ctrl, sizeof(SolveCtrl), cudaMemcpyDeviceToHost, cs));
+        PMG_CUDA(cudaEventRecord(s->ev_batch[slot], cs));
         pending[slot] = true;
         int prev = slot ^ 1;
         if (pending[prev]) {  // look at the batch before this one while this one runs
@@ -861,6 +940,11 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
         }
         if (queued >= max_cycles || b == 0) finished = true;
         slot ^= 1;
+    }
+    if (s->dist) {  // join the communication stream (last norm) before the end-of-solve timestamp
+        PMG_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
+        PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+        s->norm_pending = false;
     }
     PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
     PMG_CUDA(cudaMemcpyAsync(&s->h_ctrl[0], s->d_ctrl, sizeof(SolveCtrl), cudaMemcpyDeviceToHost, s->stream));
