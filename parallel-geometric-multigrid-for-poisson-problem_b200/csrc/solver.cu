@@ -117,6 +117,7 @@ struct pmg_solver {
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_passb = nullptr, ev_norm = nullptr;
     bool norm_pending = false;               // an ev_norm has been recorded that the next Pass B(0) must wait for
     bool coarse_redundant = false;           // every rank solves the agglomerated levels (all-gather, no scatter)
+    int split_min_rows = 512;                // slabs at least this tall overlap the exchange with interior rows
 };
 
 namespace pmg {
@@ -267,37 +268,45 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     const bool up_nb = s->rank > 0, dn_nb = s->rank < s->n_ranks - 1;
     pmg_status rc;
     trace_mark(s, "begin", l);
-    // (1) halo exchange on the communication stream, behind everything the compute stream has queued so far
+    // (1)+(2) halo exchange and Pass A.  Large slabs: the exchange AND the two boundary strips
+    // [-6, 8), [ny-8, ny+6) run on the communication stream while the compute stream works on the interior
+    // rows [8, ny-8), which need no halo; the streams join before the next level.  Small slabs (the interior
+    // is shorter than an exchange): exchange, then one launch.
     double *halo_field = !x_is_zero ? L.x : (l > 0 ? L.f : nullptr);
+    const bool split = halo_field && L.ny >= s->split_min_rows && (up_nb || dn_nb);
+    FusedLevel v = fused_view(L);
     if (halo_field) {
         PMG_CUDA(cudaEventRecord(s->ev_ready, s->stream));
         PMG_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
         if ((rc = comm_halo_exchange(halo_field, L.ny, L.pitch, PADY, s->comm_stream)) != PMG_OK) return rc;
-        PMG_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
-    }
-    // (2) Pass A: interior rows first, boundary strips after the halo
-    {
-        FusedLevel v = fused_view(L);
-        const int lo_i = (halo_field && up_nb) ? PADY : (up_nb ? -6 : 0);
-        const int hi_i = (halo_field && dn_nb) ? L.ny - PADY : (dn_nb ? L.ny + 6 : L.ny);
-        v.span_lo = lo_i;
-        v.span_hi = hi_i;
-        launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
-        trace_mark(s, "passA_in", l);
-        if (halo_field) {
-            PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+        if (split) {
             if (up_nb) {
                 v.span_lo = -6;
                 v.span_hi = PADY;
-                launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
+                launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->comm_stream, nullptr);
             }
             if (dn_nb) {
                 v.span_lo = L.ny - PADY;
                 v.span_hi = L.ny + 6;
-                launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
+                launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->comm_stream, nullptr);
             }
-            trace_mark(s, "passA_bd", l);
         }
+        PMG_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
+    }
+    if (split) {
+        v.span_lo = up_nb ? PADY : 0;
+        v.span_hi = dn_nb ? L.ny - PADY : L.ny;
+        launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
+        trace_mark(s, "passA_in", l);
+        PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+        trace_mark(s, "passA_bd", l);
+    } else {
+        if (halo_field) PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+        trace_mark(s, "halo", l);
+        v.span_lo = up_nb ? -6 : 0;
+        v.span_hi = dn_nb ? L.ny + 6 : L.ny;
+        launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
+        trace_mark(s, "passA", l);
     }
     int reps = w_form ? c.gamma : 1;
     if (!last_slab) {
@@ -720,6 +729,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         equal = equal && (s->y1s[la][cfg->n_ranks - 1] - s->y0s[la][cfg->n_ranks - 1] == s->y1s[la][0] - s->y0s[la][0] + 1);
         const char *env = getenv("PMG_COARSE_GATHER");
         s->coarse_redundant = equal && !(env && env[0] == '1');
+        if (const char *e2 = getenv("PMG_SPLIT_MIN_ROWS")) s->split_min_rows = atoi(e2);
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
