@@ -117,7 +117,7 @@ struct pmg_solver {
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_passb = nullptr, ev_norm = nullptr;
     bool norm_pending = false;               // an ev_norm has been recorded that the next Pass B(0) must wait for
     bool coarse_redundant = false;           // every rank solves the agglomerated levels (all-gather, no scatter)
-    int split_min_rows = 512;                // slabs at least this tall overlap the exchange with interior rows
+    int split_min_rows = 2048;               // slabs at least this tall overlap the exchange with interior rows
 };
 
 namespace pmg {
@@ -716,7 +716,11 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         A.x = A.base_x + level_origin(A.n);
         A.f = A.base_f + level_origin(A.n);
         if ((rc = alloc_zero(&s->d_gather, (size_t)cfg->n_ranks)) != PMG_OK) return bail(rc);
-        if (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess)
+        // highest priority: its small latency-bound kernels (NCCL, boundary strips) are scheduled ahead of the
+        // bandwidth-bound interior pass they run beside
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess)
             return bail(fail(PMG_ERR_CUDA, "cudaStreamCreate failed"));
         cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming);
