@@ -15,6 +15,7 @@
 
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "pmg_internal.h"
 
@@ -30,7 +31,7 @@ typedef struct {
     char internal[128];
 } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8 };
+enum { ncclInt8 = 0, ncclFloat64 = 8 };
 
 struct NcclApi {
     void *handle = nullptr;
@@ -191,6 +192,59 @@ pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int p
     if (!g_comm) return PMG_OK;
     PMG_NCCL(g_nccl.AllGather(slab - PADX, full - PADX, (size_t)rows * pitch, ncclFloat64, g_comm, st));
     return PMG_OK;
+}
+
+// ---- NVLink peer access (CUDA IPC) ----------------------------------------------------------------------
+// Every rank exports one cudaMalloc'ed allocation; on return peers[r] is a pointer through which THIS
+// process can load/store rank r's allocation over NVLink (peers[own rank] = base).  Collective.
+pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st)
+{
+    if (!g_comm) return PMG_OK;
+    cudaIpcMemHandle_t mine;
+    cudaError_t e = cudaIpcGetMemHandle(&mine, base);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+        return PMG_ERR_COMM;
+    }
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    unsigned char *d_mine = nullptr, *d_all = nullptr;
+    if (cudaMalloc((void **)&d_mine, hb) != cudaSuccess || cudaMalloc((void **)&d_all, hb * g_nranks) != cudaSuccess) {
+        g_last_error = "cudaMalloc failed";
+        return PMG_ERR_ALLOC;
+    }
+    cudaMemcpyAsync(d_mine, &mine, hb, cudaMemcpyHostToDevice, st);
+    ncclResult_t r = g_nccl.AllGather(d_mine, d_all, hb, ncclInt8, g_comm, st);
+    std::vector<cudaIpcMemHandle_t> all(g_nranks);
+    cudaMemcpyAsync(all.data(), d_all, hb * g_nranks, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    cudaFree(d_mine);
+    cudaFree(d_all);
+    if (r != 0) return nccl_fail("ncclAllGather(ipc handles)", r);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("ipc handle exchange: ") + cudaGetErrorString(e);
+        return PMG_ERR_CUDA;
+    }
+    for (int q = 0; q < g_nranks; ++q) {
+        if (q == g_rank) {
+            peers[q] = base;
+            continue;
+        }
+        peers[q] = nullptr;
+        // only the neighbours' mappings are ever used; opening all of them keeps the call collective-free
+        if (q != g_rank - 1 && q != g_rank + 1) continue;
+        e = cudaIpcOpenMemHandle(&peers[q], all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            g_last_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return PMG_ERR_COMM;
+        }
+    }
+    return PMG_OK;
+}
+
+void comm_ipc_close(void *peer)
+{
+    if (peer) cudaIpcCloseMemHandle(peer);
 }
 
 // every rank receives every rank's double, in rank order

@@ -283,6 +283,55 @@ __global__ void __launch_bounds__(BX *BY)
     if (x < nx && y < ny) f[(size_t)y * pitch + x] = dmul(dmul(factor, sx[x]), sy[y]);
 }
 
+// ---- NVLink peer-to-peer halo exchange ----------------------------------------------------------------------
+__global__ void k_halo_signal(int *up_flag, int *dn_flag, int epoch)
+{
+    // everything this stream ran before is complete; make it visible system-wide, then publish
+    __threadfence_system();
+    if (up_flag) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(up_flag), "r"(epoch) : "memory");
+    if (dn_flag) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dn_flag), "r"(epoch) : "memory");
+}
+
+__device__ __forceinline__ bool wait_flag(const int *flag, int epoch)
+{
+    // bounded: ~2 s at 1 us per probe, then give up (the host reports the error instead of hanging the GPU)
+    for (int it = 0; it < 2000000; ++it) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= epoch) return true;
+        __nanosleep(1000);
+    }
+    return false;
+}
+
+// blockIdx.y: 0 = rows from the upper neighbour into my rows [-depth, 0), 1 = from the lower into [ny, ny+depth)
+__global__ void __launch_bounds__(256)
+    k_halo_pull(double *__restrict__ mine, int ny, int pitch, int depth, const double *__restrict__ up_src,
+                const double *__restrict__ dn_src, const int *flag_from_up, const int *flag_from_dn, int epoch,
+                int *err)
+{
+    const bool from_up = blockIdx.y == 0;
+    const double *src = from_up ? up_src : dn_src;
+    if (src == nullptr) return;
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = wait_flag(from_up ? flag_from_up : flag_from_dn, epoch) ? 1 : 0;
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0) *err = 1;
+        return;
+    }
+    // whole padded rows, 16 bytes per thread per step (row starts are 128-byte aligned)
+    double *dst = mine - PADX + (ptrdiff_t)(from_up ? -depth : ny) * pitch;
+    const double2 *s2 = reinterpret_cast<const double2 *>(src - PADX);
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    const size_t n2 = (size_t)depth * pitch / 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        double2 v;
+        asm volatile("ld.global.cv.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(s2 + i));
+        d2[i] = v;
+    }
+}
+
 inline JacobiCoef make_coef(double h, double omega)
 {
     JacobiCoef c;
@@ -352,6 +401,23 @@ void launch_residual_norm2(const double *x, const double *f, int nx, int ny, int
     k_residual_norm2<<<blocks, RED_THREADS, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, 1.0 / (h * h), d_partials);
     count_launch();
     launch_final_sum(d_partials, blocks, d_out, st);
+}
+
+void launch_halo_signal(int *up_flag, int *dn_flag, int epoch, cudaStream_t st)
+{
+    k_halo_signal<<<1, 1, 0, st>>>(up_flag, dn_flag, epoch);
+    count_launch();
+}
+
+void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *up_src, const double *dn_src,
+                      const int *flag_from_up, const int *flag_from_dn, int epoch, int *err, cudaStream_t st)
+{
+    size_t n2 = (size_t)depth * pitch / 2;
+    int bx = (int)((n2 + 255) / 256);
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    k_halo_pull<<<dim3(bx, 2), 256, 0, st>>>(mine, ny, pitch, depth, up_src, dn_src, flag_from_up, flag_from_dn, epoch, err);
+    count_launch();
 }
 
 void launch_residual_norm2_sequential(const double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f,

@@ -160,6 +160,21 @@ pmg_status comm_gather_rows(const double *slab, double *full, int pitch, const i
 pmg_status comm_scatter_rows(const double *full, double *slab, int n_rows, int pitch, const int *y0s,
                              const int *y1s, int halo, cudaStream_t st);
 pmg_status comm_allgather_double(const double *d_mine, double *d_all, cudaStream_t st);
+// CUDA IPC: peers[r] = a pointer in this process to rank r's allocation `base` (neighbours only; others null)
+pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st);
+void comm_ipc_close(void *peer);
+
+// ---- NVLink peer-to-peer halo exchange (kernels_basic.cu) -------------------------------------------------
+// Producer side: after the kernel that finished this rank's boundary rows, publish `epoch` in the neighbours'
+// inbox flags (system-scope release).  up_flag / dn_flag: peer pointers, null where there is no neighbour.
+void launch_halo_signal(int *up_flag, int *dn_flag, int epoch, cudaStream_t st);
+// Consumer side: wait (bounded spin, acquire) until both neighbours have published `epoch` in MY inbox flags,
+// then copy their `depth` boundary rows straight out of their arrays over NVLink into my halo rows.
+//   mine: logical origin of my slab array, ny owned rows; up_src: peer pointer to the upper neighbour's row
+//   (its ny - depth), dn_src: peer pointer to the lower neighbour's row 0; flags: my inbox {from_up, from_dn};
+//   err: device int raised if the spin times out.
+void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *up_src, const double *dn_src,
+                      const int *flag_from_up, const int *flag_from_dn, int epoch, int *err, cudaStream_t st);
 // every rank contributes `rows` owned rows of its slab; all ranks receive the whole level (rank r's block at
 // row r*rows of `full`).  Needs equally sized slabs (the extra last row of the last rank is the zero ring).
 pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int pitch, cudaStream_t st);

@@ -73,6 +73,11 @@ struct Level {
     double *base_x = nullptr, *base_xb = nullptr, *base_f = nullptr, *base_r = nullptr;
     double *x = nullptr, *xb = nullptr, *f = nullptr, *r = nullptr;  // logical (0,0)
     double *d_sin = nullptr;  // sin(pi * i * h), i < n  (F-cycle analytic RHS; lazily built)
+    // NVLink peer-to-peer halo exchange: the neighbours' boundary rows of x and f as seen from this process
+    // (upper neighbour's row ny_up - PADY, lower neighbour's row 0) and the raw IPC mappings to close
+    const double *up_x = nullptr, *dn_x = nullptr, *up_f = nullptr, *dn_f = nullptr;
+    void *ipc_maps[4] = {nullptr, nullptr, nullptr, nullptr};
+    int halo_epoch = 0;
 };
 
 }  // namespace pmg
@@ -118,6 +123,10 @@ struct pmg_solver {
     bool norm_pending = false;               // an ev_norm has been recorded that the next Pass B(0) must wait for
     bool coarse_redundant = false;           // every rank solves the agglomerated levels (all-gather, no scatter)
     int split_min_rows = 2048;               // slabs at least this tall overlap the exchange with interior rows
+    bool p2p = false;                        // halo rows are pulled from the neighbours' memory over NVLink
+    int *d_flags = nullptr;                  // my inbox: [level][from_up, from_dn] epochs published by neighbours
+    int *up_flags = nullptr, *dn_flags = nullptr;  // the neighbours' inboxes (peer mappings)
+    int *d_comm_err = nullptr;               // raised by a pull whose wait timed out
 };
 
 namespace pmg {
@@ -276,9 +285,21 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     const bool split = halo_field && L.ny >= s->split_min_rows && (up_nb || dn_nb);
     FusedLevel v = fused_view(L);
     if (halo_field) {
+        int epoch = 0;
+        if (s->p2p) {  // publish "my boundary rows of this level are final" in the neighbours' inboxes
+            epoch = ++L.halo_epoch;
+            launch_halo_signal(up_nb ? s->up_flags + 2 * l + 1 : nullptr, dn_nb ? s->dn_flags + 2 * l : nullptr, epoch,
+                               s->stream);
+        }
         PMG_CUDA(cudaEventRecord(s->ev_ready, s->stream));
         PMG_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
-        if ((rc = comm_halo_exchange(halo_field, L.ny, L.pitch, PADY, s->comm_stream)) != PMG_OK) return rc;
+        if (s->p2p) {
+            const bool is_x = (halo_field == L.x);
+            launch_halo_pull(halo_field, L.ny, L.pitch, PADY, is_x ? L.up_x : L.up_f, is_x ? L.dn_x : L.dn_f,
+                             s->d_flags + 2 * l, s->d_flags + 2 * l + 1, epoch, s->d_comm_err, s->comm_stream);
+        } else if ((rc = comm_halo_exchange(halo_field, L.ny, L.pitch, PADY, s->comm_stream)) != PMG_OK) {
+            return rc;
+        }
         if (split) {
             if (up_nb) {
                 v.span_lo = -6;
@@ -749,6 +770,47 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
             L.r = L.base_r + o;
         }
     }
+    if (dist) {
+        const char *env = getenv("PMG_P2P");
+        bool want = !(env && env[0] == '0');
+        if (want) {
+            // inbox flags + error word, then the x / f arrays of every slab level, shared with the neighbours
+            std::vector<void *> peers((size_t)cfg->n_ranks, nullptr);
+            bool ok = cudaMalloc((void **)&s->d_flags, 64 * sizeof(int)) == cudaSuccess &&
+                      cudaMemset(s->d_flags, 0, 64 * sizeof(int)) == cudaSuccess &&
+                      cudaMalloc((void **)&s->d_comm_err, sizeof(int)) == cudaSuccess &&
+                      cudaMemset(s->d_comm_err, 0, sizeof(int)) == cudaSuccess;
+            ok = ok && comm_ipc_share(s->d_flags, peers.data(), s->stream) == PMG_OK;
+            if (ok) {
+                if (s->rank > 0) s->up_flags = (int *)peers[s->rank - 1];
+                if (s->rank < s->n_ranks - 1) s->dn_flags = (int *)peers[s->rank + 1];
+            }
+            for (int l = 0; ok && l < s->agg_level; ++l) {
+                Level &L = s->lv[l];
+                const size_t o = level_origin(L.n);
+                for (int which = 0; ok && which < 2; ++which) {
+                    ok = comm_ipc_share(which == 0 ? L.base_x : L.base_f, peers.data(), s->stream) == PMG_OK;
+                    if (!ok) break;
+                    if (s->rank > 0) {
+                        int ny_up = s->y1s[l][s->rank - 1] - s->y0s[l][s->rank - 1];
+                        const double *p = (const double *)peers[s->rank - 1] + o + (ptrdiff_t)(ny_up - PADY) * L.pitch;
+                        (which == 0 ? L.up_x : L.up_f) = p;
+                        L.ipc_maps[which * 2] = peers[s->rank - 1];
+                    }
+                    if (s->rank < s->n_ranks - 1) {
+                        const double *p = (const double *)peers[s->rank + 1] + o;
+                        (which == 0 ? L.dn_x : L.dn_f) = p;
+                        L.ipc_maps[which * 2 + 1] = peers[s->rank + 1];
+                    }
+                }
+            }
+            // the set-up calls above are collective, so a failure here is a failure everywhere
+            if (!ok)
+                return bail(fail(PMG_ERR_COMM, std::string("CUDA IPC set-up failed (") + g_last_error +
+                                                   "); set PMG_P2P=0 to exchange halos with NCCL send/recv"));
+            s->p2p = true;
+        }
+    }
     s->partials_cap = std::max(reduce_partials(), fused_max_partials(cfg->n));
     if ((rc = alloc_zero(&s->d_partials, (size_t)s->partials_cap)) != PMG_OK) return bail(rc);
     if ((rc = alloc_zero(&s->d_scalar, 2)) != PMG_OK) return bail(rc);
@@ -784,6 +846,12 @@ void pmg_destroy(pmg_solver *s)
     cudaFree(s->aslab.base_x);
     cudaFree(s->aslab.base_f);
     cudaFree(s->d_gather);
+    for (Level &L : s->lv)
+        for (void *m : L.ipc_maps) comm_ipc_close(m);
+    comm_ipc_close(s->up_flags);
+    comm_ipc_close(s->dn_flags);
+    cudaFree(s->d_flags);
+    cudaFree(s->d_comm_err);
     if (s->comm_stream) {
         cudaStreamSynchronize(s->comm_stream);
         cudaStreamDestroy(s->comm_stream);
@@ -964,6 +1032,11 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
     PMG_CUDA(cudaMemcpyAsync(&s->h_ctrl[0], s->d_ctrl, sizeof(SolveCtrl), cudaMemcpyDeviceToHost, s->stream));
     PMG_CUDA(cudaStreamSynchronize(s->stream));
     PMG_CUDA(cudaGetLastError());
+    if (s->p2p) {
+        int err = 0;
+        PMG_CUDA(cudaMemcpy(&err, s->d_comm_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(PMG_ERR_COMM, "peer-to-peer halo exchange timed out waiting for a neighbour");
+    }
     int k = s->h_ctrl[0].cycles;
     if (k < 0 || k > max_cycles)
         return fail(PMG_ERR_CUDA, "solve control block corrupted (cycles = " + std::to_string(k) + ")");
@@ -1077,6 +1150,7 @@ void pmg_fused_set_min_chunk_rows(int r) { fused_set_min_chunk_rows(r); }
 pmg_status pmg_smooth(pmg_solver *s, int sweeps, int block)
 {
     if (!s || sweeps < 0 || !fused_supported(block)) return fail(PMG_ERR_INVALID, "bad argument");
+    if (s->dist) return fail(PMG_ERR_UNSUPPORTED, "pmg_smooth is single-GPU only");
     PMG_CUDA(cudaSetDevice(s->device));
     Level &L = s->lv[0];
     PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
