@@ -73,6 +73,135 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+// ---- a whole V-cycle of the small levels inside ONE CTA ------------------------------------------------------
+// Levels n0 (<= VSMALL_TOP) -> ... -> n_coarse live in shared memory (x, scratch, f per level); every operator is
+// the reference's, point for point (pmg_internal.h), separated by block barriers.  Replaces 2 launches per
+// level (each ~5 us of pure latency at these sizes) by one.  MultiGrid.hpp:57-94 restricted to small N.
+extern __shared__ __align__(16) double g_vs_smem[];
+
+__device__ __forceinline__ void vs_sweeps(double *&cur, double *&oth, const double *f, int n, const JacobiCoef &c,
+                                          int sweeps)
+{
+    const int l = n * n;
+    for (int s = 0; s < sweeps; ++s) {
+        for (int i = threadIdx.x; i < l; i += blockDim.x) {
+            int y = i / n, x = i - y * n;
+            double v = cur[i];
+            if (x > 0 && x < n - 1 && y > 0 && y < n - 1)
+                v = jacobi_point(c, f[i], v, cur[i - 1], cur[i + 1], cur[i - n], cur[i + n]);
+            oth[i] = v;
+        }
+        __syncthreads();
+        double *t = cur;
+        cur = oth;
+        oth = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+    k_vcycle_small(double *__restrict__ xg, const double *__restrict__ fg, int n0, int pitch_x, int pitch_f,
+                   int n_coarse, double h0, double omega, int nu1, int nu2, int coarse_sweeps, int lo,
+                   int x_is_zero, const int *__restrict__ done)
+{
+    if (done != nullptr && *done) return;
+    constexpr int MAXL = 8;
+    double *cur[MAXL], *oth[MAXL], *f[MAXL];
+    int n[MAXL];
+    double h[MAXL];
+    int nl = 0;
+    {
+        double *p = g_vs_smem;
+        int m = n0;
+        double hh = h0;
+        for (;;) {
+            n[nl] = m;
+            h[nl] = hh;
+            cur[nl] = p;
+            oth[nl] = p + m * m;
+            f[nl] = p + 2 * m * m;
+            p += 3 * m * m;
+            ++nl;
+            if (m <= n_coarse || m <= 3 || nl == MAXL) break;
+            m = (m - 1) / 2 + 1;
+            hh = 2 * hh;  // MultiGrid.hpp:83
+        }
+    }
+    // level 0: right-hand side from global memory, iterate zero (first visit of a coarse level) or loaded
+    for (int i = threadIdx.x; i < n0 * n0; i += blockDim.x) {
+        int y = i / n0, x = i - y * n0;
+        f[0][i] = fg[(size_t)y * pitch_f + x];
+        cur[0][i] = x_is_zero ? 0.0 : xg[(size_t)y * pitch_x + x];
+    }
+    __syncthreads();
+    for (int k = 0; k + 1 < nl; ++k) {  // down
+        JacobiCoef c;
+        c.h2 = h[k] * h[k];
+        c.omega = omega;
+        c.om1 = 1.0 - omega;
+        c.weighted = (omega != 1.0);
+        vs_sweeps(cur[k], oth[k], f[k], n[k], c, nu1);
+        const double inv_h2 = 1.0 / (h[k] * h[k]);
+        const int m = n[k], l = m * m;
+        double *r = oth[k];
+        for (int i = threadIdx.x; i < l; i += blockDim.x) {
+            int y = i / m, x = i - y * m;
+            if (x > 0 && x < m - 1 && y > 0 && y < m - 1)
+                r[i] = residual_point(inv_h2, f[k][i], cur[k][i], cur[k][i - 1], cur[k][i + 1], cur[k][i - m],
+                                      cur[k][i + m]);
+        }
+        __syncthreads();
+        const int mc = n[k + 1], lc = mc * mc;
+        for (int i = threadIdx.x; i < lc; i += blockDim.x) {
+            int jc = i / mc, ic = i - jc * mc;
+            double v = 0.0;
+            if (ic > 0 && ic < mc - 1 && jc > 0 && jc < mc - 1) {
+                const double *q = r + (2 * jc) * m + 2 * ic;
+                v = restrict_point(q[0], q[1], q[-1], q[m], q[-m], q[-m - 1], q[-m + 1], q[m - 1], q[m + 1]);
+            }
+            f[k + 1][i] = v;
+            cur[k + 1][i] = 0.0;
+        }
+        __syncthreads();
+    }
+    {  // coarsest level (MultiGrid.hpp:59-63)
+        const int k = nl - 1;
+        JacobiCoef c;
+        c.h2 = h[k] * h[k];
+        c.omega = omega;
+        c.om1 = 1.0 - omega;
+        c.weighted = (omega != 1.0);
+        vs_sweeps(cur[k], oth[k], f[k], n[k], c, nl == 1 ? coarse_sweeps : coarse_sweeps);
+    }
+    for (int k = nl - 2; k >= 0; --k) {  // up
+        const int m = n[k], l = m * m, mc = n[k + 1];
+        const double *e = cur[k + 1];
+        for (int i = threadIdx.x; i < l; i += blockDim.x) {
+            int y = i / m, x = i - y * m;
+            if (x >= lo && y >= lo && x <= m - 2 && y <= m - 2) {
+                const double *q = e + (y >> 1) * mc + (x >> 1);
+                double v;
+                if ((y & 1) == 0)
+                    v = ((x & 1) == 0) ? q[0] : dmul(0.5, dadd(q[0], q[1]));
+                else
+                    v = ((x & 1) == 0) ? dmul(0.5, dadd(q[0], q[mc]))
+                                       : dmul(0.25, dadd(dadd(dadd(q[0], q[1]), q[mc]), q[mc + 1]));
+                cur[k][i] = dadd(cur[k][i], v);
+            }
+        }
+        __syncthreads();
+        JacobiCoef c;
+        c.h2 = h[k] * h[k];
+        c.omega = omega;
+        c.om1 = 1.0 - omega;
+        c.weighted = (omega != 1.0);
+        vs_sweeps(cur[k], oth[k], f[k], n[k], c, nu2);
+    }
+    for (int i = threadIdx.x; i < n0 * n0; i += blockDim.x) {
+        int y = i / n0, x = i - y * n0;
+        xg[(size_t)y * pitch_x + x] = cur[0][i];
+    }
+}
+
 // ---- residual: DynamicGridUtils.hpp:59-69 (replaces device_compute_residual, Parallel_Method.cu:26-46)
 __global__ void __launch_bounds__(BX *BY)
     k_residual(double *__restrict__ r, const double *__restrict__ xg, const double *__restrict__ f, int nx,
@@ -360,6 +489,31 @@ void launch_jacobi_small(double *x, const double *f, int nx, int ny, int pitch_x
     int l = nx * ny;
     int threads = l >= 1024 ? 1024 : ((l + 31) / 32) * 32;
     k_jacobi_small<<<1, threads, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, make_coef(h, omega), sweeps, x_is_zero ? 1 : 0, done);
+    count_launch();
+}
+
+size_t vcycle_small_smem(int n0, int n_coarse)
+{
+    size_t d = 0;
+    for (int m = n0, k = 0; k < 8; ++k) {
+        d += 3 * (size_t)m * m;
+        if (m <= n_coarse || m <= 3) break;
+        m = (m - 1) / 2 + 1;
+    }
+    return d * sizeof(double);
+}
+
+void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0,
+                         double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
+                         cudaStream_t st, const int *done)
+{
+    size_t smem = vcycle_small_smem(n0, n_coarse);
+    static bool once = (cudaFuncSetAttribute(k_vcycle_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
+    (void)once;
+    int l = n0 * n0;
+    int threads = l >= 1024 ? 1024 : ((l + 31) / 32) * 32;
+    k_vcycle_small<<<1, threads, smem, st>>>(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps,
+                                            prolong_mode == PMG_PROLONG_FULL ? 1 : 2, x_is_zero ? 1 : 0, done);
     count_launch();
 }
 

@@ -103,6 +103,7 @@ struct pmg_solver {
     cudaGraphExec_t graph[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     int graph_kernels[2][3] = {{0, 0, 0}, {0, 0, 0}};  // kernel nodes per replay (launch bookkeeping)
     bool fused = false;
+    bool small_vcycle = true;  // PMG_SMALL_VCYCLE=0 disables the single-CTA kernel for the levels <= 65
     // asynchronous solve: device control block + history of squared norms, pinned mirrors, batch events
     SolveCtrl *d_ctrl = nullptr;
     double *d_hist2 = nullptr;
@@ -228,6 +229,13 @@ static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero,
     Level &L = s->lv[l];
     if (L.n <= c.n_coarse || l + 1 == (int)s->lv.size())
         return smooth_operator(s, l, c.coarse_sweeps, x_is_zero, done);
+    // the small levels of a V-cycle (no repeated visits) run as ONE single-CTA kernel in shared memory
+    if (l > 0 && L.n <= VSMALL_TOP && (!w_form || c.gamma == 1) && s->small_vcycle && (int)s->lv.size() - l <= 8 &&
+        s->lv.back().n * s->lv.back().n <= SMALL_MAX_POINTS) {
+        launch_vcycle_small(L.x, L.f, L.n, L.pitch, L.pitch, c.n_coarse, L.h, c.omega, c.nu1, c.nu2, c.coarse_sweeps,
+                            c.prolong_mode, x_is_zero, s->stream, done);
+        return PMG_OK;
+    }
     Level &K = s->lv[l + 1];
     launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, done);
     int reps = w_form ? c.gamma : 1;
@@ -291,13 +299,19 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             launch_halo_signal(up_nb ? s->up_flags + 2 * l + 1 : nullptr, dn_nb ? s->dn_flags + 2 * l : nullptr, epoch,
                                s->stream);
         }
-        PMG_CUDA(cudaEventRecord(s->ev_ready, s->stream));
-        PMG_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
+        // tall slabs: exchange + boundary strips on the communication stream beside the interior pass;
+        // short slabs: everything in order on the compute stream (no cross-stream hops)
+        cudaStream_t xs = split ? s->comm_stream : s->stream;
+        if (split || !s->p2p) {
+            xs = s->comm_stream;
+            PMG_CUDA(cudaEventRecord(s->ev_ready, s->stream));
+            PMG_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
+        }
         if (s->p2p) {
             const bool is_x = (halo_field == L.x);
             launch_halo_pull(halo_field, L.ny, L.pitch, PADY, is_x ? L.up_x : L.up_f, is_x ? L.dn_x : L.dn_f,
-                             s->d_flags + 2 * l, s->d_flags + 2 * l + 1, epoch, s->d_comm_err, s->comm_stream);
-        } else if ((rc = comm_halo_exchange(halo_field, L.ny, L.pitch, PADY, s->comm_stream)) != PMG_OK) {
+                             s->d_flags + 2 * l, s->d_flags + 2 * l + 1, epoch, s->d_comm_err, xs);
+        } else if ((rc = comm_halo_exchange(halo_field, L.ny, L.pitch, PADY, xs)) != PMG_OK) {
             return rc;
         }
         if (split) {
@@ -312,8 +326,9 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
                 launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->comm_stream, nullptr);
             }
         }
-        PMG_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
+        if (xs == s->comm_stream) PMG_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
     }
+    const bool halo_on_comm = halo_field && (split || !s->p2p);
     if (split) {
         v.span_lo = up_nb ? PADY : 0;
         v.span_hi = dn_nb ? L.ny - PADY : L.ny;
@@ -322,7 +337,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
         trace_mark(s, "passA_bd", l);
     } else {
-        if (halo_field) PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+        if (halo_on_comm) PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
         trace_mark(s, "halo", l);
         v.span_lo = up_nb ? -6 : 0;
         v.span_hi = dn_nb ? L.ny + 6 : L.ny;
@@ -687,6 +702,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         return st;
     };
     (void)fused_max_partials(3);  // warms the cached SM count outside any stream capture
+    if (const char *e = getenv("PMG_SMALL_VCYCLE")) s->small_vcycle = !(e[0] == '0');
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(PMG_ERR_CUDA, "cudaStreamCreate failed"));
     cudaEventCreate(&s->ev0);
