@@ -557,7 +557,9 @@ constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {
     {2, 4, 4, 0},  // 2: register staged, 2 columns per lane
     {2, 3, 6, 1},  // 3: shared-memory staged, 24 warps/SM
 };
-int g_variant_down = 0, g_variant_up = 1;  // measured best per pass (tools/tune_fused.py)
+// measured best per kernel flavour on B200 (tools/tune_fused.py): Pass A, Pass A from x == 0, Pass B, Pass B + norm
+int g_variant_down = 0, g_variant_down_zero = 3, g_variant_up = 1, g_variant_up_norm = 3;
+
 int g_min_chunk_rows = 4;  // even; the pipeline warm-up (4..8 rows) is paid once per chunk
 
 int g_num_sms = 0;
@@ -709,8 +711,14 @@ void fused_set_variant(int v)
     // bit 16 clear: one variant for both passes; set: low byte = Pass A variant, next byte = Pass B variant
     int d = v & 0xff, u = (v >> 8) & 0xff;
     if (!(v & 0x10000)) u = d;
-    g_variant_down = (d >= 0 && d < NUM_VARIANTS) ? d : 0;
-    g_variant_up = (u >= 0 && u < NUM_VARIANTS) ? u : 0;
+    g_variant_down = g_variant_down_zero = (d >= 0 && d < NUM_VARIANTS) ? d : 0;
+    g_variant_up = g_variant_up_norm = (u >= 0 && u < NUM_VARIANTS) ? u : 0;
+    if (v < 0) {  // restore the per-kernel defaults
+        g_variant_down = 0;
+        g_variant_down_zero = 3;
+        g_variant_up = 1;
+        g_variant_up_norm = 3;
+    }
 }
 int fused_get_variant() { return g_variant_down | (g_variant_up << 8); }
 void fused_set_min_chunk_rows(int r) { g_min_chunk_rows = (r >= 2) ? (r + (r & 1)) : 2; }
@@ -746,7 +754,7 @@ void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int 
     bool resid = coarse_f != nullptr;
     switch (nu1) {
         case 1: down_launch<2, 3, 4, true, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
-        case 2: PMG_DISPATCH_S2(g_variant_down, down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
+        case 2: PMG_DISPATCH_S2((x_is_zero && resid) ? g_variant_down_zero : g_variant_down, down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         case 3: down_launch<2, 3, 4, true, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         case 4: down_launch<2, 2, 4, true, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         default: break;
@@ -760,7 +768,7 @@ void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, 
     int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
     switch (nu2) {
         case 1: up_launch<2, 3, 4, true, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
-        case 2: PMG_DISPATCH_S2(g_variant_up, up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
+        case 2: PMG_DISPATCH_S2(norm ? g_variant_up_norm : g_variant_up, up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
         case 3: up_launch<2, 3, 4, true, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
         case 4: up_launch<2, 2, 4, true, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
         default: break;

@@ -39,4 +39,4 @@ for n in sizes:
             rec["vcycle_gbs_69.3"] = round(69.3 * n * n * k / s.last_ms / 1e6, 1)
             s.close()
             print(json.dumps(rec), flush=True)
-pmg.set_fused_variant(0)
+pmg.set_fused_variant(-1)
