@@ -56,13 +56,6 @@ struct StripGeom {
     int stride;      // STRIP - 2*halo: columns owned per strip
 };
 
-struct FastTag {
-    static constexpr bool value = false;
-};
-struct MaskedTag {
-    static constexpr bool value = true;
-};
-
 template <int C>
 struct Row {
     double v[C];
@@ -125,9 +118,7 @@ struct SweepStage {
         cen[1] = zero_row<C>();
         part = zero_row<C>();
     }
-    // MASKED = false: the caller guarantees that every point of the output row is an interior point (the
-    // warp's strip does not touch the ring columns and the row is not a ring row), so no select is needed.
-    template <bool WEIGHTED, bool MASKED>
+    template <bool WEIGHTED>
     __device__ __forceinline__ Row<C> step(const int p, const Row<C> &in, const Row<C> &f_row, const JacobiCoef &c,
                                            bool out_row_interior, const bool (&col_interior)[C])
     {
@@ -137,7 +128,7 @@ struct SweepStage {
         for (int k = 0; k < C; ++k) {
             double jac = dmul(0.25, dadd(part.v[k], in.v[k]));
             double val = WEIGHTED ? dadd(dmul(c.om1, prev.v[k]), dmul(c.omega, jac)) : jac;
-            out.v[k] = (!MASKED || (out_row_interior && col_interior[k])) ? val : prev.v[k];
+            out.v[k] = (out_row_interior && col_interior[k]) ? val : prev.v[k];
         }
         neighbours<C>(in, w, e);
 #pragma unroll
@@ -363,13 +354,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     feed.init(x, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5);
     const int ycoarse = g.yoff >> 1;  // global coarse row of local coarse row 0
 
-    // Interior fast path: a strip that touches neither ring column, on rows whose stage outputs are all
-    // interior rows, needs none of the boundary selects.  Both conditions are warp-uniform.
-    const int c_first = col - C * lane;  // first column of the strip
-    const bool strip_fast = (c_first >= 2) && (c_first + 32 * C - 1 <= g.n - 2);
-
-    auto body = [&](auto masked_tag, const int j) {
-        constexpr bool MASKED = decltype(masked_tag)::value;
+    for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
 #pragma unroll
         for (int u = 0; u < Feed::UNROLL; ++u) {
             const int jj = j + u;  // input row of this step (steps past j_end are harmless: stores are masked)
@@ -378,8 +363,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
             for (int k = 0; k < S; ++k) {
                 const int out_row = jj - k - 1 + g.yoff;  // global row
-                cur = st[k].template step<WEIGHTED, MASKED>(u & 1, cur, feed.f_row(k), coef,
-                                                            out_row > 0 && out_row < g.n - 1, cin);
+                cur = st[k].template step<WEIGHTED>(u & 1, cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
             }
             // cur = x_S row jj - S
             const int xrow = jj - S;
@@ -399,7 +383,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                         double edge = dadd(dadd(c_ew[q], r.v[2 * q]), s_mid[q]);
                         double corner = dadd(dadd(s_cor[q], west), r.v[2 * q + 1]);
                         double val = dadd(dadd(dmul(0.25, c_mid[q]), dmul(0.125, edge)), dmul(0.0625, corner));
-                        o[q] = (!MASKED || (ic + q >= 1 && ic + q < nc - 1)) ? val : 0.0;
+                        o[q] = (ic + q >= 1 && ic + q < nc - 1) ? val : 0.0;
                         // this row is also the south row of coarse row jc+1
                         s_mid[q] = r.v[2 * q];
                         s_cor[q] = dadd(west, r.v[2 * q + 1]);
@@ -424,14 +408,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             }
             feed.end();
         }
-    };
-    for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
-        // global input rows j .. j+UNROLL-1: all stage output rows interior <=> S+1 <= row <= n-2
-        const bool fast = strip_fast && (j + g.yoff >= S + 1) && (j + Feed::UNROLL - 1 + g.yoff <= g.n - 2);
-        if (fast)
-            body(FastTag{}, j);
-        else
-            body(MaskedTag{}, j);
     }
     cp_async_wait<0>();
 }
@@ -510,11 +486,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
         eb = load_coarse<C>(e + (ptrdiff_t)(jc0 + 1) * pitch_c + cc);
     }
 
-    const int c_first = col - C * lane;
-    const bool strip_fast = (c_first >= 2) && (c_first + 32 * C - 1 <= g.n - 2);
-
-    auto body = [&](auto masked_tag, const int j) {
-        constexpr bool MASKED = decltype(masked_tag)::value;
+    for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
 #pragma unroll
         for (int u = 0; u < Feed::UNROLL; ++u) {
             const int jj = j + u;  // u even: fine row 2jc, u odd: fine row 2jc+1
@@ -544,13 +516,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                 }
 #pragma unroll
                 for (int k = 0; k < C; ++k)
-                    if (!MASKED || (rowp && cprol[k])) cur.v[k] = dadd(cur.v[k], corr[k]);
+                    if (rowp && cprol[k]) cur.v[k] = dadd(cur.v[k], corr[k]);
             }
 #pragma unroll
             for (int k = 0; k < S; ++k) {
                 const int out_row = jj - k - 1 + g.yoff;
-                cur = st[k].template step<WEIGHTED, MASKED>(u & 1, cur, feed.f_row(k), coef,
-                                                            out_row > 0 && out_row < g.n - 1, cin);
+                cur = st[k].template step<WEIGHTED>(u & 1, cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
             }
             const int xrow = jj - S;
             if (owner && xrow >= r0 && xrow < r1) store_row<C>(xo + (ptrdiff_t)xrow * g.pitch + col, cur);
@@ -566,13 +537,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             }
             feed.end();
         }
-    };
-    for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
-        const bool fast = strip_fast && (j + g.yoff >= S + 1) && (j + Feed::UNROLL - 1 + g.yoff <= g.n - 2);
-        if (fast)
-            body(FastTag{}, j);
-        else
-            body(MaskedTag{}, j);
     }
     cp_async_wait<0>();
     if (NORM) {
