@@ -197,7 +197,7 @@ pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int p
 // ---- NVLink peer access (CUDA IPC) ----------------------------------------------------------------------
 // Every rank exports one cudaMalloc'ed allocation; on return peers[r] is a pointer through which THIS
 // process can load/store rank r's allocation over NVLink (peers[own rank] = base).  Collective.
-pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st)
+pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st, bool all_peers)
 {
     if (!g_comm) return PMG_OK;
     cudaIpcMemHandle_t mine;
@@ -231,7 +231,7 @@ pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st)
         }
         peers[q] = nullptr;
         // only the neighbours' mappings are ever used; opening all of them keeps the call collective-free
-        if (q != g_rank - 1 && q != g_rank + 1) continue;
+        if (!all_peers && q != g_rank - 1 && q != g_rank + 1) continue;
         e = cudaIpcOpenMemHandle(&peers[q], all[q], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             g_last_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);

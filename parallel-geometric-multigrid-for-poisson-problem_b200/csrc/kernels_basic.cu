@@ -461,6 +461,37 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+__global__ void k_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch)
+{
+    __threadfence_system();
+    int r = threadIdx.x;
+    if (r < n_ranks && r != my_rank)
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(slots[r]), "r"(epoch) : "memory");
+}
+
+// blockIdx.y = source rank
+__global__ void __launch_bounds__(256)
+    k_gather_pull(double *__restrict__ full, int pitch, int rows, const double *const *__restrict__ srcs,
+                  const int *inbox, int my_rank, int epoch, int *err)
+{
+    const int r = blockIdx.y;
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = (r == my_rank) ? 1 : (wait_flag(inbox + r, epoch) ? 1 : 0);
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0) *err = 1;
+        return;
+    }
+    const size_t n2 = (size_t)rows * pitch / 2;
+    const double2 *s2 = reinterpret_cast<const double2 *>(srcs[r]);
+    double2 *d2 = reinterpret_cast<double2 *>(full - PADX + (size_t)r * rows * pitch);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        double2 v;
+        asm volatile("ld.global.cv.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(s2 + i));
+        d2[i] = v;
+    }
+}
+
 inline JacobiCoef make_coef(double h, double omega)
 {
     JacobiCoef c;
@@ -571,6 +602,23 @@ void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *
     if (bx > 64) bx = 64;
     if (bx < 1) bx = 1;
     k_halo_pull<<<dim3(bx, 2), 256, 0, st>>>(mine, ny, pitch, depth, up_src, dn_src, flag_from_up, flag_from_dn, epoch, err);
+    count_launch();
+}
+
+void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, cudaStream_t st)
+{
+    k_signal_all<<<1, 32, 0, st>>>(slots, n_ranks, my_rank, epoch);
+    count_launch();
+}
+
+void launch_gather_pull(double *full, int pitch, int rows, const double *const *srcs, const int *inbox, int n_ranks,
+                        int my_rank, int epoch, int *err, cudaStream_t st)
+{
+    size_t n2 = (size_t)rows * pitch / 2;
+    int bx = (int)((n2 + 255) / 256);
+    if (bx > 16) bx = 16;
+    if (bx < 1) bx = 1;
+    k_gather_pull<<<dim3(bx, n_ranks), 256, 0, st>>>(full, pitch, rows, srcs, inbox, my_rank, epoch, err);
     count_launch();
 }
 

@@ -167,7 +167,7 @@ pmg_status comm_scatter_rows(const double *full, double *slab, int n_rows, int p
                              const int *y1s, int halo, cudaStream_t st);
 pmg_status comm_allgather_double(const double *d_mine, double *d_all, cudaStream_t st);
 // CUDA IPC: peers[r] = a pointer in this process to rank r's allocation `base` (neighbours only; others null)
-pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st);
+pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st, bool all_peers = false);
 void comm_ipc_close(void *peer);
 
 // ---- NVLink peer-to-peer halo exchange (kernels_basic.cu) -------------------------------------------------
@@ -181,6 +181,12 @@ void launch_halo_signal(int *up_flag, int *dn_flag, int epoch, cudaStream_t st);
 //   err: device int raised if the spin times out.
 void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *up_src, const double *dn_src,
                       const int *flag_from_up, const int *flag_from_dn, int epoch, int *err, cudaStream_t st);
+// All-gather of a slab-partitioned level over NVLink: `slots[r]` = rank r's inbox slot for THIS rank (peer
+// pointers, device array); every rank publishes `epoch` there, then pulls the other ranks' `rows` slab rows
+// (`srcs[r]` = peer pointer to rank r's padded row 0, device array; srcs[my_rank] is local) into `full`.
+void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, cudaStream_t st);
+void launch_gather_pull(double *full, int pitch, int rows, const double *const *srcs, const int *inbox, int n_ranks,
+                        int my_rank, int epoch, int *err, cudaStream_t st);
 // every rank contributes `rows` owned rows of its slab; all ranks receive the whole level (rank r's block at
 // row r*rows of `full`).  Needs equally sized slabs (the extra last row of the last rank is the zero ring).
 pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int pitch, cudaStream_t st);

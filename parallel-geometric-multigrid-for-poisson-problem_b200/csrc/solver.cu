@@ -128,6 +128,13 @@ struct pmg_solver {
     int *d_flags = nullptr;                  // my inbox: [level][from_up, from_dn] epochs published by neighbours
     int *up_flags = nullptr, *dn_flags = nullptr;  // the neighbours' inboxes (peer mappings)
     int *d_comm_err = nullptr;               // raised by a pull whose wait timed out
+    // peer-to-peer all-gather of the first agglomerated level's right-hand side (V-cycles): double-buffered slab
+    double *agg_f[2] = {nullptr, nullptr};   // bases of the two slab buffers (agg_f[0] == aslab.base_f)
+    int **d_agg_slots = nullptr;             // [rank] -> that rank's inbox slot for me (peer pointers)
+    const double **d_agg_srcs[2] = {nullptr, nullptr};  // per buffer: [rank] -> that rank's slab row 0 (padded start)
+    std::vector<void *> agg_maps;            // IPC mappings to close
+    int agg_epoch = 0;
+    bool p2p_gather = false, cycle_has_collective = false;
 };
 
 namespace pmg {
@@ -285,6 +292,15 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     const bool up_nb = s->rank > 0, dn_nb = s->rank < s->n_ranks - 1;
     pmg_status rc;
     trace_mark(s, "begin", l);
+    // NVLink all-gather of the agglomerated level (V form, one collective per cycle keeps the two buffers safe)
+    const bool pull_gather = last_slab && s->p2p_gather && s->coarse_redundant && s->cycle_has_collective &&
+                             (!w_form || c.gamma == 1);
+    if (pull_gather) {
+        ++s->agg_epoch;
+        s->aslab.f = s->agg_f[s->agg_epoch & 1] + level_origin(s->aslab.n);
+    } else if (last_slab) {
+        s->aslab.f = s->agg_f[0] ? s->agg_f[0] + level_origin(s->aslab.n) : s->aslab.f;
+    }
     // (1)+(2) halo exchange and Pass A.  Large slabs: the exchange AND the two boundary strips
     // [-6, 8), [ny-8, ny+6) run on the communication stream while the compute stream works on the interior
     // rows [8, ny-8), which need no halo; the streams join before the next level.  Small slabs (the interior
@@ -353,7 +369,13 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         const int *y0 = s->y0s[s->agg_level].data(), *y1 = s->y1s[s->agg_level].data();
         if (s->coarse_redundant) {
             // every rank receives the whole first agglomerated level and solves it: no scatter, no idle ranks
-            if ((rc = comm_allgather_rows(K.f, A.f, y1[0] - y0[0], A.pitch, s->stream)) != PMG_OK) return rc;
+            if (pull_gather) {
+                launch_signal_all(s->d_agg_slots, s->n_ranks, s->rank, s->agg_epoch, s->stream);
+                launch_gather_pull(A.f, A.pitch, y1[0] - y0[0], s->d_agg_srcs[s->agg_epoch & 1], s->d_flags + 32,
+                                   s->n_ranks, s->rank, s->agg_epoch, s->d_comm_err, s->stream);
+            } else if ((rc = comm_allgather_rows(K.f, A.f, y1[0] - y0[0], A.pitch, s->stream)) != PMG_OK) {
+                return rc;
+            }
             trace_mark(s, "allgather", l + 1);
             for (int k = 0; k < reps; ++k)
                 if ((rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, nullptr)) != PMG_OK) return rc;
@@ -518,6 +540,7 @@ static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
         // direct launches (NCCL calls sit between the kernels); norms are combined in rank order
         int np = 0;
         const int *done = (mode == 2) ? &s->d_ctrl->done : nullptr;
+        s->cycle_has_collective = (mode != 0);  // the norm all-gather: every rank passes it once per cycle
         pmg_status rc = cycle_dist(s, 0, w, false, mode != 0, &np, done);
         if (rc != PMG_OK || mode == 0) return rc;
         // the norm is combined on the communication stream; only the NEXT cycle's last pass waits for it
@@ -796,10 +819,15 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
                       cudaMemset(s->d_flags, 0, 64 * sizeof(int)) == cudaSuccess &&
                       cudaMalloc((void **)&s->d_comm_err, sizeof(int)) == cudaSuccess &&
                       cudaMemset(s->d_comm_err, 0, sizeof(int)) == cudaSuccess;
-            ok = ok && comm_ipc_share(s->d_flags, peers.data(), s->stream) == PMG_OK;
+            // the inbox flags are mapped from EVERY rank once (halo signals use the neighbours' mappings, the
+            // agglomerated-level all-gather all of them)
+            std::vector<void *> flag_peers((size_t)cfg->n_ranks, nullptr);
+            ok = ok && comm_ipc_share(s->d_flags, flag_peers.data(), s->stream, true) == PMG_OK;
             if (ok) {
-                if (s->rank > 0) s->up_flags = (int *)peers[s->rank - 1];
-                if (s->rank < s->n_ranks - 1) s->dn_flags = (int *)peers[s->rank + 1];
+                if (s->rank > 0) s->up_flags = (int *)flag_peers[s->rank - 1];
+                if (s->rank < s->n_ranks - 1) s->dn_flags = (int *)flag_peers[s->rank + 1];
+                for (int r = 0; r < cfg->n_ranks; ++r)
+                    if (r != s->rank) s->agg_maps.push_back(flag_peers[r]);
             }
             for (int l = 0; ok && l < s->agg_level; ++l) {
                 Level &L = s->lv[l];
@@ -819,6 +847,31 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
                         L.ipc_maps[which * 2 + 1] = peers[s->rank + 1];
                     }
                 }
+            }
+            // all-to-all mappings for the agglomerated level: second slab buffer, inbox slots, slab sources
+            if (ok && s->coarse_redundant && s->n_ranks <= 32) {
+                Level &A = s->aslab;
+                s->agg_f[0] = A.base_f;
+                ok = alloc_zero(&s->agg_f[1], A.elems) == PMG_OK;
+                std::vector<void *> pf((size_t)s->n_ranks, nullptr);
+                std::vector<int *> slots((size_t)s->n_ranks, nullptr);
+                for (int r = 0; ok && r < s->n_ranks; ++r)
+                    slots[r] = (r == s->rank ? s->d_flags : (int *)flag_peers[r]) + 32 + s->rank;
+                ok = ok && cudaMalloc((void **)&s->d_agg_slots, sizeof(int *) * s->n_ranks) == cudaSuccess &&
+                     cudaMemcpy(s->d_agg_slots, slots.data(), sizeof(int *) * s->n_ranks, cudaMemcpyHostToDevice) == cudaSuccess;
+                for (int b = 0; ok && b < 2; ++b) {
+                    ok = comm_ipc_share(s->agg_f[b], pf.data(), s->stream, true) == PMG_OK;
+                    if (!ok) break;
+                    std::vector<const double *> srcs((size_t)s->n_ranks, nullptr);
+                    for (int r = 0; r < s->n_ranks; ++r) {
+                        srcs[r] = (const double *)pf[r] + level_origin(A.n) - PADX;  // padded start of local row 0
+                        if (r != s->rank) s->agg_maps.push_back(pf[r]);
+                    }
+                    ok = cudaMalloc((void **)&s->d_agg_srcs[b], sizeof(double *) * s->n_ranks) == cudaSuccess &&
+                         cudaMemcpy(s->d_agg_srcs[b], srcs.data(), sizeof(double *) * s->n_ranks, cudaMemcpyHostToDevice) == cudaSuccess;
+                }
+                const char *eg = getenv("PMG_P2P_GATHER");
+                s->p2p_gather = ok && !(eg && eg[0] == '0');
             }
             // the set-up calls above are collective, so a failure here is a failure everywhere
             if (!ok)
@@ -864,8 +917,11 @@ void pmg_destroy(pmg_solver *s)
     cudaFree(s->d_gather);
     for (Level &L : s->lv)
         for (void *m : L.ipc_maps) comm_ipc_close(m);
-    comm_ipc_close(s->up_flags);
-    comm_ipc_close(s->dn_flags);
+    for (void *m : s->agg_maps) comm_ipc_close(m);  // includes the neighbours' flag mappings
+    cudaFree(s->agg_f[1]);
+    cudaFree(s->d_agg_slots);
+    cudaFree((void *)s->d_agg_srcs[0]);
+    cudaFree((void *)s->d_agg_srcs[1]);
     cudaFree(s->d_flags);
     cudaFree(s->d_comm_err);
     if (s->comm_stream) {
