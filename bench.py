@@ -302,7 +302,7 @@ def main():
     ap.add_argument("--cycles-expected", type=int, default=39, dest="cycles_expected")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA build")
-    ap.add_argument("--agglomerate-below", type=int, default=2049, dest="agglomerate_below",
+    ap.add_argument("--agglomerate-below", type=int, default=513, dest="agglomerate_below",
                     help="multi-GPU: levels with n <= this run on rank 0 only")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -665,7 +665,7 @@ void pmg_config_default(pmg_config *cfg, int n)
     cfg->use_graph = 1;
     cfg->rank = 0;
     cfg->n_ranks = 1;
-    cfg->agglomerate_below = 2049;
+    cfg->agglomerate_below = 513;
     cfg->norm_mode = PMG_NORM_TREE;
 }
 
