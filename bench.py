@@ -45,6 +45,28 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_prefix, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r1_ncu_full_fused_passes_n16385.json, level-0 passes at N = 16385)."""
+    if n != 16385:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_fused_passes_n16385.json")) as fh:
+            recs = json.load(fh)
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = []
+        for r in recs:
+            if r["kernel"].startswith(kernel_prefix):
+                v = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    num, u = r[key].split()
+                    v += float(num) * unit[u]
+                tot.append(v)
+        return sum(tot) / len(tot) if tot else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -224,6 +246,7 @@ def run_single(args):
     alg_bytes = BYTES_PER_POINT_PASS * n * n
     dom_ms, dom_name = (t_upn, "k_up<nu2=2,prolong,norm>") if t_upn >= t_down else (t_down, "k_down<nu1=2,resid>")
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = ncu_traffic("k_up" if t_upn >= t_down else "k_down", n)
     cycle_gbs = BYTES_PER_DOF_CYCLE * n * n * k / (dev_ms / args.steps * 1e-3) / 1e9
     # Jacobi sweep sub-metric: one HBM pass per sweep, 24 B/point
     s.smooth(3, 1)
@@ -279,7 +302,7 @@ def run_single(args):
             "gdof_cycle_per_s": n * n * k / (dev_ms / args.steps * 1e-3) / 1e9,
             "device_ms_per_step": dev_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": dom_name,
+                         "frac": achieved / peak, "traffic": traffic, "kernel": dom_name,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms, "peak_source": peak_src,
                          "pass_down_ms": t_down, "pass_up_norm_ms": t_upn,
                          "vcycle_effective_gbs_at_69.3B_per_dof": cycle_gbs, "vcycle_frac": cycle_gbs / peak},

@@ -82,15 +82,17 @@ extern __shared__ __align__(16) double g_vs_smem[];
 __device__ __forceinline__ void vs_sweeps(double *&cur, double *&oth, const double *f, int n, const JacobiCoef &c,
                                           int sweeps)
 {
-    const int l = n * n;
+    // 2-D thread decomposition (64 columns x blockDim/64 rows): no integer divisions in the point loops
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, nty = blockDim.x >> 6;
     for (int s = 0; s < sweeps; ++s) {
-        for (int i = threadIdx.x; i < l; i += blockDim.x) {
-            int y = i / n, x = i - y * n;
-            double v = cur[i];
-            if (x > 0 && x < n - 1 && y > 0 && y < n - 1)
-                v = jacobi_point(c, f[i], v, cur[i - 1], cur[i + 1], cur[i - n], cur[i + n]);
-            oth[i] = v;
-        }
+        for (int y = ty; y < n; y += nty)
+            for (int x = tx; x < n; x += 64) {
+                const int i = y * n + x;
+                double v = cur[i];
+                if (x > 0 && x < n - 1 && y > 0 && y < n - 1)
+                    v = jacobi_point(c, f[i], v, cur[i - 1], cur[i + 1], cur[i - n], cur[i + n]);
+                oth[i] = v;
+            }
         __syncthreads();
         double *t = cur;
         cur = oth;
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(1024)
 {
     if (done != nullptr && *done) return;
     constexpr int MAXL = 8;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, nty = blockDim.x >> 6;
     double *cur[MAXL], *oth[MAXL], *f[MAXL];
     int n[MAXL];
     double h[MAXL];
@@ -141,26 +144,26 @@ __global__ void __launch_bounds__(1024)
         c.weighted = (omega != 1.0);
         vs_sweeps(cur[k], oth[k], f[k], n[k], c, nu1);
         const double inv_h2 = 1.0 / (h[k] * h[k]);
-        const int m = n[k], l = m * m;
+        const int m = n[k];
         double *r = oth[k];
-        for (int i = threadIdx.x; i < l; i += blockDim.x) {
-            int y = i / m, x = i - y * m;
-            if (x > 0 && x < m - 1 && y > 0 && y < m - 1)
+        for (int y = 1 + ty; y < m - 1; y += nty)
+            for (int x = 1 + tx; x < m - 1; x += 64) {
+                const int i = y * m + x;
                 r[i] = residual_point(inv_h2, f[k][i], cur[k][i], cur[k][i - 1], cur[k][i + 1], cur[k][i - m],
                                       cur[k][i + m]);
-        }
-        __syncthreads();
-        const int mc = n[k + 1], lc = mc * mc;
-        for (int i = threadIdx.x; i < lc; i += blockDim.x) {
-            int jc = i / mc, ic = i - jc * mc;
-            double v = 0.0;
-            if (ic > 0 && ic < mc - 1 && jc > 0 && jc < mc - 1) {
-                const double *q = r + (2 * jc) * m + 2 * ic;
-                v = restrict_point(q[0], q[1], q[-1], q[m], q[-m], q[-m - 1], q[-m + 1], q[m - 1], q[m + 1]);
             }
-            f[k + 1][i] = v;
-            cur[k + 1][i] = 0.0;
-        }
+        __syncthreads();
+        const int mc = n[k + 1];
+        for (int jc = ty; jc < mc; jc += nty)
+            for (int ic = tx; ic < mc; ic += 64) {
+                double v = 0.0;
+                if (ic > 0 && ic < mc - 1 && jc > 0 && jc < mc - 1) {
+                    const double *q = r + (2 * jc) * m + 2 * ic;
+                    v = restrict_point(q[0], q[1], q[-1], q[m], q[-m], q[-m - 1], q[-m + 1], q[m - 1], q[m + 1]);
+                }
+                f[k + 1][jc * mc + ic] = v;
+                cur[k + 1][jc * mc + ic] = 0.0;
+            }
         __syncthreads();
     }
     {  // coarsest level (MultiGrid.hpp:59-63)
@@ -173,11 +176,11 @@ __global__ void __launch_bounds__(1024)
         vs_sweeps(cur[k], oth[k], f[k], n[k], c, nl == 1 ? coarse_sweeps : coarse_sweeps);
     }
     for (int k = nl - 2; k >= 0; --k) {  // up
-        const int m = n[k], l = m * m, mc = n[k + 1];
+        const int m = n[k], mc = n[k + 1];
         const double *e = cur[k + 1];
-        for (int i = threadIdx.x; i < l; i += blockDim.x) {
-            int y = i / m, x = i - y * m;
-            if (x >= lo && y >= lo && x <= m - 2 && y <= m - 2) {
+        for (int y = lo + ty; y <= m - 2; y += nty)
+            for (int x = lo + tx; x <= m - 2; x += 64) {
+                const int i = y * m + x;
                 const double *q = e + (y >> 1) * mc + (x >> 1);
                 double v;
                 if ((y & 1) == 0)
@@ -187,7 +190,6 @@ __global__ void __launch_bounds__(1024)
                                        : dmul(0.25, dadd(dadd(dadd(q[0], q[1]), q[mc]), q[mc + 1]));
                 cur[k][i] = dadd(cur[k][i], v);
             }
-        }
         __syncthreads();
         JacobiCoef c;
         c.h2 = h[k] * h[k];
@@ -541,8 +543,7 @@ void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pi
     size_t smem = vcycle_small_smem(n0, n_coarse);
     static bool once = (cudaFuncSetAttribute(k_vcycle_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
     (void)once;
-    int l = n0 * n0;
-    int threads = l >= 1024 ? 1024 : ((l + 31) / 32) * 32;
+    const int threads = n0 > 33 ? 1024 : (n0 > 17 ? 512 : 256);
     k_vcycle_small<<<1, threads, smem, st>>>(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps,
                                             prolong_mode == PMG_PROLONG_FULL ? 1 : 2, x_is_zero ? 1 : 0, done);
     count_launch();
