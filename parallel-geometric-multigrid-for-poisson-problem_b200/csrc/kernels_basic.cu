@@ -103,7 +103,7 @@ __device__ __forceinline__ void vs_sweeps(double *&cur, double *&oth, const doub
 __global__ void __launch_bounds__(1024)
     k_vcycle_small(double *__restrict__ xg, const double *__restrict__ fg, int n0, int pitch_x, int pitch_f,
                    int n_coarse, double h0, double omega, int nu1, int nu2, int coarse_sweeps, int lo,
-                   int x_is_zero, const int *__restrict__ done)
+                   int x_is_zero, int gamma, const int *__restrict__ done)
 {
     if (done != nullptr && *done) return;
     constexpr int MAXL = 8;
@@ -136,13 +136,17 @@ __global__ void __launch_bounds__(1024)
         cur[0][i] = x_is_zero ? 0.0 : xg[(size_t)y * pitch_x + x];
     }
     __syncthreads();
-    for (int k = 0; k + 1 < nl; ++k) {  // down
+    auto coef_of = [&](int k) {
         JacobiCoef c;
         c.h2 = h[k] * h[k];
         c.omega = omega;
         c.om1 = 1.0 - omega;
         c.weighted = (omega != 1.0);
-        vs_sweeps(cur[k], oth[k], f[k], n[k], c, nu1);
+        return c;
+    };
+    // pre-smooth, residual, restriction into level k+1, whose iterate is zeroed (MultiGrid.hpp:66-82)
+    auto descend = [&](int k) {
+        vs_sweeps(cur[k], oth[k], f[k], n[k], coef_of(k), nu1);
         const double inv_h2 = 1.0 / (h[k] * h[k]);
         const int m = n[k];
         double *r = oth[k];
@@ -165,17 +169,9 @@ __global__ void __launch_bounds__(1024)
                 cur[k + 1][jc * mc + ic] = 0.0;
             }
         __syncthreads();
-    }
-    {  // coarsest level (MultiGrid.hpp:59-63)
-        const int k = nl - 1;
-        JacobiCoef c;
-        c.h2 = h[k] * h[k];
-        c.omega = omega;
-        c.om1 = 1.0 - omega;
-        c.weighted = (omega != 1.0);
-        vs_sweeps(cur[k], oth[k], f[k], n[k], c, nl == 1 ? coarse_sweeps : coarse_sweeps);
-    }
-    for (int k = nl - 2; k >= 0; --k) {  // up
+    };
+    // prolongation-and-add from level k+1, post-smooth (MultiGrid.hpp:86-89)
+    auto ascend = [&](int k) {
         const int m = n[k], mc = n[k + 1];
         const double *e = cur[k + 1];
         for (int y = lo + ty; y <= m - 2; y += nty)
@@ -191,12 +187,38 @@ __global__ void __launch_bounds__(1024)
                 cur[k][i] = dadd(cur[k][i], v);
             }
         __syncthreads();
-        JacobiCoef c;
-        c.h2 = h[k] * h[k];
-        c.omega = omega;
-        c.om1 = 1.0 - omega;
-        c.weighted = (omega != 1.0);
-        vs_sweeps(cur[k], oth[k], f[k], n[k], c, nu2);
+        vs_sweeps(cur[k], oth[k], f[k], n[k], coef_of(k), nu2);
+    };
+    // the recursion of v_cycle (gamma = 1) / w_cycle (gamma visits of every coarser level, MultiGrid.hpp:124-125)
+    // unrolled into a loop; every thread follows the same path
+    if (nl == 1) {
+        vs_sweeps(cur[0], oth[0], f[0], n[0], coef_of(0), coarse_sweeps);
+    } else {
+        int visits[MAXL];
+        int k = 0;
+        bool down = true;
+        for (;;) {
+            if (down) {
+                if (k == nl - 1) {  // coarsest level (MultiGrid.hpp:59-63)
+                    vs_sweeps(cur[k], oth[k], f[k], n[k], coef_of(k), coarse_sweeps);
+                    down = false;
+                    --k;
+                } else {
+                    descend(k);
+                    visits[k] = 0;
+                    ++k;
+                }
+            } else {  // one visit of level k+1 has finished
+                if (++visits[k] < gamma) {
+                    ++k;
+                    down = true;
+                } else {
+                    ascend(k);
+                    if (k == 0) break;
+                    --k;
+                }
+            }
+        }
     }
     for (int i = threadIdx.x; i < n0 * n0; i += blockDim.x) {
         int y = i / n0, x = i - y * n0;
@@ -538,14 +560,14 @@ size_t vcycle_small_smem(int n0, int n_coarse)
 
 void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0,
                          double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
-                         cudaStream_t st, const int *done)
+                         int gamma, cudaStream_t st, const int *done)
 {
     size_t smem = vcycle_small_smem(n0, n_coarse);
     static bool once = (cudaFuncSetAttribute(k_vcycle_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
     (void)once;
     const int threads = n0 > 33 ? 1024 : (n0 > 17 ? 512 : 256);
     k_vcycle_small<<<1, threads, smem, st>>>(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps,
-                                            prolong_mode == PMG_PROLONG_FULL ? 1 : 2, x_is_zero ? 1 : 0, done);
+                                            prolong_mode == PMG_PROLONG_FULL ? 1 : 2, x_is_zero ? 1 : 0, gamma < 1 ? 1 : gamma, done);
     count_launch();
 }
 

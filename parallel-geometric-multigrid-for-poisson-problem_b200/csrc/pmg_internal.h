@@ -79,12 +79,13 @@ constexpr int SMALL_MAX_POINTS = 33 * 33;
 // x_is_zero: start from x == 0 without reading x (first visit of a coarse level)
 void launch_jacobi_small(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h,
                          double omega, int sweeps, bool x_is_zero, cudaStream_t st, const int *done = nullptr);
-// one V-cycle of the levels n0 (<= VSMALL_TOP) ... n_coarse in a single CTA's shared memory; x receives the
-// result on the n0 level (whole array incl. ring); x_is_zero: start from 0 instead of reading x
+// one V- (gamma = 1) or W-cycle (gamma visits of every coarser level) of the levels n0 (<= VSMALL_TOP) ... n_coarse
+// in a single CTA's shared memory; x receives the result on the n0 level (whole array incl. ring);
+// x_is_zero: start from 0 instead of reading x
 constexpr int VSMALL_TOP = 65;
 void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0,
                          double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
-                         cudaStream_t st, const int *done = nullptr);
+                         int gamma, cudaStream_t st, const int *done = nullptr);
 void launch_residual(double *r, const double *x, const double *f, int nx, int ny, int pitch_r,
                      int pitch_x, int pitch_f, double h, cudaStream_t st);
 // sum over the interior of (f - A x)^2 -> *d_out (device double); `d_partials` >= reduce_partials() doubles

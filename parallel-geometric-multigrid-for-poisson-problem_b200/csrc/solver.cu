@@ -236,11 +236,11 @@ static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero,
     Level &L = s->lv[l];
     if (L.n <= c.n_coarse || l + 1 == (int)s->lv.size())
         return smooth_operator(s, l, c.coarse_sweeps, x_is_zero, done);
-    // the small levels of a V-cycle (no repeated visits) run as ONE single-CTA kernel in shared memory
-    if (l > 0 && L.n <= VSMALL_TOP && (!w_form || c.gamma == 1) && s->small_vcycle && (int)s->lv.size() - l <= 8 &&
+    // the small levels (V or W recursion alike) run as ONE single-CTA kernel in shared memory
+    if (l > 0 && L.n <= VSMALL_TOP && s->small_vcycle && (int)s->lv.size() - l <= 8 &&
         s->lv.back().n * s->lv.back().n <= SMALL_MAX_POINTS) {
         launch_vcycle_small(L.x, L.f, L.n, L.pitch, L.pitch, c.n_coarse, L.h, c.omega, c.nu1, c.nu2, c.coarse_sweeps,
-                            c.prolong_mode, x_is_zero, s->stream, done);
+                            c.prolong_mode, x_is_zero, w_form ? c.gamma : 1, s->stream, done);
         return PMG_OK;
     }
     Level &K = s->lv[l + 1];
