@@ -73,204 +73,30 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
-// ---- a whole V- or W-cycle of the small levels inside ONE CTA ---------------------------------------------
+// ---- a whole V-cycle of the small levels inside ONE CTA ------------------------------------------------------
 // Levels n0 (<= VSMALL_TOP) -> ... -> n_coarse live in shared memory (x, scratch, f per level); every operator is
-// the reference's, point for point (pmg_internal.h).  Levels with n > VS_WARP_N are worked on by the whole CTA
-// (block barriers between operators); the sub-tree below -- a few hundred points, but visited gamma^depth times
-// in a W-cycle -- is run by warp 0 alone with warp barriers only.  Replaces 2 launches per level visit (each
-// ~5 us of pure latency at these sizes).  MultiGrid.hpp:57-136 restricted to small N.
+// the reference's, point for point (pmg_internal.h), separated by block barriers.  Replaces 2 launches per
+// level (each ~5 us of pure latency at these sizes) by one.  MultiGrid.hpp:57-94 restricted to small N.
 extern __shared__ __align__(16) double g_vs_smem[];
-constexpr int VS_MAXL = 8;
-constexpr int VS_WARP_N = 17;
 
-struct VsLevels {
-    double *cur[VS_MAXL], *oth[VS_MAXL], *f[VS_MAXL];
-    int n[VS_MAXL];
-    double h[VS_MAXL];
-    int nl;
-    double omega;
-    int nu1, nu2, coarse_sweeps, lo, gamma;
-};
-
-template <bool WARP>
-struct VsScope {
-    int tx, ty, sx, sy;
-    __device__ __forceinline__ VsScope()
-    {
-        if (WARP) {
-            tx = threadIdx.x & 31; ty = 0; sx = 32; sy = 1;
-        } else {
-            tx = threadIdx.x & 63; ty = threadIdx.x >> 6; sx = 64; sy = blockDim.x >> 6;
-        }
-    }
-    __device__ __forceinline__ void sync() const
-    {
-        if (WARP)
-            __syncwarp();
-        else
-            __syncthreads();
-    }
-};
-
-__device__ __forceinline__ JacobiCoef vs_coef(const VsLevels &L, int k)
+__device__ __forceinline__ void vs_sweeps(double *&cur, double *&oth, const double *f, int n, const JacobiCoef &c,
+                                          int sweeps)
 {
-    JacobiCoef c;
-    c.h2 = L.h[k] * L.h[k];
-    c.omega = L.omega;
-    c.om1 = 1.0 - L.omega;
-    c.weighted = (L.omega != 1.0);
-    return c;
-}
-
-template <bool WARP>
-__device__ __forceinline__ void vs_sweeps(VsLevels &L, int k, int sweeps)
-{
-    const VsScope<WARP> t;
-    const int n = L.n[k];
-    const JacobiCoef c = vs_coef(L, k);
-    const double *f = L.f[k];
+    // 2-D thread decomposition (64 columns x blockDim/64 rows): no integer divisions in the point loops
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, nty = blockDim.x >> 6;
     for (int s = 0; s < sweeps; ++s) {
-        const double *cur = L.cur[k];
-        double *oth = L.oth[k];
-        for (int y = t.ty; y < n; y += t.sy)
-            for (int x = t.tx; x < n; x += t.sx) {
+        for (int y = ty; y < n; y += nty)
+            for (int x = tx; x < n; x += 64) {
                 const int i = y * n + x;
                 double v = cur[i];
                 if (x > 0 && x < n - 1 && y > 0 && y < n - 1)
                     v = jacobi_point(c, f[i], v, cur[i - 1], cur[i + 1], cur[i - n], cur[i + n]);
                 oth[i] = v;
             }
-        t.sync();
-        L.oth[k] = L.cur[k];
-        L.cur[k] = oth;
-    }
-}
-
-// pre-smooth, residual, restriction into level k+1, whose iterate is zeroed (MultiGrid.hpp:66-82)
-template <bool WARP>
-__device__ __forceinline__ void vs_descend(VsLevels &L, int k)
-{
-    const VsScope<WARP> t;
-    vs_sweeps<WARP>(L, k, L.nu1);
-    const double inv_h2 = 1.0 / (L.h[k] * L.h[k]);
-    const int m = L.n[k];
-    const double *cur = L.cur[k], *f = L.f[k];
-    double *r = L.oth[k];
-    for (int y = 1 + t.ty; y < m - 1; y += t.sy)
-        for (int x = 1 + t.tx; x < m - 1; x += t.sx) {
-            const int i = y * m + x;
-            r[i] = residual_point(inv_h2, f[i], cur[i], cur[i - 1], cur[i + 1], cur[i - m], cur[i + m]);
-        }
-    t.sync();
-    const int mc = L.n[k + 1];
-    double *fc = L.f[k + 1], *xc = L.cur[k + 1];
-    for (int jc = t.ty; jc < mc; jc += t.sy)
-        for (int ic = t.tx; ic < mc; ic += t.sx) {
-            double v = 0.0;
-            if (ic > 0 && ic < mc - 1 && jc > 0 && jc < mc - 1) {
-                const double *q = r + (2 * jc) * m + 2 * ic;
-                v = restrict_point(q[0], q[1], q[-1], q[m], q[-m], q[-m - 1], q[-m + 1], q[m - 1], q[m + 1]);
-            }
-            fc[jc * mc + ic] = v;
-            xc[jc * mc + ic] = 0.0;
-        }
-    t.sync();
-}
-
-// prolongation-and-add from level k+1, post-smooth (MultiGrid.hpp:86-89)
-template <bool WARP>
-__device__ __forceinline__ void vs_ascend(VsLevels &L, int k)
-{
-    const VsScope<WARP> t;
-    const int m = L.n[k], mc = L.n[k + 1], lo = L.lo;
-    const double *e = L.cur[k + 1];
-    double *cur = L.cur[k];
-    for (int y = lo + t.ty; y <= m - 2; y += t.sy)
-        for (int x = lo + t.tx; x <= m - 2; x += t.sx) {
-            const int i = y * m + x;
-            const double *q = e + (y >> 1) * mc + (x >> 1);
-            double v;
-            if ((y & 1) == 0)
-                v = ((x & 1) == 0) ? q[0] : dmul(0.5, dadd(q[0], q[1]));
-            else
-                v = ((x & 1) == 0) ? dmul(0.5, dadd(q[0], q[mc]))
-                                   : dmul(0.25, dadd(dadd(dadd(q[0], q[1]), q[mc]), q[mc + 1]));
-            cur[i] = dadd(cur[i], v);
-        }
-    t.sync();
-    vs_sweeps<WARP>(L, k, L.nu2);
-}
-
-
-// After warp 0 has run `gamma` visits of the sub-tree rooted at level k, bring every thread's cur/oth pointers of the
-// levels >= k to the state warp 0 ended in: a level's buffers swap once per sweep, and the number of sweeps is a
-// function of the schedule only.
-__device__ __forceinline__ void vs_replay_swaps(VsLevels &L, int k)
-{
-    long visits = L.gamma;  // visits of level k
-    for (int j = k; j < L.nl; ++j) {
-        long sweeps = visits * ((j == L.nl - 1) ? L.coarse_sweeps : (L.nu1 + L.nu2));
-        if (sweeps & 1) {
-            double *t = L.cur[j];
-            L.cur[j] = L.oth[j];
-            L.oth[j] = t;
-        }
-        visits *= L.gamma;
-    }
-}
-
-// One visit of level k_top and everything below it: the recursion of v_cycle (gamma = 1) / w_cycle (gamma visits
-// of every coarser level, MultiGrid.hpp:124-125) unrolled into a loop; all participating threads take the same
-// path.  In block scope the sub-tree whose top level has n <= VS_WARP_N is handed to warp 0.
-template <bool WARP>
-__device__ void vs_visit(VsLevels &L, int k_top)
-{
-    const int last = L.nl - 1;
-    if (k_top == last) {  // coarsest level (MultiGrid.hpp:59-63)
-        vs_sweeps<WARP>(L, last, L.coarse_sweeps);
-        return;
-    }
-    int visits[VS_MAXL];
-    int k = k_top;
-    bool down = true;
-    for (;;) {
-        if (down) {
-            if (k == last) {
-                vs_sweeps<WARP>(L, k, L.coarse_sweeps);
-                down = false;
-                --k;
-            } else {
-                vs_descend<WARP>(L, k);
-                visits[k] = 0;
-                if (!WARP && L.n[k + 1] <= VS_WARP_N) {
-                    // hand the whole sub-tree (all gamma visits) to warp 0; its pointer swaps are made in every
-                    // thread's copy of L by running the same bookkeeping without touching memory
-                    VsLevels Lw = L;
-                    if ((threadIdx.x >> 5) == 0)
-                        for (int rep = 0; rep < L.gamma; ++rep) vs_visit<true>(Lw, k + 1);
-                    __syncthreads();
-                    // parity of the pointer swaps below level k is a pure function of the schedule
-                    vs_replay_swaps(L, k + 1);
-                    visits[k] = L.gamma;
-                    down = false;
-                    // fallthrough to the "up" branch of this iteration's successor
-                    vs_ascend<WARP>(L, k);
-                    if (k == k_top) break;
-                    --k;
-                } else {
-                    ++k;
-                }
-            }
-        } else {  // one visit of level k+1 has finished
-            if (++visits[k] < L.gamma) {
-                ++k;
-                down = true;
-            } else {
-                vs_ascend<WARP>(L, k);
-                if (k == k_top) break;
-                --k;
-            }
-        }
+        __syncthreads();
+        double *t = cur;
+        cur = oth;
+        oth = t;
     }
 }
 
@@ -280,27 +106,25 @@ __global__ void __launch_bounds__(1024)
                    int x_is_zero, int gamma, const int *__restrict__ done)
 {
     if (done != nullptr && *done) return;
-    VsLevels L;
-    L.nl = 0;
-    L.omega = omega;
-    L.nu1 = nu1;
-    L.nu2 = nu2;
-    L.coarse_sweeps = coarse_sweeps;
-    L.lo = lo;
-    L.gamma = gamma;
+    constexpr int MAXL = 8;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, nty = blockDim.x >> 6;
+    double *cur[MAXL], *oth[MAXL], *f[MAXL];
+    int n[MAXL];
+    double h[MAXL];
+    int nl = 0;
     {
         double *p = g_vs_smem;
         int m = n0;
         double hh = h0;
         for (;;) {
-            L.n[L.nl] = m;
-            L.h[L.nl] = hh;
-            L.cur[L.nl] = p;
-            L.oth[L.nl] = p + m * m;
-            L.f[L.nl] = p + 2 * m * m;
+            n[nl] = m;
+            h[nl] = hh;
+            cur[nl] = p;
+            oth[nl] = p + m * m;
+            f[nl] = p + 2 * m * m;
             p += 3 * m * m;
-            ++L.nl;
-            if (m <= n_coarse || m <= 3 || L.nl == VS_MAXL) break;
+            ++nl;
+            if (m <= n_coarse || m <= 3 || nl == MAXL) break;
             m = (m - 1) / 2 + 1;
             hh = 2 * hh;  // MultiGrid.hpp:83
         }
@@ -308,32 +132,97 @@ __global__ void __launch_bounds__(1024)
     // level 0: right-hand side from global memory, iterate zero (first visit of a coarse level) or loaded
     for (int i = threadIdx.x; i < n0 * n0; i += blockDim.x) {
         int y = i / n0, x = i - y * n0;
-        L.f[0][i] = fg[(size_t)y * pitch_f + x];
-        L.cur[0][i] = x_is_zero ? 0.0 : xg[(size_t)y * pitch_x + x];
+        f[0][i] = fg[(size_t)y * pitch_f + x];
+        cur[0][i] = x_is_zero ? 0.0 : xg[(size_t)y * pitch_x + x];
     }
     __syncthreads();
-    if (L.n[0] <= VS_WARP_N) {  // the whole hierarchy is warp-sized
-        if ((threadIdx.x >> 5) == 0) vs_visit<true>(L, 0);
+    auto coef_of = [&](int k) {
+        JacobiCoef c;
+        c.h2 = h[k] * h[k];
+        c.omega = omega;
+        c.om1 = 1.0 - omega;
+        c.weighted = (omega != 1.0);
+        return c;
+    };
+    // pre-smooth, residual, restriction into level k+1, whose iterate is zeroed (MultiGrid.hpp:66-82)
+    auto descend = [&](int k) {
+        vs_sweeps(cur[k], oth[k], f[k], n[k], coef_of(k), nu1);
+        const double inv_h2 = 1.0 / (h[k] * h[k]);
+        const int m = n[k];
+        double *r = oth[k];
+        for (int y = 1 + ty; y < m - 1; y += nty)
+            for (int x = 1 + tx; x < m - 1; x += 64) {
+                const int i = y * m + x;
+                r[i] = residual_point(inv_h2, f[k][i], cur[k][i], cur[k][i - 1], cur[k][i + 1], cur[k][i - m],
+                                      cur[k][i + m]);
+            }
         __syncthreads();
-        // only warp 0's copy of L is current: the other warps recompute the final buffer roles by sweep parity
-        long visits = 1;
-        for (int j = 0; j < L.nl; ++j) {
-            if ((threadIdx.x >> 5) != 0) {
-                long sweeps = visits * ((j == L.nl - 1) ? L.coarse_sweeps : (L.nu1 + L.nu2));
-                if (sweeps & 1) {
-                    double *t = L.cur[j];
-                    L.cur[j] = L.oth[j];
-                    L.oth[j] = t;
+        const int mc = n[k + 1];
+        for (int jc = ty; jc < mc; jc += nty)
+            for (int ic = tx; ic < mc; ic += 64) {
+                double v = 0.0;
+                if (ic > 0 && ic < mc - 1 && jc > 0 && jc < mc - 1) {
+                    const double *q = r + (2 * jc) * m + 2 * ic;
+                    v = restrict_point(q[0], q[1], q[-1], q[m], q[-m], q[-m - 1], q[-m + 1], q[m - 1], q[m + 1]);
+                }
+                f[k + 1][jc * mc + ic] = v;
+                cur[k + 1][jc * mc + ic] = 0.0;
+            }
+        __syncthreads();
+    };
+    // prolongation-and-add from level k+1, post-smooth (MultiGrid.hpp:86-89)
+    auto ascend = [&](int k) {
+        const int m = n[k], mc = n[k + 1];
+        const double *e = cur[k + 1];
+        for (int y = lo + ty; y <= m - 2; y += nty)
+            for (int x = lo + tx; x <= m - 2; x += 64) {
+                const int i = y * m + x;
+                const double *q = e + (y >> 1) * mc + (x >> 1);
+                double v;
+                if ((y & 1) == 0)
+                    v = ((x & 1) == 0) ? q[0] : dmul(0.5, dadd(q[0], q[1]));
+                else
+                    v = ((x & 1) == 0) ? dmul(0.5, dadd(q[0], q[mc]))
+                                       : dmul(0.25, dadd(dadd(dadd(q[0], q[1]), q[mc]), q[mc + 1]));
+                cur[k][i] = dadd(cur[k][i], v);
+            }
+        __syncthreads();
+        vs_sweeps(cur[k], oth[k], f[k], n[k], coef_of(k), nu2);
+    };
+    // the recursion of v_cycle (gamma = 1) / w_cycle (gamma visits of every coarser level, MultiGrid.hpp:124-125)
+    // unrolled into a loop; every thread follows the same path
+    if (nl == 1) {
+        vs_sweeps(cur[0], oth[0], f[0], n[0], coef_of(0), coarse_sweeps);
+    } else {
+        int visits[MAXL];
+        int k = 0;
+        bool down = true;
+        for (;;) {
+            if (down) {
+                if (k == nl - 1) {  // coarsest level (MultiGrid.hpp:59-63)
+                    vs_sweeps(cur[k], oth[k], f[k], n[k], coef_of(k), coarse_sweeps);
+                    down = false;
+                    --k;
+                } else {
+                    descend(k);
+                    visits[k] = 0;
+                    ++k;
+                }
+            } else {  // one visit of level k+1 has finished
+                if (++visits[k] < gamma) {
+                    ++k;
+                    down = true;
+                } else {
+                    ascend(k);
+                    if (k == 0) break;
+                    --k;
                 }
             }
-            visits *= L.gamma;
         }
-    } else {
-        vs_visit<false>(L, 0);
     }
     for (int i = threadIdx.x; i < n0 * n0; i += blockDim.x) {
         int y = i / n0, x = i - y * n0;
-        xg[(size_t)y * pitch_x + x] = L.cur[0][i];
+        xg[(size_t)y * pitch_x + x] = cur[0][i];
     }
 }
 
