@@ -72,3 +72,28 @@ def test_reference_style_driver_matches_goldens(golden):
     assert abs(sm["res0"] - g["smoother_residuals"][0]) <= 1e-12 * sm["res0"]
     assert abs(sm["res1"] - g["smoother_residuals"][1]) <= 1e-12 * sm["res1"]
     assert len(by["gpu_exec_v3"]) == 3
+
+
+@pytest.mark.gpu
+def test_pmg_runner_writes_reference_output_formats(golden, tmp_path):
+    """tools/pmg_runner.cpp: run_all_cycles_err_h / time_h protocols, OUTPUT_RESULT text formats
+    (2_part_MG/save_to_file.hpp:59-151) with the reference's own numbers in them."""
+    exe = os.path.join(PKG, "pmg_runner")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", PKG, "pmg_runner"], check=True)
+    out = str(tmp_path / "OUTPUT_RESULT")
+    p = subprocess.run([exe, "err_h", "--n", "129,257", "--iters", "1", "--out", out], capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode == 0, p.stderr
+    want = {r["n"]: r for r in golden["mg_cpu_exec_rel_l2_error"]}
+    for tag, key in (("v", "V"), ("w", "W"), ("f", "F")):
+        rows = [l.split() for l in open(os.path.join(out, "h_errors_%s_cycle1.txt" % tag)).read().splitlines()]
+        assert [int(r[0]) for r in rows] == [129, 257]
+        for r in rows:
+            assert abs(float(r[1]) - want[int(r[0])][key]) <= 2e-6 * want[int(r[0])][key]  # 6 printed digits
+    assert "Final Relative L2 Error: 0.171973" in p.stdout
+    p = subprocess.run([exe, "ops", "--n", "257,1025", "--out", out], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    for name in ("residual", "jacobi", "restriction", "prolungator"):
+        rows = [l.split() for l in open(os.path.join(out, "timings_%s_gpu.txt" % name)).read().splitlines()]
+        assert [r[:2] for r in rows] == [["32", "257"], ["32", "1025"]] and all(float(r[2]) > 0 for r in rows)
