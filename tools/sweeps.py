@@ -33,6 +33,9 @@ else:
     import torch
     import torch.distributed as dist
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 32769
+    # fp64 floor of the UN-SCALED residual norm: ~4 eps/h^2 per entry times sqrt(N^2) = 4.8e-8 ||r0|| at N = 32769
+    # (1.2e-8 at 16385, which is why the reference's last cycles there slow down) -- 1e-8 is out of reach here
+    tol = float(sys.argv[3]) if len(sys.argv) > 3 else (1e-8 if n <= 16385 else 1e-6)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
@@ -50,13 +53,14 @@ else:
         if world > 1:
             torch.cuda.synchronize()
             dist.barrier()
-        k, hist = s.solve(pmg.V, 1e-8, 100)
+        k, hist = s.solve(pmg.V, tol, 100)
         best = s.last_ms if best is None else min(best, s.last_ms)
     if rank == 0:
         print(json.dumps({"n": n, "gpus": world, "dof_per_gpu_M": round(n * n / world / 1e6, 1), "cycles": k,
                           "solve_ms": round(best, 3), "ms_per_cycle": round(best / k, 4),
                           "gdof_cycle_per_s_per_gpu": round(n * n * k / best / 1e6 / world, 2),
-                          "converged": bool(hist[-1] < 1e-8 * hist[0])}), flush=True)
+                          "rel_tol": tol, "converged": bool(hist[-1] < tol * hist[0]),
+                          "final_rel": float(hist[-1] / hist[0])}), flush=True)
     s.close()
     if world > 1:
         pmg.comm_finalize()
