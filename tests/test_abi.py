@@ -84,3 +84,47 @@ def test_partition_rows(n, ranks):
             y0, y1 = pmg.partition_rows(n, ranks, r)
             c0, c1 = y0 // 2, (nc if r == ranks - 1 else y1 // 2)
             assert 2 * c0 == y0 and (r == ranks - 1 or 2 * c1 == y1)
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` runs on the host cores (no GPU needed) and prints one JSON line with the
+    contract's keys; it is the only place outside tests/ that executes oracle/ (as the CPU baseline)."""
+    import json
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["dtype"] == "f64" and line["unit"] == "GDOF/s"
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_product_never_touches_the_oracle():
+    """The product path (package, csrc, include, bench_dist) must not import, link or name oracle/."""
+    pkg = os.path.dirname(pmg.LIB_PATH)
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".cu", ".h", ".hpp", ".py", ".cpp")) or fn == "Makefile":
+                text = open(os.path.join(base, fn), errors="ignore").read()
+                if "oracle" in text.replace("the oracle", "").lower() and ("liboracle" in text or "cpu_checkers" in text
+                                                                          or "oracle/" in text):
+                    offenders.append(os.path.join(base, fn))
+    for fn in ("include/pmg.h", "include/pmg.hpp", "pmg_b200.py"):
+        text = open(os.path.join(ROOT, fn)).read()
+        if "liboracle" in text or "cpu_checkers" in text or "oracle/" in text:
+            offenders.append(fn)
+    assert not offenders, offenders
+    out = subprocess_check_ldd(pmg.LIB_PATH)
+    assert "oracle" not in out and "pmg_ref" not in out
+
+
+def subprocess_check_ldd(path):
+    import subprocess
+    return subprocess.run(["ldd", path], capture_output=True, text=True).stdout
