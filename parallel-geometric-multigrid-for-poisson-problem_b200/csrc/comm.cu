@@ -195,17 +195,17 @@ pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int p
 }
 
 // ---- NVLink peer access (CUDA IPC) ----------------------------------------------------------------------
-// Every rank exports one cudaMalloc'ed allocation; on return peers[r] is a pointer through which THIS
-// process can load/store rank r's allocation over NVLink (peers[own rank] = base).  Collective.
-pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st, bool all_peers)
+// Phase 1 (collective): every rank exports one cudaMalloc'ed allocation; `handles` (n_ranks entries of
+// IPC_HANDLE_BYTES) receives everybody's handle.  Nothing is opened here, so a rank cannot drop out half way.
+pmg_status comm_ipc_exchange(void *base, unsigned char *handles, cudaStream_t st)
 {
+    static_assert(sizeof(cudaIpcMemHandle_t) == IPC_HANDLE_BYTES, "IPC handle size");
     if (!g_comm) return PMG_OK;
     cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
     cudaError_t e = cudaIpcGetMemHandle(&mine, base);
-    if (e != cudaSuccess) {
-        g_last_error = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
-        return PMG_ERR_COMM;
-    }
+    bool have = (e == cudaSuccess);
+    if (!have) cudaGetLastError();
     const size_t hb = sizeof(cudaIpcMemHandle_t);
     unsigned char *d_mine = nullptr, *d_all = nullptr;
     if (cudaMalloc((void **)&d_mine, hb) != cudaSuccess || cudaMalloc((void **)&d_all, hb * g_nranks) != cudaSuccess) {
@@ -214,8 +214,7 @@ pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st, bool all_pe
     }
     cudaMemcpyAsync(d_mine, &mine, hb, cudaMemcpyHostToDevice, st);
     ncclResult_t r = g_nccl.AllGather(d_mine, d_all, hb, ncclInt8, g_comm, st);
-    std::vector<cudaIpcMemHandle_t> all(g_nranks);
-    cudaMemcpyAsync(all.data(), d_all, hb * g_nranks, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(handles, d_all, hb * g_nranks, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
     cudaFree(d_mine);
     cudaFree(d_all);
@@ -224,22 +223,39 @@ pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st, bool all_pe
         g_last_error = std::string("ipc handle exchange: ") + cudaGetErrorString(e);
         return PMG_ERR_CUDA;
     }
-    for (int q = 0; q < g_nranks; ++q) {
-        if (q == g_rank) {
-            peers[q] = base;
-            continue;
-        }
-        peers[q] = nullptr;
-        // only the neighbours' mappings are ever used; opening all of them keeps the call collective-free
-        if (!all_peers && q != g_rank - 1 && q != g_rank + 1) continue;
-        e = cudaIpcOpenMemHandle(&peers[q], all[q], cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            g_last_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
-            cudaGetLastError();
-            return PMG_ERR_COMM;
-        }
+    if (!have) {
+        g_last_error = "cudaIpcGetMemHandle failed";
+        return PMG_ERR_COMM;  // reported AFTER the collective so that the other ranks are not left waiting
     }
     return PMG_OK;
+}
+
+// Phase 2 (local): map one exchanged handle; nullptr on failure.
+void *comm_ipc_open(const unsigned char *handle)
+{
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+// Phase 3 (collective): true iff every rank says ok.
+bool comm_all_agree(bool ok, double *d_scratch /* 1 + n_ranks doubles */, cudaStream_t st)
+{
+    if (!g_comm) return ok;
+    double mine = ok ? 1.0 : 0.0;
+    std::vector<double> all((size_t)g_nranks, 0.0);
+    cudaMemcpyAsync(d_scratch, &mine, sizeof(double), cudaMemcpyHostToDevice, st);
+    ncclResult_t r = g_nccl.AllGather(d_scratch, d_scratch + 1, 1, ncclFloat64, g_comm, st);
+    cudaMemcpyAsync(all.data(), d_scratch + 1, sizeof(double) * g_nranks, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || r != 0) return false;
+    for (double v : all)
+        if (v != 1.0) return false;
+    return true;
 }
 
 void comm_ipc_close(void *peer)

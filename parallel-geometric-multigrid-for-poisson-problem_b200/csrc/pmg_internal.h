@@ -167,8 +167,12 @@ pmg_status comm_gather_rows(const double *slab, double *full, int pitch, const i
 pmg_status comm_scatter_rows(const double *full, double *slab, int n_rows, int pitch, const int *y0s,
                              const int *y1s, int halo, cudaStream_t st);
 pmg_status comm_allgather_double(const double *d_mine, double *d_all, cudaStream_t st);
-// CUDA IPC: peers[r] = a pointer in this process to rank r's allocation `base` (neighbours only; others null)
-pmg_status comm_ipc_share(void *base, void **peers, cudaStream_t st, bool all_peers = false);
+// CUDA IPC in three phases so that no rank can leave a collective half way: (1) exchange handles (collective),
+// (2) open the mappings needed (local), (3) agree that everybody succeeded (collective).
+constexpr int IPC_HANDLE_BYTES = 64;
+pmg_status comm_ipc_exchange(void *base, unsigned char *handles /* n_ranks * IPC_HANDLE_BYTES */, cudaStream_t st);
+void *comm_ipc_open(const unsigned char *handle);
+bool comm_all_agree(bool ok, double *d_scratch /* 1 + n_ranks doubles */, cudaStream_t st);
 void comm_ipc_close(void *peer);
 
 // ---- NVLink peer-to-peer halo exchange (kernels_basic.cu) -------------------------------------------------

@@ -813,71 +813,100 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         const char *env = getenv("PMG_P2P");
         bool want = !(env && env[0] == '0');
         if (want) {
-            // inbox flags + error word, then the x / f arrays of every slab level, shared with the neighbours
-            std::vector<void *> peers((size_t)cfg->n_ranks, nullptr);
+            // Everything the neighbours (halo pulls) or all ranks (agglomerated-level all-gather) read over NVLink
+            // is exported with CUDA IPC: the inbox flags, the x / f slab arrays of every partitioned level and the
+            // two buffers of the first agglomerated level's right-hand side.
+            const int R = cfg->n_ranks, me = cfg->rank;
             bool ok = cudaMalloc((void **)&s->d_flags, 64 * sizeof(int)) == cudaSuccess &&
                       cudaMemset(s->d_flags, 0, 64 * sizeof(int)) == cudaSuccess &&
                       cudaMalloc((void **)&s->d_comm_err, sizeof(int)) == cudaSuccess &&
                       cudaMemset(s->d_comm_err, 0, sizeof(int)) == cudaSuccess;
-            // the inbox flags are mapped from EVERY rank once (halo signals use the neighbours' mappings, the
-            // agglomerated-level all-gather all of them)
-            std::vector<void *> flag_peers((size_t)cfg->n_ranks, nullptr);
-            ok = ok && comm_ipc_share(s->d_flags, flag_peers.data(), s->stream, true) == PMG_OK;
-            if (ok) {
-                if (s->rank > 0) s->up_flags = (int *)flag_peers[s->rank - 1];
-                if (s->rank < s->n_ranks - 1) s->dn_flags = (int *)flag_peers[s->rank + 1];
-                for (int r = 0; r < cfg->n_ranks; ++r)
-                    if (r != s->rank) s->agg_maps.push_back(flag_peers[r]);
+            const bool want_gather = s->coarse_redundant && R <= 32;
+            if (want_gather) {
+                s->agg_f[0] = s->aslab.base_f;
+                ok = ok && alloc_zero(&s->agg_f[1], s->aslab.elems) == PMG_OK;
             }
-            for (int l = 0; ok && l < s->agg_level; ++l) {
+            // (1) handle exchange: the same list on every rank, whatever happened locally so far
+            std::vector<void *> bases;
+            bases.push_back(s->d_flags);
+            for (int l = 0; l < s->agg_level; ++l) {
+                bases.push_back(s->lv[l].base_x);
+                bases.push_back(s->lv[l].base_f);
+            }
+            if (want_gather) {
+                bases.push_back(s->agg_f[0]);
+                bases.push_back(s->agg_f[1]);
+            }
+            std::vector<std::vector<unsigned char>> hs(bases.size(), std::vector<unsigned char>((size_t)R * IPC_HANDLE_BYTES));
+            for (size_t i = 0; i < bases.size(); ++i)
+                ok = (comm_ipc_exchange(bases[i], hs[i].data(), s->stream) == PMG_OK) && ok;
+            if (const char *ef = getenv("PMG_P2P_FAIL_RANK"))  // test hook: pretend this rank cannot map its peers
+                if (atoi(ef) == me) ok = false;
+            // (2) local mappings
+            auto open_peer = [&](size_t i, int r) -> void * {
+                if (!ok) return nullptr;
+                void *p = comm_ipc_open(hs[i].data() + (size_t)r * IPC_HANDLE_BYTES);
+                if (!p) {
+                    ok = false;
+                    return nullptr;
+                }
+                s->agg_maps.push_back(p);
+                return p;
+            };
+            std::vector<void *> flag_peers((size_t)R, nullptr);
+            for (int r = 0; r < R; ++r)
+                if (r != me && (want_gather || r == me - 1 || r == me + 1)) flag_peers[r] = open_peer(0, r);
+            if (ok) {
+                if (me > 0) s->up_flags = (int *)flag_peers[me - 1];
+                if (me < R - 1) s->dn_flags = (int *)flag_peers[me + 1];
+            }
+            size_t bi = 1;
+            for (int l = 0; l < s->agg_level; ++l) {
                 Level &L = s->lv[l];
                 const size_t o = level_origin(L.n);
-                for (int which = 0; ok && which < 2; ++which) {
-                    ok = comm_ipc_share(which == 0 ? L.base_x : L.base_f, peers.data(), s->stream) == PMG_OK;
-                    if (!ok) break;
-                    if (s->rank > 0) {
-                        int ny_up = s->y1s[l][s->rank - 1] - s->y0s[l][s->rank - 1];
-                        const double *p = (const double *)peers[s->rank - 1] + o + (ptrdiff_t)(ny_up - PADY) * L.pitch;
-                        (which == 0 ? L.up_x : L.up_f) = p;
-                        L.ipc_maps[which * 2] = peers[s->rank - 1];
+                for (int which = 0; which < 2; ++which, ++bi) {
+                    if (me > 0) {
+                        int ny_up = s->y1s[l][me - 1] - s->y0s[l][me - 1];
+                        const double *p = (const double *)open_peer(bi, me - 1);
+                        if (p) (which == 0 ? L.up_x : L.up_f) = p + o + (ptrdiff_t)(ny_up - PADY) * L.pitch;
                     }
-                    if (s->rank < s->n_ranks - 1) {
-                        const double *p = (const double *)peers[s->rank + 1] + o;
-                        (which == 0 ? L.dn_x : L.dn_f) = p;
-                        L.ipc_maps[which * 2 + 1] = peers[s->rank + 1];
+                    if (me < R - 1) {
+                        const double *p = (const double *)open_peer(bi, me + 1);
+                        if (p) (which == 0 ? L.dn_x : L.dn_f) = p + o;
                     }
                 }
             }
-            // all-to-all mappings for the agglomerated level: second slab buffer, inbox slots, slab sources
-            if (ok && s->coarse_redundant && s->n_ranks <= 32) {
-                Level &A = s->aslab;
-                s->agg_f[0] = A.base_f;
-                ok = alloc_zero(&s->agg_f[1], A.elems) == PMG_OK;
-                std::vector<void *> pf((size_t)s->n_ranks, nullptr);
-                std::vector<int *> slots((size_t)s->n_ranks, nullptr);
-                for (int r = 0; ok && r < s->n_ranks; ++r)
-                    slots[r] = (r == s->rank ? s->d_flags : (int *)flag_peers[r]) + 32 + s->rank;
-                ok = ok && cudaMalloc((void **)&s->d_agg_slots, sizeof(int *) * s->n_ranks) == cudaSuccess &&
-                     cudaMemcpy(s->d_agg_slots, slots.data(), sizeof(int *) * s->n_ranks, cudaMemcpyHostToDevice) == cudaSuccess;
-                for (int b = 0; ok && b < 2; ++b) {
-                    ok = comm_ipc_share(s->agg_f[b], pf.data(), s->stream, true) == PMG_OK;
-                    if (!ok) break;
-                    std::vector<const double *> srcs((size_t)s->n_ranks, nullptr);
-                    for (int r = 0; r < s->n_ranks; ++r) {
-                        srcs[r] = (const double *)pf[r] + level_origin(A.n) - PADX;  // padded start of local row 0
-                        if (r != s->rank) s->agg_maps.push_back(pf[r]);
+            if (want_gather) {
+                std::vector<int *> slots((size_t)R, nullptr);
+                for (int r = 0; ok && r < R; ++r) slots[r] = (r == me ? s->d_flags : (int *)flag_peers[r]) + 32 + me;
+                ok = ok && cudaMalloc((void **)&s->d_agg_slots, sizeof(int *) * R) == cudaSuccess &&
+                     cudaMemcpy(s->d_agg_slots, slots.data(), sizeof(int *) * R, cudaMemcpyHostToDevice) == cudaSuccess;
+                for (int b = 0; b < 2; ++b, ++bi) {
+                    std::vector<const double *> srcs((size_t)R, nullptr);
+                    for (int r = 0; r < R; ++r) {
+                        const double *p = (r == me) ? s->agg_f[b] : (const double *)open_peer(bi, r);
+                        srcs[r] = p ? p + level_origin(s->aslab.n) - PADX : nullptr;  // padded start of local row 0
                     }
-                    ok = cudaMalloc((void **)&s->d_agg_srcs[b], sizeof(double *) * s->n_ranks) == cudaSuccess &&
-                         cudaMemcpy(s->d_agg_srcs[b], srcs.data(), sizeof(double *) * s->n_ranks, cudaMemcpyHostToDevice) == cudaSuccess;
+                    ok = ok && cudaMalloc((void **)&s->d_agg_srcs[b], sizeof(double *) * R) == cudaSuccess &&
+                         cudaMemcpy(s->d_agg_srcs[b], srcs.data(), sizeof(double *) * R, cudaMemcpyHostToDevice) == cudaSuccess;
                 }
+            }
+            // (3) every rank takes the same path: NVLink pulls if all mappings exist everywhere, NCCL otherwise
+            double *d_agree = nullptr;
+            bool all_ok = cudaMalloc((void **)&d_agree, sizeof(double) * (R + 1)) == cudaSuccess &&
+                          comm_all_agree(ok, d_agree, s->stream);
+            cudaFree(d_agree);
+            if (!all_ok) {
+                for (void *m : s->agg_maps) comm_ipc_close(m);
+                s->agg_maps.clear();
+                s->up_flags = s->dn_flags = nullptr;
+                for (int l = 0; l < s->agg_level; ++l) s->lv[l].up_x = s->lv[l].dn_x = s->lv[l].up_f = s->lv[l].dn_f = nullptr;
+                s->p2p = s->p2p_gather = false;
+            } else {
                 const char *eg = getenv("PMG_P2P_GATHER");
-                s->p2p_gather = ok && !(eg && eg[0] == '0');
+                s->p2p_gather = want_gather && !(eg && eg[0] == '0');
+                s->p2p = true;
             }
-            // the set-up calls above are collective, so a failure here is a failure everywhere
-            if (!ok)
-                return bail(fail(PMG_ERR_COMM, std::string("CUDA IPC set-up failed (") + g_last_error +
-                                                   "); set PMG_P2P=0 to exchange halos with NCCL send/recv"));
-            s->p2p = true;
         }
     }
     s->partials_cap = std::max(reduce_partials(), fused_max_partials(cfg->n));
@@ -915,8 +944,6 @@ void pmg_destroy(pmg_solver *s)
     cudaFree(s->aslab.base_x);
     cudaFree(s->aslab.base_f);
     cudaFree(s->d_gather);
-    for (Level &L : s->lv)
-        for (void *m : L.ipc_maps) comm_ipc_close(m);
     for (void *m : s->agg_maps) comm_ipc_close(m);  // includes the neighbours' flag mappings
     cudaFree(s->agg_f[1]);
     cudaFree(s->d_agg_slots);
