@@ -89,7 +89,7 @@ typedef struct pmg_config {
     int use_graph;       /* 1: replay each cycle as a CUDA graph                                    */
     /* ---- multi-GPU (row-slab decomposition, one process per GPU); leave zeroed for 1 GPU ---- */
     int rank, n_ranks;
-    int agglomerate_below; /* levels with n <= this run on rank 0 only                              */
+    int agglomerate_below; /* levels with n <= this are all-gathered and solved redundantly by every rank (513) */
     int norm_mode;       /* pmg_norm_mode: how the per-cycle residual norm is summed                */
     int reserved[7];
 } pmg_config;
@@ -163,7 +163,11 @@ pmg_status pmg_device_synchronize(void);
 int pmg_device_count(void);
 
 /* ---- multi-GPU bootstrap (one process per GPU; ids travel over the caller's own channel, e.g.
- *      torch.distributed) -------------------------------------------------------------------------- */
+ *      torch.distributed).  With n_ranks > 1 the solver partitions every fine level into row slabs; pmg_set_rhs /
+ *      pmg_set_guess / pmg_get_solution then move THIS RANK'S rows [y0, y1) (pmg_partition_rows), (y1-y0) x n
+ *      doubles.  Halo rows travel over NVLink peer memory (CUDA IPC) when every rank can map its neighbours,
+ *      over NCCL send/recv otherwise (PMG_P2P=0 forces the latter).  V- and W-cycles, nu <= 2; results are
+ *      bit-identical to one GPU. ----------------------------------------------------------------------- */
 #define PMG_COMM_ID_BYTES 128
 pmg_status pmg_comm_unique_id(unsigned char id[PMG_COMM_ID_BYTES]);
 /* must be called (collectively) before pmg_create with cfg.n_ranks > 1 */

@@ -76,7 +76,6 @@ struct Level {
     // NVLink peer-to-peer halo exchange: the neighbours' boundary rows of x and f as seen from this process
     // (upper neighbour's row ny_up - PADY, lower neighbour's row 0) and the raw IPC mappings to close
     const double *up_x = nullptr, *dn_x = nullptr, *up_f = nullptr, *dn_f = nullptr;
-    void *ipc_maps[4] = {nullptr, nullptr, nullptr, nullptr};
     int halo_epoch = 0;
 };
 
