@@ -445,18 +445,6 @@ __global__ void k_halo_signal(int *up_flag, int *dn_flag, int epoch)
     if (dn_flag) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dn_flag), "r"(epoch) : "memory");
 }
 
-__device__ __forceinline__ bool wait_flag(const int *flag, int epoch)
-{
-    // bounded: ~2 s at 1 us per probe, then give up (the host reports the error instead of hanging the GPU)
-    for (int it = 0; it < 2000000; ++it) {
-        int v;
-        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (v >= epoch) return true;
-        __nanosleep(1000);
-    }
-    return false;
-}
-
 // blockIdx.y: 0 = rows from the upper neighbour into my rows [-depth, 0), 1 = from the lower into [ny, ny+depth)
 __global__ void __launch_bounds__(256)
     k_halo_pull(double *__restrict__ mine, int ny, int pitch, int depth, const double *__restrict__ up_src,

@@ -184,24 +184,60 @@ __device__ __forceinline__ void strip_setup(const StripGeom &g, int wid, int lan
 // Row feeds: how rows of x and f travel from HBM to the pipeline, and where the delay line of f rows
 // (f of row j-d, needed by stage d) lives.
 // ---------------------------------------------------------------------------------------------------
+// Where a row comes from: this rank's slab, or -- for halo rows of a fused halo exchange -- the neighbour's HBM.
+struct RowSource {
+    const double *x_up, *x_dn, *f_up, *f_dn;  // already offset by this lane's column
+    double *f_keep;
+    int ny, pitch;
+    __device__ __forceinline__ void init(const HaloPeers &hp, int col, int ny_, int pitch_)
+    {
+        x_up = hp.x_up ? hp.x_up + col : nullptr;
+        x_dn = hp.x_dn ? hp.x_dn + col : nullptr;
+        f_up = hp.f_up ? hp.f_up + col : nullptr;
+        f_dn = hp.f_dn ? hp.f_dn + col : nullptr;
+        f_keep = hp.f_keep ? hp.f_keep + col : nullptr;
+        ny = ny_;
+        pitch = pitch_;
+    }
+    __device__ __forceinline__ const double *x_row(const double *local, int row) const
+    {
+        if (row < 0 && x_up) return x_up + (ptrdiff_t)row * pitch;
+        if (row >= ny && x_dn) return x_dn + (ptrdiff_t)(row - ny) * pitch;
+        return local + (ptrdiff_t)row * pitch;
+    }
+    __device__ __forceinline__ const double *f_row(const double *local, int row) const
+    {
+        if (row < 0 && f_up) return f_up + (ptrdiff_t)row * pitch;
+        if (row >= ny && f_dn) return f_dn + (ptrdiff_t)(row - ny) * pitch;
+        return local + (ptrdiff_t)row * pitch;
+    }
+    // f halo rows fetched from a peer are kept locally for the later Pass B
+    __device__ __forceinline__ bool keeps(int row) const
+    {
+        return f_keep != nullptr && ((row < 0 && f_up) || (row >= ny && f_dn));
+    }
+};
+
 template <int C, int PF, int S, bool USE_X>
 struct RegFeed {
     static constexpr int UNROLL = PF;  // slot index must be static: the row loop is unrolled by PF
     static constexpr int SMEM_PER_WARP = 0;
     Row<C> xbuf[PF], fbuf[PF], fq[S + 2];
     const double *x, *f;
+    RowSource src;
     int pitch, last_row;
     __device__ __forceinline__ void init(const double *x_, const double *f_, int pitch_, int col, int j_start,
-                                         int last_row_, int /*lane*/, int /*warp_in_cta*/)
+                                         int last_row_, int /*lane*/, int /*warp_in_cta*/, const HaloPeers &hp, int ny)
     {
         x = x_ + col;
         f = f_ + col;
         pitch = pitch_;
         last_row = last_row_;
+        src.init(hp, col, ny, pitch_);
 #pragma unroll
         for (int d = 0; d < PF; ++d) {
-            xbuf[d] = USE_X ? load_row<C>(x + (ptrdiff_t)(j_start + d) * pitch) : zero_row<C>();
-            fbuf[d] = load_row<C>(f + (ptrdiff_t)(j_start + d) * pitch);
+            xbuf[d] = USE_X ? load_row<C>(src.x_row(x, j_start + d)) : zero_row<C>();
+            fbuf[d] = load_row<C>(src.f_row(f, j_start + d));
         }
 #pragma unroll
         for (int d = 0; d < S + 2; ++d) fq[d] = zero_row<C>();
@@ -213,9 +249,10 @@ struct RegFeed {
 #pragma unroll
         for (int d = S + 1; d > 0; --d) fq[d] = fq[d - 1];
         fq[0] = fbuf[u];
+        if (src.keeps(jj)) store_row<C>(src.f_keep + (ptrdiff_t)jj * pitch, fq[0]);
         int nr = min(jj + PF, last_row);
-        if (USE_X) xbuf[u] = load_row<C>(x + (ptrdiff_t)nr * pitch);
-        fbuf[u] = load_row<C>(f + (ptrdiff_t)nr * pitch);
+        if (USE_X) xbuf[u] = load_row<C>(src.x_row(x, nr));
+        fbuf[u] = load_row<C>(src.f_row(f, nr));
         return cur;
     }
     __device__ __forceinline__ Row<C> f_row(int d) const { return fq[d]; }  // f of row jj - d
@@ -246,15 +283,16 @@ struct SmemFeed {
     static_assert(PF + S + 2 <= NF && PF + 1 <= 4, "ring too small");
     uint32_t fbase, xbase;  // shared-window addresses of this lane's first piece in slot 0
     const double *x, *f;
+    RowSource src;
     int pitch, last_row, t;
     __device__ __forceinline__ void issue(int row, int slot_t)
     {
-        const double *fr = f + (ptrdiff_t)row * pitch;
+        const double *fr = src.f_row(f, row);
         uint32_t fa = fbase + (uint32_t)(slot_t & (NF - 1)) * ROW_BYTES;
 #pragma unroll
         for (int p = 0; p < PLANES; ++p) cp_async16(fa + p * 512, fr + 2 * p);
         if (USE_X) {
-            const double *xr = x + (ptrdiff_t)row * pitch;
+            const double *xr = src.x_row(x, row);
             uint32_t xa = xbase + (uint32_t)(slot_t & 3) * ROW_BYTES;
 #pragma unroll
             for (int p = 0; p < PLANES; ++p) cp_async16(xa + p * 512, xr + 2 * p);
@@ -270,13 +308,14 @@ struct SmemFeed {
         return r;
     }
     __device__ __forceinline__ void init(const double *x_, const double *f_, int pitch_, int col, int j_start,
-                                         int last_row_, int lane, int warp_in_cta)
+                                         int last_row_, int lane, int warp_in_cta, const HaloPeers &hp, int ny)
     {
         x = x_ + col;
         f = f_ + col;
         pitch = pitch_;
         last_row = last_row_;
         t = 0;
+        src.init(hp, col, ny, pitch_);
         uint32_t base = (uint32_t)__cvta_generic_to_shared(g_dyn_smem) + warp_in_cta * SMEM_PER_WARP;
         // zero this lane's pieces (warm-up steps read slots that were never filled)
 #pragma unroll
@@ -292,6 +331,7 @@ struct SmemFeed {
     __device__ __forceinline__ Row<C> begin(int /*u*/, int jj)
     {
         cp_async_wait<PF - 1>();  // all but the newest PF-1 groups have landed => row jj is in its slot
+        if (src.keeps(jj)) store_row<C>(src.f_keep + (ptrdiff_t)jj * pitch, lds_row(fbase + (uint32_t)(t & (NF - 1)) * ROW_BYTES));
         Row<C> cur = USE_X ? lds_row(xbase + (uint32_t)(t & 3) * ROW_BYTES) : zero_row<C>();
         issue(min(jj + PF, last_row), t + PF);
         return cur;
@@ -319,7 +359,7 @@ template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID, bool 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_down(const double *__restrict__ x, double *__restrict__ xo, const double *__restrict__ f,
            double *__restrict__ cf, StripGeom g, int pitch_c, int nc, JacobiCoef coef, double inv_h2,
-           const int *__restrict__ done)
+           const int *__restrict__ done, HaloPeers hp)
 {
     using Feed = typename FeedSelect<C, PF, S, !ZEROX, SM>::type;
     if (done != nullptr && *done) return;  // device-side convergence control: the solve already stopped
@@ -350,8 +390,21 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
     for (int q = 0; q < NP; ++q) s_mid[q] = s_cor[q] = c_mid[q] = c_ew[q] = 0.0;
 
+    // fused halo exchange: before the first access to a neighbour's rows, wait until it has published them
+    if (hp.flag_up != nullptr || hp.flag_dn != nullptr) {
+        int ok = 1;
+        if (lane == 0) {
+            if (hp.flag_up != nullptr) ok = wait_flag(hp.flag_up, hp.epoch) ? ok : 0;
+            if (hp.flag_dn != nullptr) ok = wait_flag(hp.flag_dn, hp.epoch) ? ok : 0;
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) {
+            if (lane == 0) *hp.err = 1;
+            return;
+        }
+    }
     Feed feed;
-    feed.init(x, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5);
+    feed.init(x, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5, hp, g.ny);
     const int ycoarse = g.yoff >> 1;  // global coarse row of local coarse row 0
 
     for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
@@ -471,7 +524,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     for (int k = 0; k < C; ++k) cprol[k] = (col + k >= lo) && (col + k <= g.n - 2);
 
     Feed feed;
-    feed.init(xb, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5);
+    feed.init(xb, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5, HaloPeers{}, g.ny);
 
     // coarse rows: ec = row jc, en = row jc+1, eb = prefetch of row jc+2 (raw, before the shuffle)
     const int cc = col >> 1;
@@ -625,19 +678,19 @@ void down_launch_w(const FusedLevel &lv, double *cf, int pitch_c, bool x_is_zero
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done);
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
     } else if (resid) {
         auto k = k_down<C, PF, MINB, SM, S, false, true, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done);
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
     } else {
         auto k = k_down<C, PF, MINB, SM, S, false, false, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv, done);
+        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv, done, lv.hp);
     }
 }
 

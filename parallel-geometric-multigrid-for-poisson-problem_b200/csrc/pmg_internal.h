@@ -128,6 +128,29 @@ void launch_rhs_separable(double *f, int pitch, int nx, int ny, double factor, c
                           const double *sy, cudaStream_t st);
 
 // ---- fused streaming kernels (kernels_fused.cu) ---------------------------------------------------
+// Halo rows read straight out of the neighbours' HBM over NVLink (all null on one GPU / when the halo rows are
+// local).  Local row r < 0 lives at up + r*pitch, local row r >= ny at dn + (r - ny)*pitch (pointers to logical
+// column 0).  f halo rows fetched this way are also written to `f_keep` so that the later Pass B reads them locally.
+struct HaloPeers {
+    const double *x_up, *x_dn, *f_up, *f_dn;
+    double *f_keep;
+    const int *flag_up, *flag_dn;  // inbox flags that must reach `epoch` before the first peer access
+    int epoch;
+    int *err;                      // raised if that wait times out
+};
+
+// bounded acquire spin on a flag another GPU publishes with st.release.sys (~2 s, then give up)
+__device__ __forceinline__ bool wait_flag(const int *flag, int epoch)
+{
+    for (int it = 0; it < 2000000; ++it) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= epoch) return true;
+        __nanosleep(1000);
+    }
+    return false;
+}
+
 struct FusedLevel {
     double *x;    // logical (0,0) of the level's current iterate
     double *xb;   // ping-pong partner
@@ -138,6 +161,7 @@ struct FusedLevel {
     // [-PADY, ny + PADY); local row 0 is global row yoff.  ext_lo/ext_hi: see StripGeom.
     int ny, yoff, ext_lo, ext_hi;
     int span_lo, span_hi;  // if span_hi > span_lo: write only local rows [span_lo, span_hi) (span_lo even)
+    HaloPeers hp;          // Pass A only: fused halo exchange (wait for the neighbours, read their rows in place)
 };
 // Pass A (down): xb = S^nu1(x);  coarse_f(interior) = R(f - A xb).  x_is_zero: the iterate is known to
 // be identically zero on entry (coarse levels of a V-cycle) so x is not read.

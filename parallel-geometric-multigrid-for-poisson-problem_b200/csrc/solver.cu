@@ -124,6 +124,7 @@ struct pmg_solver {
     bool coarse_redundant = false;           // every rank solves the agglomerated levels (all-gather, no scatter)
     int split_min_rows = 2048;               // slabs at least this tall overlap the exchange with interior rows
     bool p2p = false;                        // halo rows are pulled from the neighbours' memory over NVLink
+    bool p2p_fused = true;                   // ... by Pass A itself (no pull kernel, no local copy of the x halo)
     int *d_flags = nullptr;                  // my inbox: [level][from_up, from_dn] epochs published by neighbours
     int *up_flags = nullptr, *dn_flags = nullptr;  // the neighbours' inboxes (peer mappings)
     int *d_comm_err = nullptr;               // raised by a pull whose wait timed out
@@ -161,6 +162,7 @@ static FusedLevel fused_view(const Level &L)
     v.yoff = L.y0;
     v.ext_lo = v.ext_hi = 0;
     v.span_lo = v.span_hi = 0;
+    v.hp = HaloPeers{};
     return v;
 }
 
@@ -307,6 +309,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     double *halo_field = !x_is_zero ? L.x : (l > 0 ? L.f : nullptr);
     const bool split = halo_field && L.ny >= s->split_min_rows && (up_nb || dn_nb);
     FusedLevel v = fused_view(L);
+    HaloPeers halo_peers{};
     if (halo_field) {
         int epoch = 0;
         if (s->p2p) {  // publish "my boundary rows of this level are final" in the neighbours' inboxes
@@ -322,14 +325,34 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             PMG_CUDA(cudaEventRecord(s->ev_ready, s->stream));
             PMG_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
         }
-        if (s->p2p) {
+        HaloPeers hp{};
+        if (s->p2p && s->p2p_fused) {
+            // FUSED: Pass A waits for the neighbours' epoch itself and reads their boundary rows in place over
+            // NVLink; the f rows it fetches are kept in the local halo rows for Pass B.  Level 0 keeps reading
+            // its static local f halo (exchanged once in pmg_set_rhs).
+            if (!x_is_zero) {
+                hp.x_up = up_nb ? L.up_x + (ptrdiff_t)PADY * L.pitch : nullptr;
+                hp.x_dn = dn_nb ? L.dn_x : nullptr;
+            }
+            if (l > 0) {
+                hp.f_up = up_nb ? L.up_f + (ptrdiff_t)PADY * L.pitch : nullptr;
+                hp.f_dn = dn_nb ? L.dn_f : nullptr;
+                hp.f_keep = L.f;
+            }
+            hp.flag_up = up_nb ? s->d_flags + 2 * l : nullptr;
+            hp.flag_dn = dn_nb ? s->d_flags + 2 * l + 1 : nullptr;
+            hp.epoch = epoch;
+            hp.err = s->d_comm_err;
+        } else if (s->p2p) {  // separate pull kernel: neighbours' rows are copied into the local halo rows
             const bool is_x = (halo_field == L.x);
             launch_halo_pull(halo_field, L.ny, L.pitch, PADY, is_x ? L.up_x : L.up_f, is_x ? L.dn_x : L.dn_f,
                              s->d_flags + 2 * l, s->d_flags + 2 * l + 1, epoch, s->d_comm_err, xs);
         } else if ((rc = comm_halo_exchange(halo_field, L.ny, L.pitch, PADY, xs)) != PMG_OK) {
             return rc;
         }
+        halo_peers = hp;
         if (split) {
+            v.hp = hp;
             if (up_nb) {
                 v.span_lo = -6;
                 v.span_hi = PADY;
@@ -340,6 +363,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
                 v.span_hi = L.ny + 6;
                 launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->comm_stream, nullptr);
             }
+            v.hp = HaloPeers{};
         }
         if (xs == s->comm_stream) PMG_CUDA(cudaEventRecord(s->ev_halo, s->comm_stream));
     }
@@ -356,6 +380,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         trace_mark(s, "halo", l);
         v.span_lo = up_nb ? -6 : 0;
         v.span_hi = dn_nb ? L.ny + 6 : L.ny;
+        v.hp = halo_peers;  // fused exchange (null when the halo rows were copied in)
         launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, nullptr);
         trace_mark(s, "passA", l);
     }
@@ -793,6 +818,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         const char *env = getenv("PMG_COARSE_GATHER");
         s->coarse_redundant = equal && !(env && env[0] == '1');
         if (const char *e2 = getenv("PMG_SPLIT_MIN_ROWS")) s->split_min_rows = atoi(e2);
+        if (const char *e3 = getenv("PMG_P2P_FUSED")) s->p2p_fused = !(e3[0] == '0');
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
