@@ -166,8 +166,8 @@ int pmg_device_count(void);
  *      torch.distributed).  With n_ranks > 1 the solver partitions every fine level into row slabs; pmg_set_rhs /
  *      pmg_set_guess / pmg_get_solution then move THIS RANK'S rows [y0, y1) (pmg_partition_rows), (y1-y0) x n
  *      doubles.  Halo rows travel over NVLink peer memory (CUDA IPC) when every rank can map its neighbours,
- *      over NCCL send/recv otherwise (PMG_P2P=0 forces the latter).  V- and W-cycles, nu <= 2; results are
- *      bit-identical to one GPU. ----------------------------------------------------------------------- */
+ *      over NCCL send/recv otherwise (PMG_P2P=0 forces the latter).  V-, W- and F-cycles, nu <= 2; results are
+ *      bit-identical to one GPU (the F-cycle needs equally sized slabs: n_ranks a power of two). ------------ */
 #define PMG_COMM_ID_BYTES 128
 pmg_status pmg_comm_unique_id(unsigned char id[PMG_COMM_ID_BYTES]);
 /* must be called (collectively) before pmg_create with cfg.n_ranks > 1 */

@@ -378,12 +378,15 @@ __global__ void __launch_bounds__(1024)
 
 // ---- full-weighting restriction: MultiGrid.hpp:187-205 (replaces restriction_kernel_full_weighting,
 //      Parallel_Method.cu:48-78) ---------------------------------------------------------------------
+//      Row slabs: `rows` local coarse rows, local row 0 = global coarse row `yoff` (local fine row = 2 * local
+//      coarse row because slabs start on even fine rows); whole level: rows = nc, yoff = 0.
 __global__ void __launch_bounds__(BX *BY)
-    k_restrict(const double *__restrict__ fine, double *__restrict__ coarse, int nc, int pitch_f, int pitch_c)
+    k_restrict(const double *__restrict__ fine, double *__restrict__ coarse, int nc, int rows, int yoff, int pitch_f,
+               int pitch_c)
 {
     int ic = blockIdx.x * BX + threadIdx.x;
     int jc = blockIdx.y * BY + threadIdx.y;
-    if (ic < 1 || jc < 1 || ic >= nc - 1 || jc >= nc - 1) return;
+    if (ic < 1 || ic >= nc - 1 || jc >= rows || jc + yoff < 1 || jc + yoff >= nc - 1) return;
     const double *c = fine + (size_t)(2 * jc) * pitch_f + 2 * ic;
     coarse[(size_t)jc * pitch_c + ic] =
         restrict_point(c[0], c[1], c[-1], c[pitch_f], c[-pitch_f], c[-pitch_f - 1], c[-pitch_f + 1],
@@ -393,13 +396,15 @@ __global__ void __launch_bounds__(BX *BY)
 // ---- bilinear prolongation-and-add: MultiGrid.hpp:208-226.  One thread per FINE point; the parity of
 //      (x, y) selects the same expression the reference's coarse-point loop evaluates for that point.
 //      lo = 2 (REFERENCE: fine row/col 1 skipped) or 1 (FULL). ---------------------------------------
+//      Row slabs: `rows` local fine rows, local row 0 = global fine row `yoff` (even), coarse local row 0 =
+//      global coarse row yoff / 2; whole level: rows = nf, yoff = 0.
 __global__ void __launch_bounds__(BX *BY)
-    k_prolong_add(const double *__restrict__ coarse, double *__restrict__ fine, int nf, int pitch_c,
-                  int pitch_f, int lo)
+    k_prolong_add(const double *__restrict__ coarse, double *__restrict__ fine, int nf, int rows, int yoff,
+                  int pitch_c, int pitch_f, int lo)
 {
     int x = blockIdx.x * BX + threadIdx.x;
     int y = blockIdx.y * BY + threadIdx.y;
-    if (x < lo || y < lo || x > nf - 2 || y > nf - 2) return;
+    if (x < lo || x > nf - 2 || y >= rows || y + yoff < lo || y + yoff > nf - 2) return;
     int ic = x >> 1, jc = y >> 1;
     const double *c = coarse + (size_t)jc * pitch_c + ic;
     double v;
@@ -653,7 +658,15 @@ void launch_norm2(const double *v, size_t l, double *d_partials, double *d_out, 
 void launch_restrict(const double *fine, double *coarse, int nf, int nc, int pitch_f, int pitch_c, cudaStream_t st)
 {
     (void)nf;
-    k_restrict<<<grid2d(nc, nc), dim3(BX, BY), 0, st>>>(fine, coarse, nc, pitch_f, pitch_c);
+    k_restrict<<<grid2d(nc, nc), dim3(BX, BY), 0, st>>>(fine, coarse, nc, nc, 0, pitch_f, pitch_c);
+    count_launch();
+}
+
+void launch_restrict_rows(const double *fine, double *coarse, int nc, int rows_c, int yoff_c, int pitch_f,
+                          int pitch_c, cudaStream_t st)
+{
+    if (rows_c < 1) return;
+    k_restrict<<<grid2d(nc, rows_c), dim3(BX, BY), 0, st>>>(fine, coarse, nc, rows_c, yoff_c, pitch_f, pitch_c);
     count_launch();
 }
 
@@ -661,8 +674,17 @@ void launch_prolong_add(const double *coarse, double *fine, int nc, int nf, int 
                         cudaStream_t st)
 {
     (void)nc;
-    k_prolong_add<<<grid2d(nf, nf), dim3(BX, BY), 0, st>>>(coarse, fine, nf, pitch_c, pitch_f,
+    k_prolong_add<<<grid2d(nf, nf), dim3(BX, BY), 0, st>>>(coarse, fine, nf, nf, 0, pitch_c, pitch_f,
                                                            mode == PMG_PROLONG_FULL ? 1 : 2);
+    count_launch();
+}
+
+void launch_prolong_add_rows(const double *coarse, double *fine, int nf, int rows_f, int yoff_f, int pitch_c,
+                             int pitch_f, int mode, cudaStream_t st)
+{
+    if (rows_f < 1) return;
+    k_prolong_add<<<grid2d(nf, rows_f), dim3(BX, BY), 0, st>>>(coarse, fine, nf, rows_f, yoff_f, pitch_c, pitch_f,
+                                                               mode == PMG_PROLONG_FULL ? 1 : 2);
     count_launch();
 }
 

@@ -119,6 +119,14 @@ void launch_restrict(const double *fine, double *coarse, int nf, int nc, int pit
                      cudaStream_t st);
 void launch_prolong_add(const double *coarse, double *fine, int nc, int nf, int pitch_c, int pitch_f,
                         int mode, cudaStream_t st);
+// the same two operators on ROW SLABS (pointers address each slab's local row 0, column 0): rows_c / rows_f local
+// rows whose global index is local + yoff_c / yoff_f; yoff_f is even and the coarse slab starts at yoff_f / 2, so
+// local fine row 2j sits under local coarse row j.  Restriction reads fine rows [-1, 2*rows_c); prolongation
+// reads coarse rows [0, rows_f / 2 + 1].
+void launch_restrict_rows(const double *fine, double *coarse, int nc, int rows_c, int yoff_c, int pitch_f,
+                          int pitch_c, cudaStream_t st);
+void launch_prolong_add_rows(const double *coarse, double *fine, int nf, int rows_f, int yoff_f, int pitch_c,
+                             int pitch_f, int mode, cudaStream_t st);
 // dst(y,x) = src(y,x) for a ny x nx window, arbitrary pitches (layout conversion at the ABI)
 void launch_copy2d(double *dst, int pitch_d, const double *src, int pitch_s, int nx, int ny,
                    cudaStream_t st);

@@ -549,6 +549,117 @@ static pmg_status cycle_f(pmg_solver *s)
     return rc;
 }
 
+// The F-cycle on row slabs.  Same operator sequence as cycle_f, level by level:
+//   * levels l < agg_level are slabs: every slab operator that reads a neighbour row is preceded by an NCCL halo
+//     exchange of PADY rows (set-up work -- a handful of exchanges per level, not on the V-cycle's critical path);
+//     the FMG smoothing runs as passes of <= 2 sweeps (8 halo rows in, >= 6 valid rows out), x -> xb -> x, so the
+//     x / f pointers the neighbours have mapped over NVLink never change roles;
+//   * levels l >= agg_level are whole on every rank and processed redundantly, exactly as on one GPU (every rank
+//     computes bit-identical copies);
+//   * the V-cycle of level l is cycle_dist started at level l (cycle_fused for the whole levels).
+// Every phase boundary that re-writes an array a neighbour may still be reading over NVLink (x, f of a slab level)
+// has an NCCL exchange with that neighbour in between, which orders the write after the neighbour's reads.
+static pmg_status cycle_f_dist(pmg_solver *s)
+{
+    if (!s->coarse_redundant)
+        return fail(PMG_ERR_UNSUPPORTED, "multi-GPU F-cycle needs equally sized slabs on the first agglomerated level");
+    pmg_status rc = ensure_fmg(s);
+    if (rc != PMG_OK) return rc;
+    const pmg_config &c = s->cfg;
+    const int nl = (int)s->lv.size(), lc = nl - 1, la = s->agg_level;
+    const bool up_nb = s->rank > 0, dn_nb = s->rank < s->n_ranks - 1;
+    const int *ay0 = s->y0s[la].data(), *ay1 = s->y1s[la].data();
+    Level &A = s->lv[la];
+    s->cycle_has_collective = false;  // the agglomerated level travels by NCCL all-gather inside these V-cycles
+    // (1) phi restricted down to the coarsest grid (MultiGridTestRunner.hpp:192-200); scratch = the xb arrays
+    for (int l = 0; l < lc; ++l) {
+        Level &L = s->lv[l];
+        if (l < la) {
+            double *fine = (l == 0) ? L.x : L.xb;
+            if ((rc = comm_halo_exchange(fine, L.ny, L.pitch, PADY, s->stream)) != PMG_OK) return rc;
+            Level &K = (l + 1 == la) ? s->aslab : s->lv[l + 1];
+            double *coarse = (l + 1 == la) ? K.x : K.xb;
+            launch_restrict_rows(fine, coarse, K.n, K.ny, K.y0, L.pitch, K.pitch, s->stream);
+            if (l + 1 == la && (rc = comm_allgather_rows(K.x, A.xb, ay1[0] - ay0[0], A.pitch, s->stream)) != PMG_OK)
+                return rc;
+        } else {
+            Level &K = s->lv[l + 1];
+            launch_restrict(L.xb, K.xb, L.n, K.n, L.pitch, K.pitch, s->stream);
+        }
+    }
+    launch_copy2d(s->lv[lc].x, s->lv[lc].pitch, s->lv[lc].xb, s->lv[lc].pitch, s->lv[lc].n, s->lv[lc].n, s->stream);
+    // (2) nested iteration upwards with the ANALYTIC right-hand side on every level (MultiGrid.hpp:150-170)
+    const double factor = (M_PI * M_PI / (1.0 * 1.0)) * (1.0 * 1.0 + 1.0 * 1.0);  // DynamicGridUtils.hpp:113, a = p = q = 1
+    double *user_f = s->lv[0].f;
+    analytic_rhs(s, s->lv[lc], s->lv[lc].f);
+    for (int l = lc - 1; l >= 0; --l) {
+        Level &K = s->lv[l + 1];
+        Level &L = s->lv[l];
+        // smoother->smooth(phi_current, f_current, N, N, h, 3)  (:153)
+        if (l + 1 >= la) {
+            if (fused_supported(c.fmg_sweeps) && K.n * K.n > SMALL_MAX_POINTS) {
+                launch_fused_down(fused_view(K), nullptr, 0, c.fmg_sweeps, c.omega, false, s->stream);
+                std::swap(K.x, K.xb);
+                std::swap(K.base_x, K.base_xb);
+            } else if ((rc = smooth_operator(s, l + 1, c.fmg_sweeps, false)) != PMG_OK) {
+                break;
+            }
+        } else {
+            double *cur = K.x, *oth = K.xb;
+            int left = c.fmg_sweeps;
+            do {
+                if ((rc = comm_halo_exchange(cur, K.ny, K.pitch, PADY, s->stream)) != PMG_OK) return rc;
+                const int b = std::min(2, left);
+                if (b > 0) {
+                    FusedLevel v = fused_view(K);
+                    v.x = cur;
+                    v.xb = oth;
+                    v.ext_lo = up_nb ? 2 : 0;  // one coarse row beyond the slab feeds the prolongation below
+                    v.ext_hi = dn_nb ? 2 : 0;
+                    launch_fused_down(v, nullptr, 0, b, c.omega, false, s->stream);
+                    std::swap(cur, oth);
+                }
+                left -= b;
+            } while (left > 0);
+            if (cur != K.x) {  // odd number of passes: bring rows [-2, ny + 2) back into the x array
+                const int a = up_nb ? -2 : 0, b = K.ny + (dn_nb ? 2 : 0);
+                PMG_CUDA(cudaMemcpyAsync(K.x - PADX + (ptrdiff_t)a * K.pitch, K.xb - PADX + (ptrdiff_t)a * K.pitch,
+                                         (size_t)(b - a) * K.pitch * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+            }
+        }
+        if (l < la) {
+            // analytic RHS of my rows, halo rows included (:162); zeroed iterate (:161); prolongation (:164)
+            double *f_l = (l == 0) ? s->f_fmg0 : L.f;
+            const int ga = std::max(L.y0 - PADY, 0), gb = std::min(L.y0 + L.ny + PADY, L.n);
+            launch_rhs_separable(f_l + (ptrdiff_t)(ga - L.y0) * L.pitch, L.pitch, L.n, gb - ga, factor, L.d_sin,
+                                 L.d_sin + ga, s->stream);
+            PMG_CUDA(cudaMemsetAsync(L.base_x, 0, L.elems * sizeof(double), s->stream));
+            const double *e = K.x;
+            int pitch_e = K.pitch;
+            if (l + 1 == la) {  // the whole level's rows around my slab -> the slab-shaped window
+                Level &W = s->aslab;
+                const int a = std::max(0, ay0[s->rank] - 4), b = std::min(A.n, ay1[s->rank] + 4);
+                PMG_CUDA(cudaMemcpyAsync(W.x - PADX + (ptrdiff_t)(a - ay0[s->rank]) * W.pitch, A.x - PADX + (ptrdiff_t)a * A.pitch,
+                                         (size_t)(b - a) * A.pitch * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+                e = W.x;
+                pitch_e = W.pitch;
+            }
+            launch_prolong_add_rows(e, L.x, L.n, L.ny, L.y0, pitch_e, L.pitch, c.prolong_mode, s->stream);
+            if (l == 0) L.f = s->f_fmg0;
+            rc = cycle_dist(s, l, false, false, false, nullptr, nullptr);  // :167
+            if (l == 0) L.f = user_f;
+        } else {
+            analytic_rhs(s, L, L.f);
+            launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);
+            launch_prolong_add(K.x, L.x, K.n, L.n, K.pitch, L.pitch, c.prolong_mode, s->stream);
+            rc = cycle_fused(s, l, false, false, false, nullptr);
+        }
+        if (rc != PMG_OK) break;
+    }
+    s->lv[0].f = user_f;
+    return rc;
+}
+
 // One fused V/W cycle, replayed from a CUDA graph when allowed.  mode 0: no norm, 1: norm -> d_scalar,
 // 2: norm -> device-side solve control (k_cycle_finish) with every kernel honouring ctrl->done.
 static bool fused_graph_ok(const pmg_solver *s)
@@ -620,9 +731,8 @@ static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
 static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
 {
     pmg_status rc;
-    if (s->dist && kind == PMG_CYCLE_F) return fail(PMG_ERR_UNSUPPORTED, "the F-cycle is single-GPU only");
     if (kind == PMG_CYCLE_F) {
-        rc = cycle_f(s);
+        rc = s->dist ? cycle_f_dist(s) : cycle_f(s);
         if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
         return rc;
     }
@@ -1078,6 +1188,16 @@ pmg_status pmg_residual_norm(pmg_solver *s, double *norm_out)
     return PMG_OK;
 }
 
+// a peer-to-peer wait that timed out raised the device flag (bounded spins never hang the GPU)
+static pmg_status check_comm_err(pmg_solver *s)
+{
+    if (!s->p2p) return PMG_OK;
+    int err = 0;
+    PMG_CUDA(cudaMemcpy(&err, s->d_comm_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return fail(PMG_ERR_COMM, "peer-to-peer halo exchange timed out waiting for a neighbour");
+    return PMG_OK;
+}
+
 pmg_status pmg_cycle(pmg_solver *s, pmg_cycle_kind kind, double *res_norm_out)
 {
     if (!s) return fail(PMG_ERR_INVALID, "null argument");
@@ -1098,7 +1218,7 @@ pmg_status pmg_cycle(pmg_solver *s, pmg_cycle_kind kind, double *res_norm_out)
     float ms = 0.f;
     PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->last_ms = ms;
-    return PMG_OK;
+    return check_comm_err(s);
 }
 
 /* Fused V/W solve with device-side convergence control: cycles are queued one batch ahead of the host's
@@ -1156,10 +1276,9 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
     PMG_CUDA(cudaMemcpyAsync(&s->h_ctrl[0], s->d_ctrl, sizeof(SolveCtrl), cudaMemcpyDeviceToHost, s->stream));
     PMG_CUDA(cudaStreamSynchronize(s->stream));
     PMG_CUDA(cudaGetLastError());
-    if (s->p2p) {
-        int err = 0;
-        PMG_CUDA(cudaMemcpy(&err, s->d_comm_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) return fail(PMG_ERR_COMM, "peer-to-peer halo exchange timed out waiting for a neighbour");
+    {
+        pmg_status rce = check_comm_err(s);
+        if (rce != PMG_OK) return rce;
     }
     int k = s->h_ctrl[0].cycles;
     if (k < 0 || k > max_cycles)
@@ -1194,7 +1313,6 @@ static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol,
 {
     if (!s || max_cycles < 0) return fail(PMG_ERR_INVALID, "bad argument");
     PMG_CUDA(cudaSetDevice(s->device));
-    if (s->dist && kind == PMG_CYCLE_F) return fail(PMG_ERR_UNSUPPORTED, "the F-cycle is single-GPU only");
     if (s->fused && (kind == PMG_CYCLE_V || kind == PMG_CYCLE_W) && s->cfg.norm_mode == PMG_NORM_TREE &&
         s->lv.size() > 1 && s->lv[0].n > s->cfg.n_coarse && (s->dist || fused_graph_ok(s)))
         return solve_fused_async(s, kind == PMG_CYCLE_W, rel_tol, max_cycles, res_history, n_cycles_out);
@@ -1222,7 +1340,7 @@ static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol,
     PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->last_ms = ms;
     if (n_cycles_out) *n_cycles_out = k;
-    return PMG_OK;
+    return check_comm_err(s);
 }
 
 pmg_status pmg_last_device_ms(pmg_solver *s, double *ms_out)

@@ -6,7 +6,7 @@
 
 Every rank solves its row slab; rank 0 also solves the same problem on its own GPU alone.  Checks: same
 cycle count, per-cycle norms equal to <= 1e-12 relative (only the summation order differs), and the
-gathered iterate BIT-IDENTICAL to the single-GPU iterate (V and W cycles, sine and random RHS).
+gathered iterate BIT-IDENTICAL to the single-GPU iterate (V, W and F cycles, sine and random RHS).
 """
 import os
 import sys
@@ -65,6 +65,42 @@ def main():
                 print("N=%d kind=%s rhs=%s ranks=%d: cycles %d/%d iterate_bit_identical=%s max_rel_norm_dev=%.2e "
                       "ms dist=%.3f single=%.3f %s" % (n, "VWF"[kind], rhs, world, k, k1, same, rel, ms, ms1,
                                                        "OK" if good else "FAIL"), flush=True)
+    # F-cycle (the runner's full-multigrid wrapper, MultiGridTestRunner.hpp:192-205): two passes from a random start
+    # whose ring is non-zero; iterate bit-identical to one GPU, the runner's residual norm to <= 1e-12
+    for n in sizes:
+        for prolong in (pmg.PROLONG_REFERENCE, pmg.PROLONG_FULL):
+            y0, y1 = pmg.partition_rows(n, world, rank)
+            x = np.sin(np.pi * np.arange(n) / (n - 1))
+            f = 2 * np.pi ** 2 * np.outer(x, x)
+            phi0 = np.random.default_rng(3).standard_normal((n, n))
+            s = pmg.Solver(n, omega=2.0 / 3.0, device=dev, rank=rank, n_ranks=world, prolong_mode=prolong,
+                           agglomerate_below=min(257, n // 4))
+            s.set_rhs(np.ascontiguousarray(f[y0:y1]))
+            s.set_guess(np.ascontiguousarray(phi0[y0:y1]))
+            norms, ms = [], 0.0
+            for _ in range(2):
+                norms.append(s.cycle(pmg.F))
+                ms = s.last_ms
+            mine = torch.from_numpy(s.get_solution()).cuda()
+            s.close()
+            parts = [torch.empty((pmg.partition_rows(n, world, r)[1] - pmg.partition_rows(n, world, r)[0], n),
+                                 dtype=torch.float64, device="cuda") for r in range(world)]
+            dist.all_gather(parts, mine)
+            if rank == 0:
+                full = torch.cat(parts).cpu().numpy()
+                one = pmg.Solver(n, omega=2.0 / 3.0, device=dev, prolong_mode=prolong)
+                one.set_rhs(f)
+                one.set_guess(phi0)
+                n1 = [one.cycle(pmg.F) for _ in range(2)]
+                ms1 = one.last_ms
+                ref = one.get_solution()
+                one.close()
+                same = np.array_equal(full, ref)
+                rel = max(abs(a - b) / b for a, b in zip(norms, n1))
+                good = same and rel <= 1e-12
+                ok &= good
+                print("N=%d kind=F prolong=%d ranks=%d: iterate_bit_identical=%s max_rel_norm_dev=%.2e ms dist=%.3f "
+                      "single=%.3f %s" % (n, prolong, world, same, rel, ms, ms1, "OK" if good else "FAIL"), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     pmg.comm_finalize()
