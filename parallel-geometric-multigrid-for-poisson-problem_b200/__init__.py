@@ -116,6 +116,9 @@ def lib():
     L.pmg_fused_set_variant.restype = None
     L.pmg_fused_set_variant.argtypes = [i]
     L.pmg_fused_num_variants.restype = i
+    L.pmg_small_vcycle_set_version.restype = None
+    L.pmg_small_vcycle_set_version.argtypes = [i]
+    L.pmg_small_vcycle_version.restype = i
     L.pmg_fused_set_min_chunk_rows.restype = None
     L.pmg_fused_set_min_chunk_rows.argtypes = [i]
     _lib = L
@@ -361,3 +364,12 @@ def set_fused_variant(down, up=None):
 
 def num_fused_variants():
     return lib().pmg_fused_num_variants()
+
+
+def set_small_vcycle_version(v):
+    """Which generation of the single-CTA kernel for the levels <= 65 new cycles use (1, 2; 0 = default)."""
+    lib().pmg_small_vcycle_set_version(v)
+
+
+def small_vcycle_version():
+    return lib().pmg_small_vcycle_version()

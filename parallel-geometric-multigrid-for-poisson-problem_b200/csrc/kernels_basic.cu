@@ -7,6 +7,7 @@
 // outputs are bit-identical to the CPU path.  All are HBM-bound: 24 B/pt (Jacobi, residual),
 // 10 B/fine-pt (restriction), 18 B/fine-pt (prolongation) -- see DESIGN.md section 4.
 #include <atomic>
+#include <cstdlib>
 
 #include "pmg_internal.h"
 
@@ -551,10 +552,28 @@ size_t vcycle_small_smem(int n0, int n_coarse)
     return d * sizeof(double);
 }
 
+// which generation of the single-CTA small-level kernel runs: 1 = k_vcycle_small (this file), 2 = k_vcycle_small2
+// (kernels_small.cu: per-level thread groups on named barriers).  PMG_SMALL_V2=0/1 overrides the default.
+static int g_small_version = 0;
+int vcycle_small_version()
+{
+    if (g_small_version == 0) {
+        const char *e = getenv("PMG_SMALL_V2");
+        g_small_version = (e && e[0] == '1') ? 2 : ((e && e[0] == '0') ? 1 : PMG_SMALL_DEFAULT_VERSION);
+    }
+    return g_small_version;
+}
+void vcycle_small_set_version(int v) { g_small_version = (v == 2) ? 2 : (v == 1 ? 1 : 0); }
+
 void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0,
                          double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
                          int gamma, cudaStream_t st, const int *done)
 {
+    if (vcycle_small_version() == 2 && vcycle_small_v2_supported(gamma)) {
+        launch_vcycle_small_v2(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps, prolong_mode,
+                               x_is_zero, gamma, st, done);
+        return;
+    }
     size_t smem = vcycle_small_smem(n0, n_coarse);
     static bool once = (cudaFuncSetAttribute(k_vcycle_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
     (void)once;

@@ -1,7 +1,13 @@
 // pmg_internal.h -- declarations shared by the CUDA translation units of libpmg.so.
 // Nothing here is part of the public ABI (that is include/pmg.h).
 #pragma once
+#ifdef PMG_HOST_EMULATION
+// tests/cpp/emu/host_emulation.h: runs a single-CTA kernel's source on CPU threads (barrier logic and arithmetic
+// checked against the oracle without a GPU); test infrastructure only, never part of libpmg.so
+#include "host_emulation.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <cstddef>
 #include <cstdint>
@@ -86,6 +92,14 @@ constexpr int VSMALL_TOP = 65;
 void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0,
                          double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
                          int gamma, cudaStream_t st, const int *done = nullptr);
+// second generation of the same kernel (kernels_small.cu); launch_vcycle_small dispatches on vcycle_small_version()
+constexpr int PMG_SMALL_DEFAULT_VERSION = 1;
+int vcycle_small_version();
+void vcycle_small_set_version(int v);  // 1, 2, or 0 = re-read PMG_SMALL_V2 / the default
+bool vcycle_small_v2_supported(int gamma);
+void launch_vcycle_small_v2(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0,
+                            double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
+                            int gamma, cudaStream_t st, const int *done = nullptr);
 void launch_residual(double *r, const double *x, const double *f, int nx, int ny, int pitch_r,
                      int pitch_x, int pitch_f, double h, cudaStream_t st);
 // sum over the interior of (f - A x)^2 -> *d_out (device double); `d_partials` >= reduce_partials() doubles
@@ -147,6 +161,7 @@ struct HaloPeers {
     int *err;                      // raised if that wait times out
 };
 
+#ifndef PMG_HOST_EMULATION
 // bounded acquire spin on a flag another GPU publishes with st.release.sys (~2 s, then give up)
 __device__ __forceinline__ bool wait_flag(const int *flag, int epoch)
 {
@@ -158,6 +173,7 @@ __device__ __forceinline__ bool wait_flag(const int *flag, int epoch)
     }
     return false;
 }
+#endif
 
 struct FusedLevel {
     double *x;    // logical (0,0) of the level's current iterate

@@ -1383,6 +1383,11 @@ void pmg_dist_trace_dump(int rank_to_print)
     g_trace.clear();
 }
 
+/* generation of the single-CTA kernel for the levels <= 65 (1 or 2; 0 = default / PMG_SMALL_V2); graphs captured
+ * with the other generation are dropped by the caller re-creating the solver */
+void pmg_small_vcycle_set_version(int v) { vcycle_small_set_version(v); }
+int pmg_small_vcycle_version(void) { return vcycle_small_version(); }
+
 int pmg_fused_num_variants(void) { return fused_num_variants(); }
 void pmg_fused_set_variant(int v) { fused_set_variant(v); }
 void pmg_fused_set_min_chunk_rows(int r) { fused_set_min_chunk_rows(r); }

@@ -324,6 +324,37 @@ def test_engines_and_variants_agree_bitwise(n):
         _hist_close(norms, out[0][0])
 
 
+@pytest.mark.parametrize("n,kind,gamma,omega,prolong", [
+    (129, pmg.V, 1, 2.0 / 3.0, pmg.PROLONG_REFERENCE),
+    (129, pmg.W, 2, 1.0, pmg.PROLONG_FULL),
+    (65, pmg.W, 3, 2.0 / 3.0, pmg.PROLONG_REFERENCE),
+    (33, pmg.V, 1, 0.8, pmg.PROLONG_REFERENCE),
+    (17, pmg.W, 2, 2.0 / 3.0, pmg.PROLONG_FULL),
+    (1025, pmg.W, 2, 2.0 / 3.0, pmg.PROLONG_REFERENCE),
+])
+def test_small_level_kernel_generations_agree_bitwise(orc, n, kind, gamma, omega, prolong):
+    """Both generations of the single-CTA kernel for the levels <= 65 (k_vcycle_small: whole-CTA barriers;
+    k_vcycle_small2: per-level thread groups on named barriers) against each other and against the oracle."""
+    f = cc.random_rhs(n, seed=61)
+    got = {}
+    for version in (1, 2):
+        pmg.set_small_vcycle_version(version)
+        assert pmg.small_vcycle_version() == version
+        with pmg.Solver(n, omega=omega, gamma=gamma, prolong_mode=prolong) as s:
+            s.set_rhs(f)
+            s.zero_guess()
+            norms = [s.cycle(kind) for _ in range(3)]
+            got[version] = (norms, s.get_solution())
+    pmg.set_small_vcycle_version(0)
+    assert np.array_equal(got[1][1], got[2][1])
+    assert got[1][0] == got[2][0]
+    if n <= 129:
+        want = np.zeros((n, n))
+        for _ in range(3):
+            orc.cycle(want, f, kind=cc.W if kind == pmg.W else cc.V, omega=omega, eps=0.0, alpha=gamma, prolong=prolong)
+        assert np.array_equal(got[2][1], want)
+
+
 def test_scaling_by_two_is_exact():
     """Linearity in a form floating point honours exactly: f -> 2f doubles every iterate bit for bit."""
     n = 4097
