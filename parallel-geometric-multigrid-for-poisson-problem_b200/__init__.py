@@ -116,6 +116,8 @@ def lib():
     L.pmg_fused_set_variant.restype = None
     L.pmg_fused_set_variant.argtypes = [i]
     L.pmg_fused_num_variants.restype = i
+    L.pmg_fused_set_deep_prefetch_below.restype = None
+    L.pmg_fused_set_deep_prefetch_below.argtypes = [i]
     L.pmg_small_vcycle_set_version.restype = None
     L.pmg_small_vcycle_set_version.argtypes = [i]
     L.pmg_small_vcycle_version.restype = i
@@ -373,3 +375,8 @@ def set_small_vcycle_version(v):
 
 def small_vcycle_version():
     return lib().pmg_small_vcycle_version()
+
+
+def set_deep_prefetch_below(n):
+    """Levels with n <= this use the 7-rows-in-flight variant of the nu == 2 fused passes (0: never, -1: default)."""
+    lib().pmg_fused_set_deep_prefetch_below(n)

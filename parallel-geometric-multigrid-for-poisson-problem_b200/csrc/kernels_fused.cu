@@ -26,6 +26,8 @@
 // FMA contraction: every value written is bit-identical to the CPU path.  Partial sums
 // ((h^2 f + W) + E) + S are formed when a row arrives and completed with + N one row later, which is
 // exactly the reference's left-to-right evaluation.
+#include <cstdlib>
+
 #include "pmg_internal.h"
 
 namespace pmg {
@@ -275,12 +277,13 @@ extern __shared__ __align__(16) unsigned char g_dyn_smem[];
 template <int C, int PF, int S, bool USE_X>
 struct SmemFeed {
     static constexpr int UNROLL = 2;
-    static constexpr int NF = 8;                       // f ring slots  (>= PF + S + 2)
-    static constexpr int NX = USE_X ? 4 : 0;           // x ring slots  (>= PF + 1)
+    static constexpr int NF = (PF + S + 2 <= 8) ? 8 : 16;            // f ring slots  (power of two >= PF + S + 2)
+    static constexpr int NXR = (PF + 1 <= 4) ? 4 : 8;                // x ring slots  (power of two >= PF + 1)
+    static constexpr int NX = USE_X ? NXR : 0;
     static constexpr int PLANES = C / 2;               // 16-byte pieces per lane per row
     static constexpr int ROW_BYTES = PLANES * 512;     // plane p of a row: 32 lanes x 16 B, conflict free
     static constexpr int SMEM_PER_WARP = (NF + NX) * ROW_BYTES;
-    static_assert(PF + S + 2 <= NF && PF + 1 <= 4, "ring too small");
+    static_assert(PF + S + 2 <= NF && PF + 1 <= NXR, "ring too small");
     uint32_t fbase, xbase;  // shared-window addresses of this lane's first piece in slot 0
     const double *x, *f;
     RowSource src;
@@ -293,7 +296,7 @@ struct SmemFeed {
         for (int p = 0; p < PLANES; ++p) cp_async16(fa + p * 512, fr + 2 * p);
         if (USE_X) {
             const double *xr = src.x_row(x, row);
-            uint32_t xa = xbase + (uint32_t)(slot_t & 3) * ROW_BYTES;
+            uint32_t xa = xbase + (uint32_t)(slot_t & (NXR - 1)) * ROW_BYTES;
 #pragma unroll
             for (int p = 0; p < PLANES; ++p) cp_async16(xa + p * 512, xr + 2 * p);
         }
@@ -332,7 +335,7 @@ struct SmemFeed {
     {
         cp_async_wait<PF - 1>();  // all but the newest PF-1 groups have landed => row jj is in its slot
         if (src.keeps(jj)) store_row<C>(src.f_keep + (ptrdiff_t)jj * pitch, lds_row(fbase + (uint32_t)(t & (NF - 1)) * ROW_BYTES));
-        Row<C> cur = USE_X ? lds_row(xbase + (uint32_t)(t & 3) * ROW_BYTES) : zero_row<C>();
+        Row<C> cur = USE_X ? lds_row(xbase + (uint32_t)(t & (NXR - 1)) * ROW_BYTES) : zero_row<C>();
         issue(min(jj + PF, last_row), t + PF);
         return cur;
     }
@@ -603,13 +606,26 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 struct VariantDesc {
     int c, pf, minb, sm;
 };
-constexpr int NUM_VARIANTS = 4;
+constexpr int NUM_VARIANTS = 5;
 constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {
     {2, 3, 4, 1},  // 0: shared-memory staged, 2 columns per lane, 16 warps/SM   (default for Pass A)
     {2, 3, 5, 1},  // 1: same, 20 warps/SM                                       (default for Pass B)
     {2, 4, 4, 0},  // 2: register staged, 2 columns per lane
     {2, 3, 6, 1},  // 3: shared-memory staged, 24 warps/SM
+    {2, 7, 4, 1},  // 4: 7 rows in flight per warp (16 + 8 ring slots): for the LATENCY-bound small levels, where a
+                   //    warp's whole chunk is a dozen rows and the pass time is (rows x load latency / depth)
 };
+// levels with n <= this use variant 4 (0 = never).  PMG_DEEP_PREFETCH_BELOW overrides.
+int g_deep_prefetch_below = -1;
+int deep_prefetch_below()
+{
+    if (g_deep_prefetch_below < 0) {
+        const char *e = getenv("PMG_DEEP_PREFETCH_BELOW");
+        g_deep_prefetch_below = e ? atoi(e) : PMG_DEEP_PREFETCH_DEFAULT;
+        if (g_deep_prefetch_below < 0) g_deep_prefetch_below = 0;
+    }
+    return g_deep_prefetch_below;
+}
 // measured best per kernel flavour on B200 (tools/tune_fused.py): Pass A, Pass A from x == 0, Pass B, Pass B + norm
 int g_variant_down = 0, g_variant_down_zero = 3, g_variant_up = 1, g_variant_up_norm = 3;
 
@@ -775,6 +791,7 @@ void fused_set_variant(int v)
 }
 int fused_get_variant() { return g_variant_down | (g_variant_up << 8); }
 void fused_set_min_chunk_rows(int r) { g_min_chunk_rows = (r >= 2) ? (r + (r & 1)) : 2; }
+void fused_set_deep_prefetch_below(int n) { g_deep_prefetch_below = n; }
 
 int fused_max_partials(int n)
 {
@@ -798,6 +815,7 @@ int fused_max_partials(int n)
         case 1: FN<2, 3, 5, true, 2>(__VA_ARGS__); break;                   \
         case 2: FN<2, 4, 4, false, 2>(__VA_ARGS__); break;                  \
         case 3: FN<2, 3, 6, true, 2>(__VA_ARGS__); break;                   \
+        case 4: FN<2, 7, 4, true, 2>(__VA_ARGS__); break;                   \
         default: FN<2, 3, 4, true, 2>(__VA_ARGS__); break;                  \
     }
 
@@ -807,7 +825,7 @@ void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int 
     bool resid = coarse_f != nullptr;
     switch (nu1) {
         case 1: down_launch<2, 3, 4, true, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
-        case 2: PMG_DISPATCH_S2((x_is_zero && resid) ? g_variant_down_zero : g_variant_down, down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
+        case 2: PMG_DISPATCH_S2(lv.n <= deep_prefetch_below() ? 4 : ((x_is_zero && resid) ? g_variant_down_zero : g_variant_down), down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         case 3: down_launch<2, 3, 4, true, 3>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         case 4: down_launch<2, 2, 4, true, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         default: break;
@@ -821,7 +839,7 @@ void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, 
     int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
     switch (nu2) {
         case 1: up_launch<2, 3, 4, true, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
-        case 2: PMG_DISPATCH_S2(norm ? g_variant_up_norm : g_variant_up, up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
+        case 2: PMG_DISPATCH_S2(lv.n <= deep_prefetch_below() ? 4 : (norm ? g_variant_up_norm : g_variant_up), up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
         case 3: up_launch<2, 3, 4, true, 3>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
         case 4: up_launch<2, 2, 4, true, 4>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
         default: break;

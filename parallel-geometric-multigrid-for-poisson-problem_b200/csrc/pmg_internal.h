@@ -204,6 +204,10 @@ int fused_num_variants();
 void fused_set_variant(int v);
 int fused_get_variant();
 void fused_set_min_chunk_rows(int r);
+// levels with n <= this run the nu == 2 passes with the deep-prefetch variant (7 rows in flight per warp);
+// n < 0: back to PMG_DEEP_PREFETCH_BELOW / the default
+constexpr int PMG_DEEP_PREFETCH_DEFAULT = 0;
+void fused_set_deep_prefetch_below(int n);
 
 // ---- multi-GPU plumbing (comm.cu): no-ops returning PMG_OK while no communicator exists ---------------
 bool comm_ready();

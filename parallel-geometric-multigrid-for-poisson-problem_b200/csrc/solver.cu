@@ -1353,6 +1353,9 @@ pmg_status pmg_last_device_ms(pmg_solver *s, double *ms_out)
 void *pmg_stream(pmg_solver *s) { return s ? (void *)s->stream : nullptr; }
 
 /* ---- tuning / benchmarking hooks (not part of the reference surface) ---------------------------------- */
+/* run-time switch for the phase trace (same effect as PMG_DIST_TRACE=1 / 0) */
+void pmg_dist_trace_enable(int on) { g_trace_on = on ? 1 : 0; }
+
 /* PMG_DIST_TRACE=1: prints, per phase label and level, the average device time between consecutive marks of
  * the distributed cycle recorded since the last dump (the stream must be idle). */
 void pmg_dist_trace_dump(int rank_to_print)
@@ -1391,6 +1394,7 @@ int pmg_small_vcycle_version(void) { return vcycle_small_version(); }
 int pmg_fused_num_variants(void) { return fused_num_variants(); }
 void pmg_fused_set_variant(int v) { fused_set_variant(v); }
 void pmg_fused_set_min_chunk_rows(int r) { fused_set_min_chunk_rows(r); }
+void pmg_fused_set_deep_prefetch_below(int n) { fused_set_deep_prefetch_below(n); }
 
 /* `sweeps` weighted-Jacobi sweeps on the solver's finest level, `block` sweeps per streaming pass
  * (block = 1: one HBM pass per sweep, 24 B/point -- the "Jacobi sweep GB/s" sub-metric). */

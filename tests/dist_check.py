@@ -21,8 +21,55 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pmg_b200 as pmg  # noqa: E402
 
 
+def timing(sizes, rank, world, dev):
+    """solve time per cycle for the latency options (small-level kernel generation, deep prefetch threshold) and,
+    for the last combination, the phase trace of the distributed cycle on rank 0"""
+    import ctypes
+    L = pmg.lib()
+    L.pmg_dist_trace_dump.argtypes = [ctypes.c_int]
+    L.pmg_dist_trace_dump.restype = None
+    L.pmg_dist_trace_enable.argtypes = [ctypes.c_int]
+    L.pmg_dist_trace_enable.restype = None
+    for n in sizes:
+        combos = [(1, 0, 0), (2, 0, 0), (2, 2049, 0), (2, 2049, 1)]
+        for small, deep, trace in combos:
+            pmg.set_small_vcycle_version(small)
+            pmg.set_deep_prefetch_below(deep)
+            L.pmg_dist_trace_enable(trace)
+            s = pmg.Solver(n, omega=2.0 / 3.0, device=dev, rank=rank, n_ranks=world)
+            s.set_rhs_sine()
+            ms = []
+            for it in range(4):
+                s.zero_guess()
+                torch.cuda.synchronize()
+                dist.barrier()
+                k, hist = s.solve(pmg.V, 1e-8, 100)
+                ms.append(s.last_ms)
+                if it == 0 and trace:
+                    L.pmg_dist_trace_dump(-1)  # drop the warm-up marks
+            t = torch.tensor(ms[1:], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print("timing ranks=%d N=%d small_kernel=%d deep_prefetch_below=%d trace=%d: cycles=%d ms %s -> %.1f us/cycle"
+                      % (world, n, small, deep, trace, k, [round(float(v), 3) for v in t], 1e3 * float(t.min()) / k),
+                      flush=True)
+            if trace:
+                L.pmg_dist_trace_dump(0)
+                dist.barrier()
+            s.close()
+        L.pmg_dist_trace_enable(0)
+    pmg.set_small_vcycle_version(0)
+    pmg.set_deep_prefetch_below(-1)
+
+
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [1025, 4097]
+    args = sys.argv[1:]
+    timing_n = []
+    if "--timing" in args:  # --timing N1,N2: per-cycle times of the latency options + one phase trace per size
+        i = args.index("--timing")
+        timing_n = [int(v) for v in args[i + 1].split(",")]
+        args = args[:i] + args[i + 2:]
+    sizes = [int(a) for a in args] or [1025, 4097]
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -101,6 +148,8 @@ def main():
                 ok &= good
                 print("N=%d kind=F prolong=%d ranks=%d: iterate_bit_identical=%s max_rel_norm_dev=%.2e ms dist=%.3f "
                       "single=%.3f %s" % (n, prolong, world, same, rel, ms, ms1, "OK" if good else "FAIL"), flush=True)
+    if timing_n:
+        timing(timing_n, rank, world, dev)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     pmg.comm_finalize()
