@@ -93,7 +93,7 @@ void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pi
                          double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
                          int gamma, cudaStream_t st, const int *done = nullptr);
 // second generation of the same kernel (kernels_small.cu); launch_vcycle_small dispatches on vcycle_small_version()
-constexpr int PMG_SMALL_DEFAULT_VERSION = 1;
+constexpr int PMG_SMALL_DEFAULT_VERSION = 2;
 int vcycle_small_version();
 void vcycle_small_set_version(int v);  // 1, 2, or 0 = re-read PMG_SMALL_V2 / the default
 bool vcycle_small_v2_supported(int gamma);
