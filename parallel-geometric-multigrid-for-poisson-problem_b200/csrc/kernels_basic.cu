@@ -487,12 +487,19 @@ __global__ void k_signal_all(int *const *slots, int n_ranks, int my_rank, int ep
         asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(slots[r]), "r"(epoch) : "memory");
 }
 
+constexpr int GATHER_ILP = 4;
 // blockIdx.y = source rank
 __global__ void __launch_bounds__(256)
     k_gather_pull(double *__restrict__ full, int pitch, int rows, const double *const *__restrict__ srcs,
-                  const int *inbox, int my_rank, int epoch, int *err)
+                  const int *inbox, int my_rank, int epoch, int *err, int *const *slots, int n_ranks)
 {
     const int r = blockIdx.y;
+    // "my slab is final" (everything this stream ran before this launch is complete): published by the first block
+    if (slots != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < n_ranks &&
+        (int)threadIdx.x != my_rank) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(slots[threadIdx.x]), "r"(epoch) : "memory");
+    }
     __shared__ int ok;
     if (threadIdx.x == 0) ok = (r == my_rank) ? 1 : (wait_flag(inbox + r, epoch) ? 1 : 0);
     __syncthreads();
@@ -500,13 +507,21 @@ __global__ void __launch_bounds__(256)
         if (threadIdx.x == 0) *err = 1;
         return;
     }
+    // a remote load costs an NVLink round trip (~2-3 us): keep GATHER_ILP independent loads in flight per thread
+    // and enough blocks (launch_gather_pull) that every thread makes one or two trips, not twenty
     const size_t n2 = (size_t)rows * pitch / 2;
     const double2 *s2 = reinterpret_cast<const double2 *>(srcs[r]);
     double2 *d2 = reinterpret_cast<double2 *>(full - PADX + (size_t)r * rows * pitch);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
-        double2 v;
-        asm volatile("ld.global.cv.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(s2 + i));
-        d2[i] = v;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += GATHER_ILP * stride) {
+        double2 v[GATHER_ILP];
+#pragma unroll
+        for (int u = 0; u < GATHER_ILP; ++u)
+            if (i + u * stride < n2)
+                asm volatile("ld.global.cv.v2.f64 {%0, %1}, [%2];" : "=d"(v[u].x), "=d"(v[u].y) : "l"(s2 + i + u * stride));
+#pragma unroll
+        for (int u = 0; u < GATHER_ILP; ++u)
+            if (i + u * stride < n2) d2[i + u * stride] = v[u];
     }
 }
 
@@ -647,13 +662,15 @@ void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, c
 }
 
 void launch_gather_pull(double *full, int pitch, int rows, const double *const *srcs, const int *inbox, int n_ranks,
-                        int my_rank, int epoch, int *err, cudaStream_t st)
+                        int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots)
 {
     size_t n2 = (size_t)rows * pitch / 2;
-    int bx = (int)((n2 + 255) / 256);
-    if (bx > 16) bx = 16;
+    int bx = (int)((n2 + 256 * GATHER_ILP - 1) / (256 * GATHER_ILP));  // one trip per thread ...
+    int cap = (148 * 4) / (n_ranks > 0 ? n_ranks : 1);                   // ... within about one wave of CTAs
+    if (cap < 16) cap = 16;
+    if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    k_gather_pull<<<dim3(bx, n_ranks), 256, 0, st>>>(full, pitch, rows, srcs, inbox, my_rank, epoch, err);
+    k_gather_pull<<<dim3(bx, n_ranks), 256, 0, st>>>(full, pitch, rows, srcs, inbox, my_rank, epoch, err, slots, n_ranks);
     count_launch();
 }
 

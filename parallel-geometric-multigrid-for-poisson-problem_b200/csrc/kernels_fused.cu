@@ -393,7 +393,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
     for (int q = 0; q < NP; ++q) s_mid[q] = s_cor[q] = c_mid[q] = c_ew[q] = 0.0;
 
-    // fused halo exchange: before the first access to a neighbour's rows, wait until it has published them
+    // fused halo exchange.  First, one thread of the launch tells the neighbours that MY boundary rows are final
+    // (the kernels that produced them ran earlier on this stream) ...
+    if ((hp.pub_up != nullptr || hp.pub_dn != nullptr) && blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        if (hp.pub_up != nullptr) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hp.pub_up), "r"(hp.epoch) : "memory");
+        if (hp.pub_dn != nullptr) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hp.pub_dn), "r"(hp.epoch) : "memory");
+    }
+    // ... then, before the first access to a neighbour's rows, every warp waits until it has published them
     if (hp.flag_up != nullptr || hp.flag_dn != nullptr) {
         int ok = 1;
         if (lane == 0) {

@@ -157,6 +157,9 @@ struct HaloPeers {
     const double *x_up, *x_dn, *f_up, *f_dn;
     double *f_keep;
     const int *flag_up, *flag_dn;  // inbox flags that must reach `epoch` before the first peer access
+    int *pub_up, *pub_dn;          // the neighbours' inbox slots for ME (peer pointers): thread 0 of the launch
+                                   // publishes `epoch` there first -- everything this stream ran before the launch
+                                   // is complete, so "my boundary rows are final" needs no kernel of its own
     int epoch;
     int *err;                      // raised if that wait times out
 };
@@ -242,8 +245,9 @@ void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *
 // pointers, device array); every rank publishes `epoch` there, then pulls the other ranks' `rows` slab rows
 // (`srcs[r]` = peer pointer to rank r's padded row 0, device array; srcs[my_rank] is local) into `full`.
 void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, cudaStream_t st);
+// slots != nullptr: the pull kernel publishes `epoch` itself (no launch_signal_all needed before it)
 void launch_gather_pull(double *full, int pitch, int rows, const double *const *srcs, const int *inbox, int n_ranks,
-                        int my_rank, int epoch, int *err, cudaStream_t st);
+                        int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots = nullptr);
 // every rank contributes `rows` owned rows of its slab; all ranks receive the whole level (rank r's block at
 // row r*rows of `full`).  Needs equally sized slabs (the extra last row of the last rank is the zero ring).
 pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int pitch, cudaStream_t st);

@@ -314,8 +314,9 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         int epoch = 0;
         if (s->p2p) {  // publish "my boundary rows of this level are final" in the neighbours' inboxes
             epoch = ++L.halo_epoch;
-            launch_halo_signal(up_nb ? s->up_flags + 2 * l + 1 : nullptr, dn_nb ? s->dn_flags + 2 * l : nullptr, epoch,
-                               s->stream);
+            if (!s->p2p_fused)  // (the fused exchange publishes from inside Pass A, see hp.pub_up / pub_dn below)
+                launch_halo_signal(up_nb ? s->up_flags + 2 * l + 1 : nullptr, dn_nb ? s->dn_flags + 2 * l : nullptr, epoch,
+                                   s->stream);
         }
         // tall slabs: exchange + boundary strips on the communication stream beside the interior pass;
         // short slabs: everything in order on the compute stream (no cross-stream hops)
@@ -341,6 +342,8 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             }
             hp.flag_up = up_nb ? s->d_flags + 2 * l : nullptr;
             hp.flag_dn = dn_nb ? s->d_flags + 2 * l + 1 : nullptr;
+            hp.pub_up = up_nb ? s->up_flags + 2 * l + 1 : nullptr;  // published by the FIRST launch that carries hp
+            hp.pub_dn = dn_nb ? s->dn_flags + 2 * l : nullptr;
             hp.epoch = epoch;
             hp.err = s->d_comm_err;
         } else if (s->p2p) {  // separate pull kernel: neighbours' rows are copied into the local halo rows
@@ -357,6 +360,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
                 v.span_lo = -6;
                 v.span_hi = PADY;
                 launch_fused_down(v, K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->comm_stream, nullptr);
+                v.hp.pub_up = v.hp.pub_dn = nullptr;  // published once
             }
             if (dn_nb) {
                 v.span_lo = L.ny - PADY;
@@ -394,9 +398,9 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         if (s->coarse_redundant) {
             // every rank receives the whole first agglomerated level and solves it: no scatter, no idle ranks
             if (pull_gather) {
-                launch_signal_all(s->d_agg_slots, s->n_ranks, s->rank, s->agg_epoch, s->stream);
+                // publishes "my slab is final" to every rank, then pulls theirs (one launch)
                 launch_gather_pull(A.f, A.pitch, y1[0] - y0[0], s->d_agg_srcs[s->agg_epoch & 1], s->d_flags + 32,
-                                   s->n_ranks, s->rank, s->agg_epoch, s->d_comm_err, s->stream);
+                                   s->n_ranks, s->rank, s->agg_epoch, s->d_comm_err, s->stream, s->d_agg_slots);
             } else if ((rc = comm_allgather_rows(K.f, A.f, y1[0] - y0[0], A.pitch, s->stream)) != PMG_OK) {
                 return rc;
             }
@@ -404,9 +408,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             for (int k = 0; k < reps; ++k)
                 if ((rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, nullptr)) != PMG_OK) return rc;
             trace_mark(s, "coarse", l + 1);
-            int a = std::max(0, y0[s->rank] - 4), b = std::min(A.n, y1[s->rank] + 4);
-            PMG_CUDA(cudaMemcpyAsync(K.x - PADX + (ptrdiff_t)(a - y0[s->rank]) * K.pitch, A.x - PADX + (ptrdiff_t)a * A.pitch,
-                                     (size_t)(b - a) * A.pitch * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+            // no scatter: Pass B below reads its coarse rows straight out of the whole level (coarse_x)
         } else {
             if ((rc = comm_gather_rows(K.f, A.f, A.pitch, y0, y1, s->stream)) != PMG_OK) return rc;
             trace_mark(s, "gather", l + 1);
@@ -431,7 +433,15 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         const int e = (l == 0) ? 0 : 4;
         v.ext_lo = up_nb ? e : 0;
         v.ext_hi = dn_nb ? e : 0;
-        launch_fused_up(v, K.x, K.pitch, c.nu2, c.omega, c.prolong_mode, want_norm ? s->d_partials : nullptr,
+        // coarse correction: the child slab's iterate, or -- below the last slab level, where every rank holds the
+        // whole agglomerated level -- that level's rows around my slab, read in place (same pitch; the rows beyond
+        // the grid are the level's zero padding, exactly what a slab's halo rows hold there)
+        const double *coarse_x = K.x;
+        if (last_slab && s->coarse_redundant) {
+            const Level &A = s->lv[s->agg_level];
+            coarse_x = A.x + (ptrdiff_t)s->y0s[s->agg_level][s->rank] * A.pitch;
+        }
+        launch_fused_up(v, coarse_x, K.pitch, c.nu2, c.omega, c.prolong_mode, want_norm ? s->d_partials : nullptr,
                         n_partials, s->stream, l == 0 ? done : nullptr);
     }
     trace_mark(s, "passB", l);
@@ -634,17 +644,9 @@ static pmg_status cycle_f_dist(pmg_solver *s)
             launch_rhs_separable(f_l + (ptrdiff_t)(ga - L.y0) * L.pitch, L.pitch, L.n, gb - ga, factor, L.d_sin,
                                  L.d_sin + ga, s->stream);
             PMG_CUDA(cudaMemsetAsync(L.base_x, 0, L.elems * sizeof(double), s->stream));
-            const double *e = K.x;
-            int pitch_e = K.pitch;
-            if (l + 1 == la) {  // the whole level's rows around my slab -> the slab-shaped window
-                Level &W = s->aslab;
-                const int a = std::max(0, ay0[s->rank] - 4), b = std::min(A.n, ay1[s->rank] + 4);
-                PMG_CUDA(cudaMemcpyAsync(W.x - PADX + (ptrdiff_t)(a - ay0[s->rank]) * W.pitch, A.x - PADX + (ptrdiff_t)a * A.pitch,
-                                         (size_t)(b - a) * A.pitch * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-                e = W.x;
-                pitch_e = W.pitch;
-            }
-            launch_prolong_add_rows(e, L.x, L.n, L.ny, L.y0, pitch_e, L.pitch, c.prolong_mode, s->stream);
+            // the coarse iterate: the child slab, or my rows of the whole agglomerated level read in place
+            const double *e = (l + 1 == la) ? A.x + (ptrdiff_t)ay0[s->rank] * A.pitch : K.x;
+            launch_prolong_add_rows(e, L.x, L.n, L.ny, L.y0, K.pitch, L.pitch, c.prolong_mode, s->stream);
             if (l == 0) L.f = s->f_fmg0;
             rc = cycle_dist(s, l, false, false, false, nullptr, nullptr);  // :167
             if (l == 0) L.f = user_f;
