@@ -135,6 +135,10 @@ struct pmg_solver {
     std::vector<void *> agg_maps;            // IPC mappings to close
     int agg_epoch = 0;
     bool p2p_gather = false, cycle_has_collective = false;
+    // the redundant solve of the agglomerated levels (fixed pointers, no communication) replayed as a CUDA graph
+    cudaGraphExec_t coarse_graph[2] = {nullptr, nullptr};  // [V, W]
+    int coarse_graph_kernels[2] = {0, 0};
+    bool coarse_graph_on = true;  // PMG_COARSE_GRAPH=0 launches the kernels one by one
 };
 
 namespace pmg {
@@ -147,6 +151,11 @@ static void drop_graphs(pmg_solver *s)
                 cudaGraphExecDestroy(g);
                 g = nullptr;
             }
+    for (auto &g : s->coarse_graph)
+        if (g) {
+            cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
 }
 
 static FusedLevel fused_view(const Level &L)
@@ -253,6 +262,45 @@ static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero,
     }
     launch_fused_up(fused_view(L), K.x, K.pitch, c.nu2, c.omega, c.prolong_mode,
                     want_norm ? s->d_partials : nullptr, n_partials, s->stream, done);
+    return PMG_OK;
+}
+
+static bool fused_graph_ok(const pmg_solver *s);
+
+// Multi-GPU: every rank solves the agglomerated levels [agg_level, coarsest] itself.  The launch sequence has fixed
+// arguments and no communication, so it is captured once and replayed (7+ launches -> one graph launch).
+static pmg_status coarse_solve_redundant(pmg_solver *s, bool w_form, int reps)
+{
+    auto direct = [&]() -> pmg_status {
+        for (int k = 0; k < reps; ++k) {
+            pmg_status rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, nullptr);
+            if (rc != PMG_OK) return rc;
+        }
+        return PMG_OK;
+    };
+    if (!s->coarse_graph_on || !fused_graph_ok(s)) return direct();
+    cudaGraphExec_t &ge = s->coarse_graph[w_form ? 1 : 0];
+    int &gk = s->coarse_graph_kernels[w_form ? 1 : 0];
+    if (ge == nullptr) {
+        const unsigned long long before = launches_so_far();
+        PMG_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        pmg_status rc = direct();
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaStreamEndCapture (coarse solve): ") + cudaGetErrorString(e));
+        if (rc != PMG_OK) {
+            cudaGraphDestroy(g);
+            return rc;
+        }
+        gk = (int)(launches_so_far() - before);  // counted during capture; the replay below executes them
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaGraphInstantiate (coarse solve): ") + cudaGetErrorString(e));
+        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+        return PMG_OK;
+    }
+    PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+    count_launch(gk);
     return PMG_OK;
 }
 
@@ -405,8 +453,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
                 return rc;
             }
             trace_mark(s, "allgather", l + 1);
-            for (int k = 0; k < reps; ++k)
-                if ((rc = cycle_fused(s, s->agg_level, w_form, k == 0, false, nullptr, nullptr)) != PMG_OK) return rc;
+            if ((rc = coarse_solve_redundant(s, w_form, reps)) != PMG_OK) return rc;
             trace_mark(s, "coarse", l + 1);
             // no scatter: Pass B below reads its coarse rows straight out of the whole level (coarse_x)
         } else {
@@ -581,6 +628,7 @@ static pmg_status cycle_f_dist(pmg_solver *s)
     const int *ay0 = s->y0s[la].data(), *ay1 = s->y1s[la].data();
     Level &A = s->lv[la];
     s->cycle_has_collective = false;  // the agglomerated level travels by NCCL all-gather inside these V-cycles
+    drop_graphs(s);                   // the smoothing of the whole levels below swaps their x / xb roles
     // (1) phi restricted down to the coarsest grid (MultiGridTestRunner.hpp:192-200); scratch = the xb arrays
     for (int l = 0; l < lc; ++l) {
         Level &L = s->lv[l];
@@ -659,6 +707,7 @@ static pmg_status cycle_f_dist(pmg_solver *s)
         if (rc != PMG_OK) break;
     }
     s->lv[0].f = user_f;
+    drop_graphs(s);  // the smoothing of the whole levels swapped x / xb roles: a captured coarse solve is stale
     return rc;
 }
 
@@ -931,6 +980,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         s->coarse_redundant = equal && !(env && env[0] == '1');
         if (const char *e2 = getenv("PMG_SPLIT_MIN_ROWS")) s->split_min_rows = atoi(e2);
         if (const char *e3 = getenv("PMG_P2P_FUSED")) s->p2p_fused = !(e3[0] == '0');
+        if (const char *e4 = getenv("PMG_COARSE_GRAPH")) s->coarse_graph_on = !(e4[0] == '0');
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
