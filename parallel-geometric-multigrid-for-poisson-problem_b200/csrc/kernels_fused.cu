@@ -27,6 +27,7 @@
 // ((h^2 f + W) + E) + S are formed when a row arrives and completed with + N one row later, which is
 // exactly the reference's left-to-right evaluation.
 #include <cstdlib>
+#include <cstring>
 
 #include "pmg_internal.h"
 
@@ -261,6 +262,24 @@ struct RegFeed {
     __device__ __forceinline__ void end() {}
 };
 
+// The few PTX primitives the kernels use.  Under PMG_HOST_EMULATION (tests/cpp/emu/host_emulation.h: the kernel source
+// run lane by lane on the CPU, test infrastructure only) they act on the emulated shared-memory array instead.
+#ifdef PMG_HOST_EMULATION
+#define g_dyn_smem emu_smem
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr) { std::memcpy(emu_smem + saddr, gptr, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+__device__ __forceinline__ void lds_v2(uint32_t a, double &v0, double &v1)
+{
+    std::memcpy(&v0, emu_smem + a, 8);
+    std::memcpy(&v1, emu_smem + a + 8, 8);
+}
+__device__ __forceinline__ void sts_zero_v2(uint32_t a) { std::memset(emu_smem + a, 0, 16); }
+__device__ __forceinline__ void publish_epoch(int *flag, int epoch) { *(volatile int *)flag = epoch; }
+__device__ __forceinline__ void __threadfence_system() {}
+__device__ __forceinline__ bool wait_flag(const int *flag, int epoch) { return *(const volatile int *)flag >= epoch; }
+#else
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gptr) : "memory");
@@ -271,8 +290,21 @@ __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void lds_v2(uint32_t a, double &v0, double &v1)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v0), "=d"(v1) : "r"(a));
+}
+__device__ __forceinline__ void sts_zero_v2(uint32_t a)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %1};\n" ::"r"(a), "d"(0.0) : "memory");
+}
+__device__ __forceinline__ void publish_epoch(int *flag, int epoch)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
 
 extern __shared__ __align__(16) unsigned char g_dyn_smem[];
+#endif
 
 template <int C, int PF, int S, bool USE_X>
 struct SmemFeed {
@@ -306,8 +338,7 @@ struct SmemFeed {
     {
         Row<C> r;
 #pragma unroll
-        for (int p = 0; p < PLANES; ++p)
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(r.v[2 * p]), "=d"(r.v[2 * p + 1]) : "r"(a + p * 512));
+        for (int p = 0; p < PLANES; ++p) lds_v2(a + p * 512, r.v[2 * p], r.v[2 * p + 1]);
         return r;
     }
     __device__ __forceinline__ void init(const double *x_, const double *f_, int pitch_, int col, int j_start,
@@ -324,8 +355,7 @@ struct SmemFeed {
 #pragma unroll
         for (int sl = 0; sl < NF + NX; ++sl)
 #pragma unroll
-            for (int p = 0; p < PLANES; ++p)
-                asm volatile("st.shared.v2.f64 [%0], {%1, %1};\n" ::"r"(base + sl * ROW_BYTES + p * 512 + lane * 16), "d"(0.0) : "memory");
+            for (int p = 0; p < PLANES; ++p) sts_zero_v2(base + sl * ROW_BYTES + p * 512 + lane * 16);
         fbase = base + lane * 16;
         xbase = base + NF * ROW_BYTES + lane * 16;
 #pragma unroll
@@ -397,8 +427,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     // (the kernels that produced them ran earlier on this stream) ...
     if ((hp.pub_up != nullptr || hp.pub_dn != nullptr) && blockIdx.x == 0 && threadIdx.x == 0) {
         __threadfence_system();
-        if (hp.pub_up != nullptr) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hp.pub_up), "r"(hp.epoch) : "memory");
-        if (hp.pub_dn != nullptr) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(hp.pub_dn), "r"(hp.epoch) : "memory");
+        if (hp.pub_up != nullptr) publish_epoch(hp.pub_up, hp.epoch);
+        if (hp.pub_dn != nullptr) publish_epoch(hp.pub_dn, hp.epoch);
     }
     // ... then, before the first access to a neighbour's rows, every warp waits until it has published them
     if (hp.flag_up != nullptr || hp.flag_dn != nullptr) {
@@ -641,12 +671,17 @@ int g_min_chunk_rows = 4;  // even; the pipeline warm-up (4..8 rows) is paid onc
 int g_num_sms = 0;
 int num_sms()
 {
+#ifdef PMG_HOST_EMULATION
+    return emu_num_sms;
+#endif
+#ifndef PMG_HOST_EMULATION
     if (g_num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms <= 0) g_num_sms = 148;
     }
+#endif
     return g_num_sms;
 }
 
@@ -686,11 +721,19 @@ inline int grid_for(const StripGeom &g)
     return (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 }
 
+#ifdef PMG_HOST_EMULATION
+template <typename K>
+void set_smem(K, int) {}
+#define PMG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu_launch_warps((grid), (block), [&] { kernel(__VA_ARGS__); })
+#else
 template <typename K>
 void set_smem(K kernel, int bytes)
 {
     if (bytes > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
+#define PMG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 
 template <int C, int PF, int MINB, bool SM, int S, bool WEIGHTED>
 void down_launch_w(const FusedLevel &lv, double *cf, int pitch_c, bool x_is_zero, bool resid, const StripGeom &g,
@@ -701,19 +744,19 @@ void down_launch_w(const FusedLevel &lv, double *cf, int pitch_c, bool x_is_zero
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
     } else if (resid) {
         auto k = k_down<C, PF, MINB, SM, S, false, true, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
     } else {
         auto k = k_down<C, PF, MINB, SM, S, false, false, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
         (void)once;
-        k<<<grid, block, sm, st>>>(lv.x, lv.xb, lv.f, nullptr, g, 0, nc, c, inv, done, lv.hp);
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, (double *)nullptr, g, 0, nc, c, inv, done, lv.hp);
     }
 }
 
@@ -742,7 +785,7 @@ void up_launch_k(const FusedLevel &lv, const double *e, int pitch_c, const Strip
     int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
     static bool once = (set_smem(k, sm), true);
     (void)once;
-    k<<<dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st>>>(lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials, done);
+    PMG_LAUNCH(k, dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st, lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials, done);
 }
 
 template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM>

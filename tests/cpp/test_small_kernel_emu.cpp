@@ -14,10 +14,6 @@
 #include "../../parallel-geometric-multigrid-for-poisson-problem_b200/csrc/kernels_small.cu"
 #include "../../oracle/oracle.h"
 
-thread_local EmuDim3 threadIdx;
-EmuDim3 blockDim;
-EmuBarrier g_emu_named[16];
-EmuBarrier g_emu_warp[32];
 
 static int run_case(int n0, int gamma, double omega, int nu1, int nu2, int lo, bool x_is_zero, unsigned seed)
 {
