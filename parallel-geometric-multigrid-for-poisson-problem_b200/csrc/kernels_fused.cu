@@ -221,6 +221,21 @@ struct RowSource {
     }
 };
 
+// PADY rows x C columns of this lane, peer memory -> local halo rows: all loads first (L1-bypassing), then the stores
+template <int C>
+__device__ __forceinline__ void copy_halo_rows(const double *__restrict__ src, double *__restrict__ dst, int pitch)
+{
+    double2 v[PADY][C / 2];
+#pragma unroll
+    for (int r = 0; r < PADY; ++r)
+#pragma unroll
+        for (int p = 0; p < C / 2; ++p) v[r][p] = __ldcg(reinterpret_cast<const double2 *>(src + (ptrdiff_t)r * pitch) + p);
+#pragma unroll
+    for (int r = 0; r < PADY; ++r)
+#pragma unroll
+        for (int p = 0; p < C / 2; ++p) reinterpret_cast<double2 *>(dst + (ptrdiff_t)r * pitch)[p] = v[r][p];
+}
+
 template <int C, int PF, int S, bool USE_X>
 struct RegFeed {
     static constexpr int UNROLL = PF;  // slot index must be static: the row loop is unrolled by PF
@@ -388,7 +403,7 @@ struct FeedSelect<C, PF, S, USE_X, true> {
 // ---------------------------------------------------------------------------------------------------
 // Pass A.  S sweeps; RESID adds residual + full weighting into the coarse RHS; ZEROX: x == 0 on entry.
 // ---------------------------------------------------------------------------------------------------
-template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID, bool WEIGHTED>
+template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID, bool WEIGHTED, bool PROLOGUE = false>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_down(const double *__restrict__ x, double *__restrict__ xo, const double *__restrict__ f,
            double *__restrict__ cf, StripGeom g, int pitch_c, int nc, JacobiCoef coef, double inv_h2,
@@ -430,21 +445,58 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
         if (hp.pub_up != nullptr) publish_epoch(hp.pub_up, hp.epoch);
         if (hp.pub_dn != nullptr) publish_epoch(hp.pub_dn, hp.epoch);
     }
-    // ... then, before the first access to a neighbour's rows, every warp waits until it has published them
-    if (hp.flag_up != nullptr || hp.flag_dn != nullptr) {
-        int ok = 1;
-        if (lane == 0) {
-            if (hp.flag_up != nullptr) ok = wait_flag(hp.flag_up, hp.epoch) ? ok : 0;
-            if (hp.flag_dn != nullptr) ok = wait_flag(hp.flag_dn, hp.epoch) ? ok : 0;
+    // ... then, before the first access to a neighbour's rows, wait until it has published them.
+    HaloPeers feed_peers = hp;  // what the row feed sees
+    if constexpr (!PROLOGUE) {
+        // every warp waits; halo rows are streamed from the neighbour's memory in place by the row feed
+        if (hp.flag_up != nullptr || hp.flag_dn != nullptr) {
+            int ok = 1;
+            if (lane == 0) {
+                if (hp.flag_up != nullptr) ok = wait_flag(hp.flag_up, hp.epoch) ? ok : 0;
+                if (hp.flag_dn != nullptr) ok = wait_flag(hp.flag_dn, hp.epoch) ? ok : 0;
+            }
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (!ok) {
+                if (lane == 0) *hp.err = 1;
+                return;
+            }
         }
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) {
-            if (lane == 0) *hp.err = 1;
-            return;
+    } else {
+        // HALO PROLOGUE (shared-memory feed only; opt-in, PMG_HALO_PROLOGUE=1).  Only the warps whose rows reach into
+        // a neighbour's slab wait for its flag -- the others start at once and hide the flag latency -- and they copy
+        // the PADY remote rows of their strip into the local halo rows with every load in flight at once (one NVLink
+        // round trip instead of one per pipelined row step), then stream from local memory.  Each lane later reads
+        // back exactly the 16-byte pieces it wrote itself (cp.async.cg, L2), so no barrier is needed.
+        static_assert(!PROLOGUE || SM, "the register feed reads through the non-coherent path: no prologue");
+        if (hp.flag_up != nullptr || hp.flag_dn != nullptr) {
+            const bool need_up = hp.flag_up != nullptr && j_start < 0;
+            const bool need_dn = hp.flag_dn != nullptr && j_end >= g.ny;
+            if (need_up || need_dn) {
+                int ok = 1;
+                if (lane == 0) {
+                    if (need_up) ok = wait_flag(hp.flag_up, hp.epoch) ? ok : 0;
+                    if (need_dn) ok = wait_flag(hp.flag_dn, hp.epoch) ? ok : 0;
+                }
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (!ok) {
+                    if (lane == 0) *hp.err = 1;
+                    return;
+                }
+                const ptrdiff_t up_off = (ptrdiff_t)col - (ptrdiff_t)PADY * g.pitch, dn_off = (ptrdiff_t)col + (ptrdiff_t)g.ny * g.pitch;
+                if (need_up) {
+                    if (!ZEROX && hp.x_up != nullptr) copy_halo_rows<C>(hp.x_up + up_off, hp.x_keep + up_off, g.pitch);
+                    if (hp.f_up != nullptr) copy_halo_rows<C>(hp.f_up + up_off, hp.f_keep + up_off, g.pitch);
+                }
+                if (need_dn) {
+                    if (!ZEROX && hp.x_dn != nullptr) copy_halo_rows<C>(hp.x_dn + col, hp.x_keep + dn_off, g.pitch);
+                    if (hp.f_dn != nullptr) copy_halo_rows<C>(hp.f_dn + col, hp.f_keep + dn_off, g.pitch);
+                }
+            }
+            feed_peers = HaloPeers{};
         }
     }
     Feed feed;
-    feed.init(x, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5, hp, g.ny);
+    feed.init(x, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5, feed_peers, g.ny);
     const int ycoarse = g.yoff >> 1;  // global coarse row of local coarse row 0
 
     for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
@@ -652,6 +704,8 @@ constexpr VariantDesc VARIANTS[NUM_VARIANTS] = {
     {2, 7, 4, 1},  // 4: 7 rows in flight per warp (16 + 8 ring slots): for the LATENCY-bound small levels, where a
                    //    warp's whole chunk is a dozen rows and the pass time is (rows x load latency / depth)
 };
+// fused halo exchange with the halo prologue (see k_down); PMG_HALO_PROLOGUE=1, or fused_set_halo_prologue
+int g_halo_prologue = PMG_HALO_PROLOGUE_DEFAULT;
 // levels with n <= this use variant 4 (0 = never).  PMG_DEEP_PREFETCH_BELOW overrides.
 int g_deep_prefetch_below = -1;
 int deep_prefetch_below()
@@ -739,7 +793,22 @@ template <int C, int PF, int MINB, bool SM, int S, bool WEIGHTED>
 void down_launch_w(const FusedLevel &lv, double *cf, int pitch_c, bool x_is_zero, bool resid, const StripGeom &g,
                    int nc, const JacobiCoef &c, double inv, dim3 grid, dim3 block, const int *done, cudaStream_t st)
 {
-    if (resid && x_is_zero) {
+    // the halo-prologue flavour exists for the headline sweep count on the shared-memory feed only
+    constexpr bool CAN_PROLOGUE = SM && S == 2;
+    const bool prologue = CAN_PROLOGUE && g_halo_prologue && (lv.hp.flag_up != nullptr || lv.hp.flag_dn != nullptr);
+    if (resid && x_is_zero && prologue) {
+        auto k = k_down<C, PF, MINB, SM, S, true, true, WEIGHTED, CAN_PROLOGUE>;
+        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
+        static bool once = (set_smem(k, sm), true);
+        (void)once;
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
+    } else if (resid && prologue) {
+        auto k = k_down<C, PF, MINB, SM, S, false, true, WEIGHTED, CAN_PROLOGUE>;
+        int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
+        static bool once = (set_smem(k, sm), true);
+        (void)once;
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
+    } else if (resid && x_is_zero) {
         auto k = k_down<C, PF, MINB, SM, S, true, true, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
         static bool once = (set_smem(k, sm), true);
@@ -842,6 +911,8 @@ void fused_set_variant(int v)
 int fused_get_variant() { return g_variant_down | (g_variant_up << 8); }
 void fused_set_min_chunk_rows(int r) { g_min_chunk_rows = (r >= 2) ? (r + (r & 1)) : 2; }
 void fused_set_deep_prefetch_below(int n) { g_deep_prefetch_below = n; }
+void fused_set_halo_prologue(int on) { g_halo_prologue = on ? 1 : 0; }
+int fused_halo_prologue() { return g_halo_prologue; }
 
 int fused_max_partials(int n)
 {

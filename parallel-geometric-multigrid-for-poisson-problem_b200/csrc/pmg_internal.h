@@ -155,13 +155,14 @@ void launch_rhs_separable(double *f, int pitch, int nx, int ny, double factor, c
 // column 0).  f halo rows fetched this way are also written to `f_keep` so that the later Pass B reads them locally.
 struct HaloPeers {
     const double *x_up, *x_dn, *f_up, *f_dn;
-    double *f_keep;
+    double *f_keep;                // local f (writable): halo rows fetched from a peer are kept for Pass B
     const int *flag_up, *flag_dn;  // inbox flags that must reach `epoch` before the first peer access
     int *pub_up, *pub_dn;          // the neighbours' inbox slots for ME (peer pointers): thread 0 of the launch
                                    // publishes `epoch` there first -- everything this stream ran before the launch
                                    // is complete, so "my boundary rows are final" needs no kernel of its own
     int epoch;
     int *err;                      // raised if that wait times out
+    double *x_keep;                // local x (writable): where the halo prologue stores the neighbours' x rows
 };
 
 #ifndef PMG_HOST_EMULATION
@@ -211,6 +212,11 @@ void fused_set_min_chunk_rows(int r);
 // n < 0: back to PMG_DEEP_PREFETCH_BELOW / the default
 constexpr int PMG_DEEP_PREFETCH_DEFAULT = 0;
 void fused_set_deep_prefetch_below(int n);
+// Pass A's fused halo exchange copies the neighbours' halo rows in a prologue (all loads in flight, only the
+// boundary warps wait for the flags) instead of streaming them in place.  Opt-in until validated on 4+ GPUs.
+constexpr int PMG_HALO_PROLOGUE_DEFAULT = 0;
+void fused_set_halo_prologue(int on);
+int fused_halo_prologue();
 
 // ---- multi-GPU plumbing (comm.cu): no-ops returning PMG_OK while no communicator exists ---------------
 bool comm_ready();

@@ -382,6 +382,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             if (!x_is_zero) {
                 hp.x_up = up_nb ? L.up_x + (ptrdiff_t)PADY * L.pitch : nullptr;
                 hp.x_dn = dn_nb ? L.dn_x : nullptr;
+                hp.x_keep = L.x;
             }
             if (l > 0) {
                 hp.f_up = up_nb ? L.up_f + (ptrdiff_t)PADY * L.pitch : nullptr;
@@ -981,6 +982,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         if (const char *e2 = getenv("PMG_SPLIT_MIN_ROWS")) s->split_min_rows = atoi(e2);
         if (const char *e3 = getenv("PMG_P2P_FUSED")) s->p2p_fused = !(e3[0] == '0');
         if (const char *e4 = getenv("PMG_COARSE_GRAPH")) s->coarse_graph_on = !(e4[0] == '0');
+        if (const char *e5 = getenv("PMG_HALO_PROLOGUE")) fused_set_halo_prologue(e5[0] == '1');
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
@@ -1447,6 +1449,7 @@ int pmg_fused_num_variants(void) { return fused_num_variants(); }
 void pmg_fused_set_variant(int v) { fused_set_variant(v); }
 void pmg_fused_set_min_chunk_rows(int r) { fused_set_min_chunk_rows(r); }
 void pmg_fused_set_deep_prefetch_below(int n) { fused_set_deep_prefetch_below(n); }
+void pmg_fused_set_halo_prologue(int on) { fused_set_halo_prologue(on); }
 
 /* `sweeps` weighted-Jacobi sweeps on the solver's finest level, `block` sweeps per streaming pass
  * (block = 1: one HBM pass per sweep, 24 B/point -- the "Jacobi sweep GB/s" sub-metric). */

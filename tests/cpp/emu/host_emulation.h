@@ -102,6 +102,8 @@ struct double2 {
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 template <typename T>
 inline T __ldg(const T *p) { return *p; }
+template <typename T>
+inline T __ldcg(const T *p) { return *p; }
 using std::max;
 using std::min;
 

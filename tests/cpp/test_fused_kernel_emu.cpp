@@ -236,10 +236,11 @@ struct Rank {
           f(n, y1_ - y0_), cf(nc, yc1_ - yc0_), e(nc, yc1_ - yc0_), inbox{0, 0} {}
 };
 
-static void slab_visit(int n, int ranks, bool first_visit, bool split, int prolong, int sms, bool level0)
+static void slab_visit(int n, int ranks, bool first_visit, bool split, int prolong, int sms, bool level0, bool prologue = false)
 {
     emu_num_sms = sms;
     fused_set_variant(-1);
+    fused_set_halo_prologue(prologue ? 1 : 0);  // halo rows copied by a prologue of Pass A instead of streamed in place
     const double omega = 2.0 / 3.0;
     const int nc = (n - 1) / 2 + 1, nu1 = 2, nu2 = 2, epoch = 7;
     const double h = 1.0 / (n - 1);
@@ -300,6 +301,7 @@ static void slab_visit(int n, int ranks, bool first_visit, bool split, int prolo
         if (!first_visit) {
             hp.x_up = up ? R[r - 1].x.p() + (ptrdiff_t)R[r - 1].ny * K.x.pitch : nullptr;  // row -1 == neighbour's last row
             hp.x_dn = dn ? R[r + 1].x.p() : nullptr;
+            hp.x_keep = K.x.p();
         }
         if (!level0) {
             hp.f_up = up ? R[r - 1].f.p() + (ptrdiff_t)R[r - 1].ny * K.f.pitch : nullptr;
@@ -351,6 +353,13 @@ static void slab_visit(int n, int ranks, bool first_visit, bool split, int prolo
             for (int xx = 0; xx < nc; ++xx) ok = ok && same_bits(K.cf.at(y, xx), E.cf.at(y + K.yc0, xx));
         check(ok, "slab Pass A: coarse f", n, r, ranks);
         check(K.cf.untouched_outside(cf0, 0, K.nyc), "slab Pass A wrote coarse f outside the owned rows", n, r);
+        if (prologue && !first_visit) {  // the prologue stored the neighbours' x rows in the local halo rows
+            ok = true;
+            for (int y = (up ? -PADY : 0); y < (dn ? K.ny + PADY : K.ny); ++y)
+                if (y < 0 || y >= K.ny)
+                    for (int xx = 0; xx < n; ++xx) ok = ok && same_bits(K.x.at(y, xx), x.at(y + K.y0, xx));
+            check(ok, "slab Pass A (prologue): x halo rows", n, r, ranks);
+        }
         if (!level0) {  // the fetched f halo rows were kept locally for Pass B
             ok = true;
             for (int y = (up ? -PADY + 2 : 0); y < (dn ? K.ny + PADY - 2 : K.ny); ++y)
@@ -389,8 +398,9 @@ static void slab_visit(int n, int ranks, bool first_visit, bool split, int prolo
         for (int i = 0; i < np; ++i) s2 += partials[i];
     }
     if (level0 && !first_visit) check(std::fabs(s2 - E.norm2) <= 1e-12 * E.norm2, "slab Pass B: rank-summed residual norm", n, ranks);
-    std::printf("slabs n=%d ranks=%d first_visit=%d split=%d prolong=%d level0=%d sms=%d: %s\n", n, ranks, (int)first_visit,
-                (int)split, prolong, (int)level0, sms, g_bad ? "see above" : "ok");
+    std::printf("slabs n=%d ranks=%d first_visit=%d split=%d prolong=%d level0=%d sms=%d prologue=%d: %s\n", n, ranks,
+                (int)first_visit, (int)split, prolong, (int)level0, sms, (int)prologue, g_bad ? "see above" : "ok");
+    fused_set_halo_prologue(0);
     std::fflush(stdout);
 }
 
@@ -412,6 +422,11 @@ int main(int argc, char **argv)
     slab_visit(129, 2, true, false, ORC_PROLONG_REFERENCE, 148, false);   // coarse level, first visit: f exchanged
     slab_visit(129, 3, false, false, ORC_PROLONG_FULL, 2, false);         // W re-visit on a coarse level, middle rank
     slab_visit(257, 2, false, true, ORC_PROLONG_REFERENCE, 148, true);    // interior / boundary split
+    // the same with the halo prologue (opt-in flavour of Pass A)
+    slab_visit(129, 2, false, false, ORC_PROLONG_REFERENCE, 148, true, true);
+    slab_visit(129, 2, true, false, ORC_PROLONG_REFERENCE, 148, false, true);
+    slab_visit(129, 3, false, false, ORC_PROLONG_FULL, 2, false, true);
+    slab_visit(257, 4, false, true, ORC_PROLONG_REFERENCE, 148, true, true);
     if (full) {
         slab_visit(257, 4, true, true, ORC_PROLONG_REFERENCE, 4, false);
         slab_visit(257, 3, false, true, ORC_PROLONG_FULL, 148, true);
