@@ -1,6 +1,9 @@
 // pmg_internal.h -- declarations shared by the CUDA translation units of libpmg.so.
 // Nothing here is part of the public ABI (that is include/pmg.h).
 #pragma once
+#if defined(PMG_HOST_EMULATION) && defined(__CUDACC__)
+#error "PMG_HOST_EMULATION is for the g++-compiled kernel tests under tests/cpp only; libpmg.so is never built with it"
+#endif
 #ifdef PMG_HOST_EMULATION
 // tests/cpp/emu/host_emulation.h: runs a single-CTA kernel's source on CPU threads (barrier logic and arithmetic
 // checked against the oracle without a GPU); test infrastructure only, never part of libpmg.so
