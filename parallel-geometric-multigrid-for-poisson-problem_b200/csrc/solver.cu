@@ -1510,6 +1510,94 @@ pmg_status pmg_bench_pass(pmg_solver *s, int which, int level, int reps, double 
     return PMG_OK;
 }
 
+/* ---- test hooks: one fused pass on caller-built padded arrays (not part of the reference surface) ----------
+ * tests/test_gpu_slab_kernels.py runs the multi-GPU flavours of Pass A / Pass B -- row slabs, halo rows read from a
+ * "neighbour" through HaloPeers (in place or with the halo prologue), interior / boundary spans, rows finished beyond
+ * the slab -- on ONE GPU, with every rank's arrays in the same device memory, and compares them with the oracle.
+ * All pointers are device pointers to logical (0,0) of arrays in the solver's padded layout (pmg_test_layout). */
+static pmg_status require_device();
+
+typedef struct {
+    double *x, *xb;
+    const double *f;
+    int n, pitch;
+    double h;
+    int ny, yoff, ext_lo, ext_hi, span_lo, span_hi;
+    const double *x_up, *x_dn, *f_up, *f_dn;
+    double *f_keep, *x_keep;
+    int *flag_up, *flag_dn, *pub_up, *pub_dn;
+    int epoch;
+    int *err;
+} pmg_test_slab;
+
+void pmg_test_layout(int n, int *pitch, int *padx, int *pady)
+{
+    if (pitch) *pitch = level_pitch(n);
+    if (padx) *padx = PADX;
+    if (pady) *pady = PADY;
+}
+
+static FusedLevel test_view(const pmg_test_slab *t)
+{
+    FusedLevel v{};
+    v.x = t->x;
+    v.xb = t->xb;
+    v.f = t->f;
+    v.n = t->n;
+    v.pitch = t->pitch;
+    v.h = t->h;
+    v.ny = t->ny;
+    v.yoff = t->yoff;
+    v.ext_lo = t->ext_lo;
+    v.ext_hi = t->ext_hi;
+    v.span_lo = t->span_lo;
+    v.span_hi = t->span_hi;
+    v.hp.x_up = t->x_up;
+    v.hp.x_dn = t->x_dn;
+    v.hp.f_up = t->f_up;
+    v.hp.f_dn = t->f_dn;
+    v.hp.f_keep = t->f_keep;
+    v.hp.x_keep = t->x_keep;
+    v.hp.flag_up = t->flag_up;
+    v.hp.flag_dn = t->flag_dn;
+    v.hp.pub_up = t->pub_up;
+    v.hp.pub_dn = t->pub_dn;
+    v.hp.epoch = t->epoch;
+    v.hp.err = t->err;
+    return v;
+}
+
+pmg_status pmg_test_fused_down(const pmg_test_slab *t, double *coarse_f, int pitch_c, int nu1, double omega, int x_is_zero,
+                               int halo_prologue)
+{
+    if (!t || !fused_supported(nu1)) return fail(PMG_ERR_INVALID, "bad argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    const int before = fused_halo_prologue();
+    fused_set_halo_prologue(halo_prologue);
+    launch_fused_down(test_view(t), coarse_f, pitch_c, nu1, omega, x_is_zero != 0, nullptr);
+    fused_set_halo_prologue(before);
+    PMG_CUDA(cudaDeviceSynchronize());
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+pmg_status pmg_test_fused_up(const pmg_test_slab *t, const double *coarse_x, int pitch_c, int nu2, double omega,
+                             int prolong_mode, double *d_partials, int *n_partials)
+{
+    if (!t || !fused_supported(nu2)) return fail(PMG_ERR_INVALID, "bad argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    FusedLevel v = test_view(t);
+    v.hp = HaloPeers{};
+    launch_fused_up(v, coarse_x, pitch_c, nu2, omega, prolong_mode, d_partials, n_partials, nullptr);
+    PMG_CUDA(cudaDeviceSynchronize());
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+int pmg_test_fused_max_partials(int n) { return fused_max_partials(n); }
+
 /* ---- operator level (dense reference layout, device pointers) ------------------------------------------ */
 static std::mutex g_scratch_mu;
 static double *g_scratch_partials = nullptr;  // reduce_partials() + 1 doubles, per process
