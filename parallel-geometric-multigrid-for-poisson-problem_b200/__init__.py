@@ -118,6 +118,8 @@ def lib():
     L.pmg_fused_num_variants.restype = i
     L.pmg_fused_set_deep_prefetch_below.restype = None
     L.pmg_fused_set_deep_prefetch_below.argtypes = [i]
+    L.pmg_fused_set_halo_prologue.restype = None
+    L.pmg_fused_set_halo_prologue.argtypes = [i]
     L.pmg_small_vcycle_set_version.restype = None
     L.pmg_small_vcycle_set_version.argtypes = [i]
     L.pmg_small_vcycle_version.restype = i
@@ -380,3 +382,9 @@ def small_vcycle_version():
 def set_deep_prefetch_below(n):
     """Levels with n <= this use the 7-rows-in-flight variant of the nu == 2 fused passes (0: never, -1: default)."""
     lib().pmg_fused_set_deep_prefetch_below(n)
+
+
+def set_halo_prologue(on):
+    """Multi-GPU Pass A: copy the neighbours' halo rows in a prologue (only boundary warps wait) instead of
+    streaming them in place.  Opt-in this round (PMG_HALO_PROLOGUE=1 does the same)."""
+    lib().pmg_fused_set_halo_prologue(1 if on else 0)

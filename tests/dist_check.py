@@ -31,10 +31,12 @@ def timing(sizes, rank, world, dev):
     L.pmg_dist_trace_enable.argtypes = [ctypes.c_int]
     L.pmg_dist_trace_enable.restype = None
     for n in sizes:
-        combos = [(1, 0, 0), (2, 0, 0), (2, 2049, 0), (2, 2049, 1)]
-        for small, deep, trace in combos:
+        # (small-level kernel generation, deep-prefetch threshold, halo prologue, phase trace)
+        combos = [(1, 0, 0, 0), (2, 0, 0, 0), (2, 0, 1, 0), (2, 0, 0, 1), (2, 0, 1, 1)]
+        for small, deep, prologue, trace in combos:
             pmg.set_small_vcycle_version(small)
             pmg.set_deep_prefetch_below(deep)
+            pmg.set_halo_prologue(prologue)
             L.pmg_dist_trace_enable(trace)
             s = pmg.Solver(n, omega=2.0 / 3.0, device=dev, rank=rank, n_ranks=world)
             s.set_rhs_sine()
@@ -50,9 +52,9 @@ def timing(sizes, rank, world, dev):
             t = torch.tensor(ms[1:], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print("timing ranks=%d N=%d small_kernel=%d deep_prefetch_below=%d trace=%d: cycles=%d ms %s -> %.1f us/cycle"
-                      % (world, n, small, deep, trace, k, [round(float(v), 3) for v in t], 1e3 * float(t.min()) / k),
-                      flush=True)
+                print("timing ranks=%d N=%d small_kernel=%d deep_prefetch_below=%d halo_prologue=%d trace=%d: cycles=%d ms %s "
+                      "-> %.1f us/cycle" % (world, n, small, deep, prologue, trace, k, [round(float(v), 3) for v in t],
+                                            1e3 * float(t.min()) / k), flush=True)
             if trace:
                 L.pmg_dist_trace_dump(0)
                 dist.barrier()
@@ -60,6 +62,7 @@ def timing(sizes, rank, world, dev):
         L.pmg_dist_trace_enable(0)
     pmg.set_small_vcycle_version(0)
     pmg.set_deep_prefetch_below(-1)
+    pmg.set_halo_prologue(False)
 
 
 def main():
@@ -69,6 +72,10 @@ def main():
         i = args.index("--timing")
         timing_n = [int(v) for v in args[i + 1].split(",")]
         args = args[:i] + args[i + 2:]
+    if "--prologue" in args:  # run the equivalence checks with the halo prologue of Pass A switched on
+        args.remove("--prologue")
+        pmg.set_halo_prologue(True)
+        print("halo prologue ON", flush=True) if int(os.environ.get("RANK", "0")) == 0 else None
     sizes = [int(a) for a in args] or [1025, 4097]
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
