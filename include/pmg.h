@@ -48,7 +48,18 @@ typedef enum pmg_status {
 } pmg_status;
 
 /* MultigridSolver::v_cycle / w_cycle / f_cycle (MultiGrid.hpp:57 / :96 / :138) */
-typedef enum pmg_cycle_kind { PMG_CYCLE_V = 0, PMG_CYCLE_W = 1, PMG_CYCLE_F = 2 } pmg_cycle_kind;
+typedef enum pmg_cycle_kind {
+    PMG_CYCLE_V = 0,
+    PMG_CYCLE_W = 1,
+    PMG_CYCLE_F = 2,
+    /* NOT in the reference: one full-multigrid pass for an ARBITRARY right-hand side and Dirichlet ring (the
+     * reference's F-cycle regenerates the analytic RHS on every level, MultiGrid.hpp:162, and zeroes the ring).
+     * The iterate's ring is kept, its interior restarted from 0: r0 = f - A x; f_1 = R r0, f_{l+1} = R f_l; coarsest
+     * level: coarse_sweeps sweeps from 0; upwards e_l = P e_{l+1} and one V-cycle on (e_l, f_l); finest level
+     * x += P e_1 and one V-cycle on (x, f).  pmg_solve with this kind = one such pass, then V-cycles.  One GPU only.
+     * Specification: the CPU checker's orc_fmg_general, which the GPU result equals bit for bit. */
+    PMG_CYCLE_FMG = 3
+} pmg_cycle_kind;
 
 /* PMG_PROLONG_REFERENCE reproduces MultigridSolver::prolongation (MultiGrid.hpp:208-226): fine row 1
  * and fine column 1 receive no correction.  PMG_PROLONG_FULL corrects every interior fine point

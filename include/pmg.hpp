@@ -234,6 +234,9 @@ public:
         run(PMG_CYCLE_F, phi, f, N);
         if (N == N_final) std::copy(phi, phi + (size_t)N * N, final_solution);
     }
+    // Not in the reference: one full-multigrid pass for an arbitrary right-hand side f and the Dirichlet ring of phi
+    // (PMG_CYCLE_FMG in pmg.h); phi's interior is restarted from zero.  Same signature as v_cycle.
+    void fmg_cycle(double *phi, const double *f, int N, double /*h*/) { run(PMG_CYCLE_FMG, phi, f, N); }
 };
 
 // ---- 3_part_parallel/Parallel_Method.cu:140-199 -----------------------------------------------------------------

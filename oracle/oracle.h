@@ -50,7 +50,12 @@ enum { ORC_PROLONG_REFERENCE = 0, ORC_PROLONG_FULL = 1 };
     /* when hist[k] < rel_tol*hist[0] or k == max_cycles; returns number of cycles done        */ \
     int P##solve(double *phi, const double *f, int n, int kind, double omega, double eps,         \
                  int alpha, int v1, int v2, int prolong_mode, double rel_tol, int max_cycles,     \
-                 double *hist);
+                 double *hist);                                                                   \
+    /* NOT in the reference ("general-RHS FMG"): one full-multigrid pass for an   */ \
+    /* arbitrary f and Dirichlet ring -- the SPECIFICATION libpmg's PMG_CYCLE_FMG is tested      */ \
+    /* against; the ref_ library returns -1                                                     */ \
+    int P##fmg_general(double *phi, const double *f, int n, double h, double omega, int v1,       \
+                       int v2, int prolong_mode);
 
 ORC_DECLARE(orc_)
 ORC_DECLARE(ref_)

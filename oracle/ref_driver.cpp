@@ -208,4 +208,7 @@ int ref_solve(double *phi, const double *f, int n, int kind, double omega, doubl
     return k;
 }
 
+/* general-RHS FMG is not a reference function (oracle.h) */
+int ref_fmg_general(double *, const double *, int, double, double, int, int, int) { return -1; }
+
 }  // extern "C"

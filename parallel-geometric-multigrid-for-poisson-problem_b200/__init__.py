@@ -21,7 +21,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmg.so")
 
-V, W, F = 0, 1, 2
+V, W, F, FMG = 0, 1, 2, 3
 PROLONG_REFERENCE, PROLONG_FULL = 0, 1
 ENGINE_FUSED, ENGINE_OPERATOR = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -607,6 +607,41 @@ static pmg_status cycle_f(pmg_solver *s)
     return rc;
 }
 
+// PMG_CYCLE_FMG: one full-multigrid pass for an arbitrary right-hand side and Dirichlet ring (pmg.h; not a
+// reference function -- SURVEY.md 8f-2; specification: the CPU checker's orc_fmg_general).  Scratch: the
+// residual r0 lives in the F-cycle's spare level-0 array; the coarse right-hand sides are the levels' own f arrays.
+static pmg_status cycle_fmg_general(pmg_solver *s)
+{
+    pmg_status rc = ensure_fmg(s);
+    if (rc != PMG_OK) return rc;
+    const pmg_config &c = s->cfg;
+    const int lc = (int)s->lv.size() - 1;
+    Level &L0 = s->lv[0];
+    drop_graphs(s);  // the coarsest solve may swap x / xb roles
+    // x = (ring kept, interior 0)
+    if (L0.n > 2) launch_fill2d(L0.x + L0.pitch + 1, L0.pitch, L0.n - 2, L0.n - 2, 0.0, s->stream);
+    if (lc == 0 || L0.n <= c.n_coarse) return smooth_operator(s, 0, c.coarse_sweeps, false);
+    // r0 = f - A x into the spare array (interior; its ring is never read), then the chain of restrictions
+    launch_residual(s->f_fmg0, L0.x, L0.f, L0.n, L0.n, L0.pitch, L0.pitch, L0.pitch, L0.h, s->stream);
+    for (int l = 0; l < lc; ++l) {
+        const Level &L = s->lv[l];
+        Level &K = s->lv[l + 1];
+        launch_restrict(l == 0 ? s->f_fmg0 : L.f, K.f, L.n, K.n, L.pitch, K.pitch, s->stream);
+    }
+    // coarsest level: coarse_sweeps sweeps from zero
+    if ((rc = smooth_operator(s, lc, c.coarse_sweeps, true)) != PMG_OK) return rc;
+    // upwards: prolongation into a zeroed level, one V-cycle there; on the finest level the true problem (x, f)
+    for (int l = lc - 1; l >= 0; --l) {
+        Level &K = s->lv[l + 1];
+        Level &L = s->lv[l];
+        if (l > 0) launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);
+        launch_prolong_add(K.x, L.x, K.n, L.n, K.pitch, L.pitch, c.prolong_mode, s->stream);
+        rc = s->fused ? cycle_fused(s, l, false, false, false, nullptr) : cycle_operator(s, l, false, false);
+        if (rc != PMG_OK) return rc;
+    }
+    return PMG_OK;
+}
+
 // The F-cycle on row slabs.  Same operator sequence as cycle_f, level by level:
 //   * levels l < agg_level are slabs: every slab operator that reads a neighbour row is preceded by an NCCL halo
 //     exchange of PADY rows (set-up work -- a handful of exchanges per level, not on the V-cycle's critical path);
@@ -783,6 +818,12 @@ static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
 static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
 {
     pmg_status rc;
+    if (kind == PMG_CYCLE_FMG) {
+        if (s->dist) return fail(PMG_ERR_UNSUPPORTED, "PMG_CYCLE_FMG is single-GPU only");
+        rc = cycle_fmg_general(s);
+        if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
+        return rc;
+    }
     if (kind == PMG_CYCLE_F) {
         rc = s->dist ? cycle_f_dist(s) : cycle_f(s);
         if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
@@ -1379,7 +1420,8 @@ static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol,
     if (res_history) res_history[0] = r0;
     int k = 0;
     while (k < max_cycles) {
-        rc = run_cycle(s, kind, true);
+        // PMG_CYCLE_FMG: one full-multigrid pass, then V-cycles
+        rc = run_cycle(s, (kind == PMG_CYCLE_FMG && k > 0) ? PMG_CYCLE_V : kind, true);
         if (rc != PMG_OK) return rc;
         rc = read_scalar(s, &v);
         if (rc != PMG_OK) return rc;

@@ -52,6 +52,8 @@ class Checker:
         g("cycle").argtypes = [_dp, _dp, _i, _d, _i, _d, _d, _i, _i, _i, _i]
         g("solve").restype = _i
         g("solve").argtypes = [_dp, _dp, _i, _i, _d, _d, _i, _i, _i, _i, _d, _i, _dp]
+        g("fmg_general").restype = _i
+        g("fmg_general").argtypes = [_dp, _dp, _i, _d, _d, _i, _i, _i]
         self._g = g
 
     def jacobi(self, x, f, h, omega=1.0, num_iter=1, eps=0.0):
@@ -97,6 +99,15 @@ class Checker:
         rc = self._g("cycle")(_p(phi), _p(f), n, 1.0 / (n - 1), kind, omega, eps, alpha, v1, v2, prolong)
         if rc != 0:
             raise NotImplementedError("cycle configuration not available in %s" % self.prefix)
+        return phi
+
+    def fmg_general(self, phi, f, omega=2.0 / 3.0, v1=1, v2=1, prolong=PROLONG_REFERENCE):
+        """One general-RHS full-multigrid pass in place on phi (ring kept, interior restarted from 0) -- not a
+        reference function: the specification of PMG_CYCLE_FMG (oracle.h)."""
+        n = phi.shape[0]
+        rc = self._g("fmg_general")(_p(phi), _p(f), n, 1.0 / (n - 1), omega, v1, v2, prolong)
+        if rc != 0:
+            raise NotImplementedError("fmg_general not available in %s" % self.prefix)
         return phi
 
     def solve(self, phi, f, kind=V, omega=2.0 / 3.0, eps=0.0, alpha=2, v1=1, v2=1,
