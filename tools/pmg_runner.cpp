@@ -13,7 +13,7 @@
 //   ops        ParallelTestRunner::plotTimeSequentialVsParallel (:98-125), device side only
 //                                                              timings_{residual,jacobi,restriction,prolungator}_gpu.txt
 //                                                                                                           "num_thread N seconds"
-//   history    (new) residual history to a relative tolerance: history_<cycle>_N<n>.txt                     "cycle norm"
+//   history    (new) residual history to a relative tolerance (V, W, FMG-then-V): history_<cycle>_N<n>.txt  "cycle norm"
 //
 // usage: pmg_runner <mode> [--n 33,65,...] [--iters K] [--alpha A] [--omega W] [--eps E] [--tol T]
 //                          [--prolong reference|full] [--out DIR]
@@ -259,7 +259,7 @@ int main(int argc, char **argv)
             for (int n : o.n_list) {
                 std::vector<double> f((size_t)n * n), u(f.size());
                 manufactured(f, u, n);
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < 3; ++k) {  // V, W, and one general full-multigrid pass followed by V-cycles
                     pmg_config c;
                     pmg_config_default(&c, n);
                     c.omega = o.omega;
@@ -268,11 +268,13 @@ int main(int argc, char **argv)
                     pmg::Solver s(c);
                     s.set_rhs(f.data());
                     s.zero_guess();
-                    std::vector<double> hist = s.solve(k ? PMG_CYCLE_W : PMG_CYCLE_V, o.tol, 200);
-                    std::ofstream out(o.out + "/history_" + (k ? "w" : "v") + "_N" + std::to_string(n) + ".txt");
+                    const pmg_cycle_kind kinds[3] = {PMG_CYCLE_V, PMG_CYCLE_W, PMG_CYCLE_FMG};
+                    const char *tags[3] = {"v", "w", "fmg"};
+                    std::vector<double> hist = s.solve(kinds[k], o.tol, 200);
+                    std::ofstream out(o.out + "/history_" + tags[k] + "_N" + std::to_string(n) + ".txt");
                     out.precision(17);
                     for (size_t i = 0; i < hist.size(); ++i) out << i << " " << hist[i] << "\n";
-                    std::cout << "N = " << n << (k ? " W" : " V") << ": " << hist.size() - 1 << " cycles to "
+                    std::cout << "N = " << n << " " << tags[k] << ": " << hist.size() - 1 << " cycles to "
                               << hist.back() / hist.front() << "\n";
                 }
             }
