@@ -491,9 +491,11 @@ constexpr int GATHER_ILP = 4;
 // blockIdx.y = source rank
 __global__ void __launch_bounds__(256)
     k_gather_pull(double *__restrict__ full, int pitch, int rows, const double *const *__restrict__ srcs,
-                  const int *inbox, int my_rank, int epoch, int *err, int *const *slots, int n_ranks)
+                  const int *inbox, int my_rank, int epoch, int *err, int *const *slots, int n_ranks,
+                  const int *__restrict__ epoch_base)
 {
     const int r = blockIdx.y;
+    if (epoch_base != nullptr) epoch += *epoch_base;
     // "my slab is final" (everything this stream ran before this launch is complete): published by the first block
     if (slots != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < n_ranks &&
         (int)threadIdx.x != my_rank) {
@@ -655,6 +657,17 @@ void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *
     count_launch();
 }
 
+__global__ void k_set_ints(int *dst, IntPack16 vals, int count)
+{
+    if ((int)threadIdx.x < count) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+
+void launch_set_ints(int *dst, const IntPack16 &vals, int count, cudaStream_t st)
+{
+    k_set_ints<<<1, 32, 0, st>>>(dst, vals, count < 16 ? count : 16);
+    count_launch();
+}
+
 void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, cudaStream_t st)
 {
     k_signal_all<<<1, 32, 0, st>>>(slots, n_ranks, my_rank, epoch);
@@ -662,7 +675,7 @@ void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, c
 }
 
 void launch_gather_pull(double *full, int pitch, int rows, const double *const *srcs, const int *inbox, int n_ranks,
-                        int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots)
+                        int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots, const int *epoch_base)
 {
     size_t n2 = (size_t)rows * pitch / 2;
     int bx = (int)((n2 + 256 * GATHER_ILP - 1) / (256 * GATHER_ILP));  // one trip per thread ...
@@ -670,7 +683,8 @@ void launch_gather_pull(double *full, int pitch, int rows, const double *const *
     if (cap < 16) cap = 16;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    k_gather_pull<<<dim3(bx, n_ranks), 256, 0, st>>>(full, pitch, rows, srcs, inbox, my_rank, epoch, err, slots, n_ranks);
+    k_gather_pull<<<dim3(bx, n_ranks), 256, 0, st>>>(full, pitch, rows, srcs, inbox, my_rank, epoch, err, slots, n_ranks,
+                                                     epoch_base);
     count_launch();
 }
 

@@ -440,10 +440,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 
     // fused halo exchange.  First, one thread of the launch tells the neighbours that MY boundary rows are final
     // (the kernels that produced them ran earlier on this stream) ...
+    const int epoch = hp.epoch + (hp.epoch_base != nullptr ? *hp.epoch_base : 0);
     if ((hp.pub_up != nullptr || hp.pub_dn != nullptr) && blockIdx.x == 0 && threadIdx.x == 0) {
         __threadfence_system();
-        if (hp.pub_up != nullptr) publish_epoch(hp.pub_up, hp.epoch);
-        if (hp.pub_dn != nullptr) publish_epoch(hp.pub_dn, hp.epoch);
+        if (hp.pub_up != nullptr) publish_epoch(hp.pub_up, epoch);
+        if (hp.pub_dn != nullptr) publish_epoch(hp.pub_dn, epoch);
     }
     // ... then, before the first access to a neighbour's rows, wait until it has published them.
     HaloPeers feed_peers = hp;  // what the row feed sees
@@ -452,8 +453,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
         if (hp.flag_up != nullptr || hp.flag_dn != nullptr) {
             int ok = 1;
             if (lane == 0) {
-                if (hp.flag_up != nullptr) ok = wait_flag(hp.flag_up, hp.epoch) ? ok : 0;
-                if (hp.flag_dn != nullptr) ok = wait_flag(hp.flag_dn, hp.epoch) ? ok : 0;
+                if (hp.flag_up != nullptr) ok = wait_flag(hp.flag_up, epoch) ? ok : 0;
+                if (hp.flag_dn != nullptr) ok = wait_flag(hp.flag_dn, epoch) ? ok : 0;
             }
             ok = __shfl_sync(0xffffffffu, ok, 0);
             if (!ok) {
@@ -474,8 +475,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             if (need_up || need_dn) {
                 int ok = 1;
                 if (lane == 0) {
-                    if (need_up) ok = wait_flag(hp.flag_up, hp.epoch) ? ok : 0;
-                    if (need_dn) ok = wait_flag(hp.flag_dn, hp.epoch) ? ok : 0;
+                    if (need_up) ok = wait_flag(hp.flag_up, epoch) ? ok : 0;
+                    if (need_dn) ok = wait_flag(hp.flag_dn, epoch) ? ok : 0;
                 }
                 ok = __shfl_sync(0xffffffffu, ok, 0);
                 if (!ok) {

@@ -166,6 +166,8 @@ struct HaloPeers {
     int epoch;
     int *err;                      // raised if that wait times out
     double *x_keep;                // local x (writable): where the halo prologue stores the neighbours' x rows
+    const int *epoch_base;         // (nullable) device int added to `epoch`: a captured launch keeps its arguments, so
+                                   // the host writes the visit's epoch to device memory before each graph replay
 };
 
 #ifndef PMG_HOST_EMULATION
@@ -255,8 +257,15 @@ void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *
 // (`srcs[r]` = peer pointer to rank r's padded row 0, device array; srcs[my_rank] is local) into `full`.
 void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, cudaStream_t st);
 // slots != nullptr: the pull kernel publishes `epoch` itself (no launch_signal_all needed before it)
+// epoch_base (nullable): device int added to `epoch` (graph replay, see HaloPeers)
 void launch_gather_pull(double *full, int pitch, int rows, const double *const *srcs, const int *inbox, int n_ranks,
-                        int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots = nullptr);
+                        int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots = nullptr,
+                        const int *epoch_base = nullptr);
+// dst[i] = vals[i], i < count <= 16 (the epochs of one cycle, written ahead of a graph replay)
+struct IntPack16 {
+    int v[16];
+};
+void launch_set_ints(int *dst, const IntPack16 &vals, int count, cudaStream_t st);
 // every rank contributes `rows` owned rows of its slab; all ranks receive the whole level (rank r's block at
 // row r*rows of `full`).  Needs equally sized slabs (the extra last row of the last rank is the zero ring).
 pmg_status comm_allgather_rows(const double *slab, double *full, int rows, int pitch, cudaStream_t st);

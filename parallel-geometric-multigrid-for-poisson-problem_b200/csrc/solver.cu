@@ -139,6 +139,16 @@ struct pmg_solver {
     cudaGraphExec_t coarse_graph[2] = {nullptr, nullptr};  // [V, W]
     int coarse_graph_kernels[2] = {0, 0};
     bool coarse_graph_on = true;  // PMG_COARSE_GRAPH=0 launches the kernels one by one
+    // The latency-bound MIDDLE of a distributed V-cycle -- Pass A of the short-slab levels, the all-gather, the redundant
+    // coarse solve and Pass B back up: ~16 launches on one stream, no host-visible events -- replayed as ONE CUDA graph
+    // per all-gather buffer parity.  A captured launch keeps its arguments, so the epochs of the visit are written to
+    // `d_epochs` ([l] = halo epoch of slab level l, [15] = all-gather epoch) by a tiny kernel ahead of each replay and
+    // the kernels add them in (HaloPeers::epoch_base).  Opt-in (PMG_MID_GRAPH=1) until measured on GPUs.
+    int *d_epochs = nullptr;
+    cudaGraphExec_t mid_graph[2] = {nullptr, nullptr};
+    int mid_graph_kernels[2] = {0, 0};
+    bool mid_graph_on = false;
+    bool capturing_mid = false;
 };
 
 namespace pmg {
@@ -152,6 +162,11 @@ static void drop_graphs(pmg_solver *s)
                 g = nullptr;
             }
     for (auto &g : s->coarse_graph)
+        if (g) {
+            cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+    for (auto &g : s->mid_graph)
         if (g) {
             cudaGraphExecDestroy(g);
             g = nullptr;
@@ -278,7 +293,7 @@ static pmg_status coarse_solve_redundant(pmg_solver *s, bool w_form, int reps)
         }
         return PMG_OK;
     };
-    if (!s->coarse_graph_on || !fused_graph_ok(s)) return direct();
+    if (!s->coarse_graph_on || !fused_graph_ok(s) || s->capturing_mid) return direct();
     cudaGraphExec_t &ge = s->coarse_graph[w_form ? 1 : 0];
     int &gk = s->coarse_graph_kernels[w_form ? 1 : 0];
     if (ge == nullptr) {
@@ -332,6 +347,57 @@ static void trace_mark(pmg_solver *s, const char *label, int level)
 // The exchange runs on `comm_stream` WHILE Pass A works on the interior rows [8, ny-8), which need no halo;
 // the two boundary strips [-6, 8) and [ny-8, ny+6) follow once the halo has landed.
 static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, bool want_norm, int *n_partials,
+                             const int *done);
+
+// First level of the middle graph: the smallest lg >= 1 such that the slab levels lg .. agg_level-1 all run on the
+// compute stream alone (no interior / boundary split, hence no cross-stream events); 0 = no graph.
+static int mid_graph_first_level(const pmg_solver *s, bool w_form)
+{
+    if (!s->mid_graph_on || w_form || !s->p2p || !s->p2p_fused || !s->p2p_gather || !s->coarse_redundant ||
+        !s->cycle_has_collective || s->d_epochs == nullptr || g_trace_on == 1 || !s->cfg.use_graph)
+        return 0;
+    int lg = s->agg_level;
+    while (lg > 1 && s->lv[lg - 1].ny < s->split_min_rows) --lg;
+    return lg < s->agg_level ? lg : 0;
+}
+
+// levels lg .. coarsest and back: epochs to device memory, then the graph of this all-gather parity
+static pmg_status run_mid_graph(pmg_solver *s, int lg)
+{
+    IntPack16 vals{};
+    for (int l = lg; l < s->agg_level; ++l) vals.v[l] = ++s->lv[l].halo_epoch;
+    vals.v[15] = ++s->agg_epoch;
+    const int parity = s->agg_epoch & 1;
+    s->aslab.f = s->agg_f[parity] + level_origin(s->aslab.n);
+    launch_set_ints(s->d_epochs, vals, 16, s->stream);
+    cudaGraphExec_t &ge = s->mid_graph[parity];
+    int &gk = s->mid_graph_kernels[parity];
+    if (ge == nullptr) {
+        const unsigned long long before = launches_so_far();
+        PMG_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        s->capturing_mid = true;  // cycle_dist: no epoch increments, epochs through d_epochs, plain coarse launches
+        pmg_status rc = cycle_dist(s, lg, false, true, false, nullptr, nullptr);
+        s->capturing_mid = false;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaStreamEndCapture (middle graph): ") + cudaGetErrorString(e));
+        if (rc != PMG_OK) {
+            cudaGraphDestroy(g);
+            return rc;
+        }
+        gk = (int)(launches_so_far() - before);
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaGraphInstantiate (middle graph): ") + cudaGetErrorString(e));
+        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+        return PMG_OK;
+    }
+    PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+    count_launch(gk);
+    return PMG_OK;
+}
+
+static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, bool want_norm, int *n_partials,
                              const int *done)
 {
     const pmg_config &c = s->cfg;
@@ -345,7 +411,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     const bool pull_gather = last_slab && s->p2p_gather && s->coarse_redundant && s->cycle_has_collective &&
                              (!w_form || c.gamma == 1);
     if (pull_gather) {
-        ++s->agg_epoch;
+        if (!s->capturing_mid) ++s->agg_epoch;  // (run_mid_graph advanced it before the capture / replay)
         s->aslab.f = s->agg_f[s->agg_epoch & 1] + level_origin(s->aslab.n);
     } else if (last_slab) {
         s->aslab.f = s->agg_f[0] ? s->agg_f[0] + level_origin(s->aslab.n) : s->aslab.f;
@@ -361,7 +427,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     if (halo_field) {
         int epoch = 0;
         if (s->p2p) {  // publish "my boundary rows of this level are final" in the neighbours' inboxes
-            epoch = ++L.halo_epoch;
+            epoch = s->capturing_mid ? 0 : ++L.halo_epoch;  // captured launches take the epoch from d_epochs[l]
             if (!s->p2p_fused)  // (the fused exchange publishes from inside Pass A, see hp.pub_up / pub_dn below)
                 launch_halo_signal(up_nb ? s->up_flags + 2 * l + 1 : nullptr, dn_nb ? s->dn_flags + 2 * l : nullptr, epoch,
                                    s->stream);
@@ -394,6 +460,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             hp.pub_up = up_nb ? s->up_flags + 2 * l + 1 : nullptr;  // published by the FIRST launch that carries hp
             hp.pub_dn = dn_nb ? s->dn_flags + 2 * l : nullptr;
             hp.epoch = epoch;
+            hp.epoch_base = s->capturing_mid ? s->d_epochs + l : nullptr;
             hp.err = s->d_comm_err;
         } else if (s->p2p) {  // separate pull kernel: neighbours' rows are copied into the local halo rows
             const bool is_x = (halo_field == L.x);
@@ -438,7 +505,9 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         trace_mark(s, "passA", l);
     }
     int reps = w_form ? c.gamma : 1;
-    if (!last_slab) {
+    if (!last_slab && !s->capturing_mid && mid_graph_first_level(s, w_form) == l + 1) {
+        if ((rc = run_mid_graph(s, l + 1)) != PMG_OK) return rc;  // everything below this level: one graph launch
+    } else if (!last_slab) {
         for (int k = 0; k < reps; ++k)
             if ((rc = cycle_dist(s, l + 1, w_form, k == 0, false, nullptr, done)) != PMG_OK) return rc;
     } else {
@@ -449,7 +518,8 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             if (pull_gather) {
                 // publishes "my slab is final" to every rank, then pulls theirs (one launch)
                 launch_gather_pull(A.f, A.pitch, y1[0] - y0[0], s->d_agg_srcs[s->agg_epoch & 1], s->d_flags + 32,
-                                   s->n_ranks, s->rank, s->agg_epoch, s->d_comm_err, s->stream, s->d_agg_slots);
+                                   s->n_ranks, s->rank, s->capturing_mid ? 0 : s->agg_epoch, s->d_comm_err, s->stream,
+                                   s->d_agg_slots, s->capturing_mid ? s->d_epochs + 15 : nullptr);
             } else if ((rc = comm_allgather_rows(K.f, A.f, y1[0] - y0[0], A.pitch, s->stream)) != PMG_OK) {
                 return rc;
             }
@@ -1024,6 +1094,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         if (const char *e3 = getenv("PMG_P2P_FUSED")) s->p2p_fused = !(e3[0] == '0');
         if (const char *e4 = getenv("PMG_COARSE_GRAPH")) s->coarse_graph_on = !(e4[0] == '0');
         if (const char *e5 = getenv("PMG_HALO_PROLOGUE")) fused_set_halo_prologue(e5[0] == '1');
+        if (const char *e6 = getenv("PMG_MID_GRAPH")) s->mid_graph_on = (e6[0] == '1');
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
@@ -1049,6 +1120,8 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
             const int R = cfg->n_ranks, me = cfg->rank;
             bool ok = cudaMalloc((void **)&s->d_flags, 64 * sizeof(int)) == cudaSuccess &&
                       cudaMemset(s->d_flags, 0, 64 * sizeof(int)) == cudaSuccess &&
+                      cudaMalloc((void **)&s->d_epochs, 16 * sizeof(int)) == cudaSuccess &&
+                      cudaMemset(s->d_epochs, 0, 16 * sizeof(int)) == cudaSuccess &&
                       cudaMalloc((void **)&s->d_comm_err, sizeof(int)) == cudaSuccess &&
                       cudaMemset(s->d_comm_err, 0, sizeof(int)) == cudaSuccess;
             const bool want_gather = s->coarse_redundant && R <= 32;
@@ -1180,6 +1253,7 @@ void pmg_destroy(pmg_solver *s)
     cudaFree((void *)s->d_agg_srcs[0]);
     cudaFree((void *)s->d_agg_srcs[1]);
     cudaFree(s->d_flags);
+    cudaFree(s->d_epochs);
     cudaFree(s->d_comm_err);
     if (s->comm_stream) {
         cudaStreamSynchronize(s->comm_stream);

@@ -313,6 +313,11 @@ static void slab_visit(int n, int ranks, bool first_visit, bool split, int prolo
         hp.pub_up = up ? &outbox[2 * r] : nullptr;
         hp.pub_dn = dn ? &outbox[2 * r + 1] : nullptr;
         hp.epoch = epoch;
+        static const int base_part = 5;  // graph replay form: part of the epoch comes from device memory
+        if (prologue || split) {
+            hp.epoch = epoch - base_part;
+            hp.epoch_base = &base_part;
+        }
         int err = 0;
         hp.err = &err;
         Padded xb0 = K.xb, cf0 = K.cf;

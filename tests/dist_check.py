@@ -22,7 +22,7 @@ import pmg_b200 as pmg  # noqa: E402
 
 
 def timing(sizes, rank, world, dev):
-    """solve time per cycle for the latency options (small-level kernel generation, deep prefetch threshold) and,
+    """solve time per cycle for the latency options (small-level kernel generation, halo prologue, middle graph) and,
     for the last combination, the phase trace of the distributed cycle on rank 0"""
     import ctypes
     L = pmg.lib()
@@ -30,13 +30,18 @@ def timing(sizes, rank, world, dev):
     L.pmg_dist_trace_dump.restype = None
     L.pmg_dist_trace_enable.argtypes = [ctypes.c_int]
     L.pmg_dist_trace_enable.restype = None
+    ref_hist = {}
     for n in sizes:
-        # (small-level kernel generation, deep-prefetch threshold, halo prologue, phase trace)
-        combos = [(1, 0, 0, 0), (2, 0, 0, 0), (2, 0, 1, 0), (2, 0, 0, 1), (2, 0, 1, 1)]
-        for small, deep, prologue, trace in combos:
+        # (small-level kernel generation, halo prologue, middle graph [+ no interior/boundary split], phase trace)
+        combos = [(1, 0, 0, 0), (2, 0, 0, 0), (2, 1, 0, 0), (2, 0, 1, 0), (2, 1, 1, 0), (2, 1, 2, 0), (2, 0, 0, 1), (2, 1, 0, 1)]
+        for small, prologue, graph, trace in combos:
             pmg.set_small_vcycle_version(small)
-            pmg.set_deep_prefetch_below(deep)
             pmg.set_halo_prologue(prologue)
+            os.environ["PMG_MID_GRAPH"] = "1" if graph else "0"  # read by pmg_create
+            if graph == 2:  # with the prologue the interior warps never wait: no need to split tall slabs
+                os.environ["PMG_SPLIT_MIN_ROWS"] = "1000000000"
+            else:
+                os.environ.pop("PMG_SPLIT_MIN_ROWS", None)
             L.pmg_dist_trace_enable(trace)
             s = pmg.Solver(n, omega=2.0 / 3.0, device=dev, rank=rank, n_ranks=world)
             s.set_rhs_sine()
@@ -51,18 +56,23 @@ def timing(sizes, rank, world, dev):
                     L.pmg_dist_trace_dump(-1)  # drop the warm-up marks
             t = torch.tensor(ms[1:], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            # every option must reproduce the first combination's residual history bit for bit
+            if ref_hist.get(n) is None:
+                ref_hist[n] = hist.copy()
+            hist_ok = bool(len(hist) == len(ref_hist[n]) and np.array_equal(hist, ref_hist[n]))
             if rank == 0:
-                print("timing ranks=%d N=%d small_kernel=%d deep_prefetch_below=%d halo_prologue=%d trace=%d: cycles=%d ms %s "
-                      "-> %.1f us/cycle" % (world, n, small, deep, prologue, trace, k, [round(float(v), 3) for v in t],
-                                            1e3 * float(t.min()) / k), flush=True)
+                print("timing ranks=%d N=%d small_kernel=%d halo_prologue=%d mid_graph=%d trace=%d: cycles=%d hist_ok=%s ms %s "
+                      "-> %.1f us/cycle" % (world, n, small, prologue, graph, trace, k, hist_ok,
+                                            [round(float(v), 3) for v in t], 1e3 * float(t.min()) / k), flush=True)
             if trace:
                 L.pmg_dist_trace_dump(0)
                 dist.barrier()
             s.close()
         L.pmg_dist_trace_enable(0)
     pmg.set_small_vcycle_version(0)
-    pmg.set_deep_prefetch_below(-1)
     pmg.set_halo_prologue(False)
+    os.environ.pop("PMG_MID_GRAPH", None)
+    os.environ.pop("PMG_SPLIT_MIN_ROWS", None)
 
 
 def main():
