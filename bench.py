@@ -35,6 +35,121 @@ OMEGA = 2.0 / 3.0
 REL_TOL = 1e-8
 BYTES_PER_DOF_CYCLE = 69.3   # 52 B per level-point * 1.3334 (fused two-pass minimum)
 BYTES_PER_POINT_PASS = 26.0  # one fused pass: read x, read f, write x', + coarse array traffic (2 B)
+BYTES_PER_DOF_W2 = 104.0     # W-cycle, gamma = 2: 52 / (1 - 2/4)
+BYTES_PER_DOF_FMG = 125.0    # one full-multigrid pass ~ 1.333 * (69.3 + 18 + 24/4)
+
+
+def goldens():
+    """Residual histories of the reference's CPU multigrid (mg_cpu_exec semantics) at the BASELINE sizes:
+    tests/golden/golden.json["survey"] (SURVEY.md 8c, N = 16385) and tests/golden/golden_large.json
+    (tests/golden/make_golden_large.py over oracle/_ref, N = 4097 and the F-cycle).  Committed fixtures: nothing
+    under oracle/ or /root/reference is touched at run time."""
+    g = {}
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as fh:
+            sv = json.load(fh)["survey"]
+        g["V_n16385"] = sv["V_n16385"]
+        g["V_n16385_full"] = sv["V_n16385_full_prolong"]
+        g["W2_n16385"] = sv["W_alpha2_n16385"]
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "golden_large.json")) as fh:
+            lg = json.load(fh)
+        g["V_n4097"] = lg["V_n4097"]["history"][1:]
+        g["W2_n4097"] = lg["W_alpha2_n4097"]["history"][1:]
+        g["F_n4097"] = lg["F_n4097"]["norms"]
+        if "F_n16385" in lg:
+            g["F_n16385"] = lg["F_n16385"]["norms"]
+    except Exception:
+        pass
+    return g
+
+
+def history_check(hist_after_cycles, golden):
+    """Parity fields of a bench leg: our per-cycle norms (after cycle 1, 2, ...) against the reference's.  The
+    benchmarked configuration sums the norm with the parallel TREE order (pmg_norm_mode), the reference left to
+    right: expected deviation <= 1e-10 up to N = 4097 and <= 2e-9 at N = 16385 (the reference's own summation
+    drift); the cycle count must be identical."""
+    if golden is None:
+        return {"golden": "missing", "cycles_match": None, "history_max_rel_dev": None}
+    ours = [float(v) for v in hist_after_cycles]
+    k = min(len(ours), len(golden))
+    dev = max(abs(a - b) / abs(b) for a, b in zip(ours[:k], golden[:k])) if k else None
+    return {"cycles_match": len(ours) == len(golden), "cycles": len(ours), "golden_cycles": len(golden),
+            "history_max_rel_dev": dev}
+
+
+def config_legs(make_solver, peak, world, reduce_max=None, skip=()):
+    """The other BASELINE.json configs as short legs after the headline (extra keys of the JSON line):
+      W_gamma2_n16385 / F_n16385   configs[3]: W-cycle and the F-cycle (full multigrid pass) at N = 16385
+      V_n4097                      configs[1]: N = 4097 V(2,2) to 1e-8
+      V_n32769                     configs[4]: the 1.07 G DOF weak-scaling point, fixed 8 cycles (1e-8 is below
+                                   the fp64 rounding floor of the un-scaled residual at this size)
+    Each reports cycles, device ms per cycle (max over ranks), GDOF*cycle/s and the fraction of ITS OWN roofline
+    (bytes per DOF per cycle from SURVEY 8d times the aggregate measured HBM peak), plus the history parity
+    fields where a golden exists.  make_solver(n, **cfg) -> solver on this rank's slab."""
+    import pmg_b200 as pmg
+    gold = goldens()
+    rmax = reduce_max or (lambda v: v)
+    legs = {}
+
+    def frac(bytes_per_dof, n, cycles, ms):
+        gbs = bytes_per_dof * n * n * cycles / (ms * 1e-3) / 1e9
+        return {"effective_gbs": gbs, "bytes_per_dof_cycle": bytes_per_dof, "frac_of_aggregate_peak": gbs / (peak * world)}
+
+    def solve_leg(name, n, kind, gamma, bpd, golden, rel_tol=REL_TOL, max_cycles=100, reps=2):
+        try:
+            s = make_solver(n, gamma=gamma)
+            s.set_rhs_sine()
+            best, k, hist = None, 0, None
+            for it in range(reps + 1):
+                s.zero_guess()
+                k, hist = s.solve(kind, rel_tol=rel_tol, max_cycles=max_cycles)
+                ms = rmax(s.last_ms)
+                if it > 0:
+                    best = ms if best is None else min(best, ms)
+            s.close()
+            leg = {"n": n, "cycles": k, "ms_per_solve": best, "ms_per_cycle": best / max(k, 1),
+                   "gdof_per_s_to_tol": (n * n / (best * 1e-3) / 1e9) if rel_tol > 0 else None,
+                   "gdof_cycle_per_s": n * n * k / (best * 1e-3) / 1e9,
+                   "final_rel_residual": float(hist[-1] / hist[0])}
+            leg.update(frac(bpd, n, k, best))
+            if golden is not None or rel_tol > 0:
+                leg.update(history_check(hist[1:], golden))
+            legs[name] = leg
+        except Exception as e:  # noqa: BLE001 -- a failing leg must not lose the headline line
+            legs[name] = {"error": repr(e)[:300]}
+
+    if "W" not in skip:
+        solve_leg("W_gamma2_n16385", 16385, pmg.W, 2, BYTES_PER_DOF_W2, gold.get("W2_n16385"))
+    if "F" not in skip:
+        try:
+            n = 16385
+            s = make_solver(n, gamma=1)
+            s.set_rhs_sine()
+            best, norm = None, None
+            for it in range(3):
+                s.zero_guess()
+                norm = s.cycle(pmg.F)
+                ms = rmax(s.last_ms)
+                if it > 0:
+                    best = ms if best is None else min(best, ms)
+            s.close()
+            leg = {"n": n, "passes": 1, "ms_per_pass": best, "gdof_per_s": n * n / (best * 1e-3) / 1e9,
+                   "residual_norm_after_pass": norm}
+            leg.update(frac(BYTES_PER_DOF_FMG, n, 1, best))
+            gf = gold.get("F_n16385")
+            leg["golden_norm"] = gf[0] if gf else None
+            leg["norm_rel_dev"] = abs(norm - gf[0]) / gf[0] if gf else None
+            legs["F_n16385"] = leg
+        except Exception as e:  # noqa: BLE001
+            legs["F_n16385"] = {"error": repr(e)[:300]}
+    if "4097" not in skip:
+        solve_leg("V_n4097", 4097, pmg.V, 1, BYTES_PER_DOF_CYCLE, gold.get("V_n4097"), reps=3)
+    if "32769" not in skip:
+        solve_leg("V_n32769", 32769, pmg.V, 1, BYTES_PER_DOF_CYCLE, None, rel_tol=0.0, max_cycles=8, reps=1)
+    return legs
 
 
 def hbm_peak():
@@ -166,15 +281,37 @@ def reference_cuda_build(sizes=((4097, 3), (16385, 2))):
     return out
 
 
+def cpu_same_config_n4097():
+    """BASELINE config 2 measured for real on the host: the reference's CPU multigrid from phi0 = 0 to 1e-8 at
+    N = 4097 (36 cycles, ~1 min on one core).  bench.py's own arm reports the same solve on the GPU (leg V_n4097)."""
+    import cpu_checkers as cc
+    lib = cc.load("ref")
+    kind = "reference"
+    if lib is None:
+        lib, kind = cc.load("orc"), "port"
+    n = 4097
+    f = lib.rhs(n)
+    phi = np.zeros((n, n))
+    t0 = time.perf_counter()
+    k, hist = lib.solve(phi, f, kind=cc.V, omega=OMEGA, eps=0.0, alpha=1, v1=1, v2=1, rel_tol=REL_TOL, max_cycles=100)
+    dt = time.perf_counter() - t0
+    return {"n": n, "cycles": int(k), "seconds": dt, "gdof_per_s_to_tol": n * n / dt / 1e9, "kind": kind, "cores": 1,
+            "final_rel_residual": float(hist[-1] / hist[0])}
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores.  Each step
-    is a bounded sample (one V(2,2) cycle at N = 4097, ~2 s) scaled by DOF*cycles to the 39-cycle solve at
-    N = 16385.  The reference is single-threaded (no OpenMP/threads anywhere): cores = 1."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle/_ref =
+    the unmodified reference headers compiled here).  The named workload (39 cycles at N = 16385) takes the
+    reference ~20 min and 13 GB, so each STEP is a bounded sample -- one V(2,2) cycle at N = 4097 -- and `value`
+    is that sample scaled by DOF*cycles to the named workload; `ms_per_step` is the time the sample really took
+    and `config.workload` says so.  In addition the line carries `measured_same_config`: BASELINE config 2
+    (N = 4097 to 1e-8) solved for real, once, which pairs with our arm's `legs.V_n4097`.  The reference is
+    single-threaded (no OpenMP / threads anywhere in it): cores = 1."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     n_s, cyc_s = 4097, 1
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 2)):
         cpu_reference_sample(n_s, cyc_s, args.n, args.cycles_expected)
     vals, secs, kind = [], 0.0, "reference"
     for _ in range(args.steps):
@@ -182,15 +319,22 @@ def run_reference(args):
         vals.append(v)
         secs += dt
     value = len(vals) / sum(1.0 / v for v in vals)  # total work / total time
-    ms_per_step = 1e3 * args.n * args.n / (value * 1e9)
-    sample = ("%d V(2,2) cycle(s) at N=%d per step, scaled by DOF*cycles to %d cycles at N=%d"
-              % (cyc_s, n_s, args.cycles_expected, args.n))
+    same = None if args.no_same_config else cpu_same_config_n4097()
+    sample = ("%d V(2,2) cycle(s) at N=%d per step (%.2f s each, 1 core), scaled by DOF*cycles to %d cycles at N=%d"
+              % (cyc_s, n_s, secs / max(args.steps, 1), args.cycles_expected, args.n))
+    cfg = workload_config(args, 1)
+    cfg["workload"] = ("SAMPLE of the named workload: " + sample + " -- the full N=%d solve is NOT run on the CPU "
+                       "(~20 min, 13 GB); see measured_same_config for a solve measured end to end" % args.n)
+    cfg["sampled"] = True
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+            "ms_per_solve_extrapolated": 1e3 * args.n * args.n / (value * 1e9),
+            "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                              "host_cores_available": os.cpu_count(), "measured_seconds": secs},
+            "measured_same_config": same,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -202,6 +346,7 @@ def workload_config(args, n_gpus):
                         "RHS 2pi^2 sin(pi x)sin(pi y), phi0=0" % (args.n, args.n * args.n / 1e6),
             "n": args.n, "cycle": "V(2,2)", "omega": OMEGA, "rel_tol": REL_TOL,
             "prolongation": args.prolong, "engine": "fused", "l2": "inputs_exceed_l2 (2.1 GB per array)",
+            "norm_mode": "tree (pmg_norm_mode; the reference sums left to right -- see history_max_rel_dev)",
             "parallelism": "1 GPU" if n_gpus == 1 else "row slabs x%d" % n_gpus}
 
 
@@ -281,6 +426,15 @@ def run_single(args):
         pmg.lib().pmg_host_free_pinned(p)
     s.close()
 
+    # ---- parity of the timed configuration against the reference's CPU history (committed golden) ----
+    gold = goldens()
+    parity = history_check(hist[1:], gold.get("V_n16385_full" if args.prolong == "full" else "V_n16385")) \
+        if n == 16385 else history_check(hist[1:], gold.get("V_n%d" % n))
+    # ---- the other BASELINE configs (W, F, N = 4097, N = 32769) as short legs ----
+    legs = None
+    if not args.no_legs:
+        legs = config_legs(lambda nn, **cfg: pmg.Solver(nn, omega=OMEGA, prolong_mode=prolong, device=0, **cfg), peak, 1)
+
     # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
     cpu = None
     if not args.no_cpu_baseline:
@@ -290,7 +444,12 @@ def run_single(args):
                          "reference is single-threaded" % (secs, k, n),
                "host_cores_available": os.cpu_count()}
 
-    ref_cuda = None if args.no_ref_cuda else reference_cuda_build()
+    ref_cuda = None
+    if not args.no_ref_cuda:
+        rc_clocks = ClockSampler(0)
+        rc_clocks.start()
+        ref_cuda = reference_cuda_build()
+        ref_cuda["clocks"] = rc_clocks.stop()
     if ref_cuda and str(n) in ref_cuda and "best_cycle_ms" in ref_cuda[str(n)]:
         ref_cuda["ours_cycle_ms_same_n"] = dev_ms / args.steps / k
         ref_cuda["speedup_per_cycle_same_n"] = ref_cuda[str(n)]["best_cycle_ms"] / (dev_ms / args.steps / k)
@@ -299,10 +458,15 @@ def run_single(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
             "cycles_to_converge": k, "converged": converged, "final_rel_residual": float(hist[-1] / hist[0]),
+            "cycles_match": parity["cycles_match"], "history_max_rel_dev": parity["history_max_rel_dev"],
+            "history_parity": parity,
             "gdof_cycle_per_s": n * n * k / (dev_ms / args.steps * 1e-3) / 1e9,
             "device_ms_per_step": dev_ms / args.steps,
+            "legs": legs,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": dom_name,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "committed ncu --set full capture (profiles/), not re-measured in this run",
+                         "kernel": dom_name,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms, "peak_source": peak_src,
                          "pass_down_ms": t_down, "pass_up_norm_ms": t_upn,
                          "vcycle_effective_gbs_at_69.3B_per_dof": cycle_gbs, "vcycle_frac": cycle_gbs / peak},
@@ -325,6 +489,10 @@ def main():
     ap.add_argument("--cycles-expected", type=int, default=39, dest="cycles_expected")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA build")
+    ap.add_argument("--no-legs", action="store_true", dest="no_legs",
+                    help="skip the W / F / N=4097 / N=32769 legs (the other BASELINE configs)")
+    ap.add_argument("--no-same-config", action="store_true", dest="no_same_config",
+                    help="--impl reference: skip the N=4097 solve measured end to end (~1 min)")
     ap.add_argument("--agglomerate-below", type=int, default=513, dest="agglomerate_below",
                     help="multi-GPU: levels with n <= this run on rank 0 only")
     args = ap.parse_args()

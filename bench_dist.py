@@ -97,6 +97,19 @@ def run(args):
     for p in (pf, px, po):
         pmg.lib().pmg_host_free_pinned(p)
     s.close()
+
+    # the other BASELINE configs on the same ranks (W and F at N = 16385, N = 4097, the N = 32769 weak-scaling point)
+    def reduce_max(v):
+        tv = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return float(tv[0])
+
+    legs = None
+    if not args.no_legs:
+        legs = bench.config_legs(lambda nn, **cfg: pmg.Solver(nn, omega=bench.OMEGA, prolong_mode=prolong, device=dev,
+                                                              rank=rank, n_ranks=world,
+                                                              agglomerate_below=args.agglomerate_below, **cfg),
+                                 peak, world, reduce_max)
     pmg.comm_finalize()
 
     if rank == 0:
@@ -104,12 +117,17 @@ def run(args):
         dom_ms, dom_name = (t_upn, "k_up<nu2=2,prolong,norm>") if t_upn >= t_down else (t_down, "k_down<nu1=2,resid>")
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         cycle_gbs = bench.BYTES_PER_DOF_CYCLE * n * n * k / (dev_ms / args.steps * 1e-3) / 1e9
+        gold = bench.goldens()
+        parity = bench.history_check(hist[1:], gold.get(("V_n16385_full" if args.prolong == "full" else "V_n16385")
+                                                        if n == 16385 else "V_n%d" % n))
         line = {"metric": bench.METRIC, "value": n * n / (wall / args.steps) / 1e9, "unit": bench.UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench.workload_config(args, world),
                 "cycles_to_converge": k, "converged": bool(hist[-1] < bench.REL_TOL * hist[0]),
                 "final_rel_residual": float(hist[-1] / hist[0]),
+                "cycles_match": parity["cycles_match"], "history_max_rel_dev": parity["history_max_rel_dev"],
+                "history_parity": parity, "legs": legs,
                 "gdof_cycle_per_s": n * n * k / (dev_ms / args.steps * 1e-3) / 1e9,
                 "device_ms_per_step": dev_ms / args.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

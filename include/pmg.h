@@ -136,6 +136,18 @@ pmg_status pmg_residual_norm(pmg_solver *s, double *norm_out);
 /* one cycle in place (MultiGridTestRunner.hpp:190-209; F = the runner's wrapper :192-205);
  * res_norm_out (nullable) receives ||f - A phi|| after the cycle */
 pmg_status pmg_cycle(pmg_solver *s, pmg_cycle_kind kind, double *res_norm_out);
+/* MultigridSolver::compute_coarsest_grid (MultiGrid.hpp:28-55): `fine` (n x n, the solver's size) restricted by repeated
+ * full weighting down to the n_out x n_out level of the hierarchy (rings stay zero); the solver's iterate is untouched.
+ * Single GPU. */
+pmg_status pmg_restrict_to_level(pmg_solver *s, const double *fine, pmg_mem where_in, int n_out, double *out,
+                                 pmg_mem where_out);
+/* MultigridSolver::f_cycle(phi, f, N_init, h_init) (MultiGrid.hpp:138-183): nested iteration from the n_init x n_init
+ * level -- starting iterate phi_init and right-hand side f_init, both n_init x n_init -- up to the solver's n: per level
+ * fmg_sweeps sweeps, prolongation into a zeroed finer grid, the ANALYTIC right-hand side there (:162) and one V-cycle.
+ * The result is the solver's iterate (the reference's `final_solution`: pmg_get_solution); the solver's own right-hand
+ * side is untouched.  n_init == n copies phi_init (the while loop never runs).  res_norm_out nullable.  Single GPU. */
+pmg_status pmg_f_cycle_from(pmg_solver *s, const double *phi_init, const double *f_init, int n_init, pmg_mem where,
+                            double *res_norm_out);
 /* cycles until ||r|| < rel_tol*||r0|| or max_cycles; res_history (nullable, max_cycles+1 doubles):
  * [0] = ||r0||, [k] = after cycle k; n_cycles_out (nullable) = cycles done.  The "residual-history
  * output" the reference computes and discards (MultiGridTestRunner.hpp:210-212). */
@@ -164,6 +176,10 @@ pmg_status pmg_prolong_add(const double *coarse, double *fine, int nc, int nf, i
 /* sum v[i]^2 over l entries -> HOST double (DynamicGridUtils::norm squared, :21-27) */
 pmg_status pmg_norm2(const double *v, size_t l, double *norm2_out, void *stream);
 
+/* The operator-level calls keep a little per-device scratch between calls (reduction partials; for long pmg_jacobi
+ * runs three padded copies of the field).  This frees it; the next call re-allocates. */
+pmg_status pmg_release_scratch(void);
+
 /* ---- memory helpers for callers without a CUDA toolchain ------------------------------------- */
 pmg_status pmg_device_alloc(void **p, size_t bytes);
 pmg_status pmg_device_free(void *p);
@@ -178,7 +194,11 @@ int pmg_device_count(void);
  *      pmg_set_guess / pmg_get_solution then move THIS RANK'S rows [y0, y1) (pmg_partition_rows), (y1-y0) x n
  *      doubles.  Halo rows travel over NVLink peer memory (CUDA IPC) when every rank can map its neighbours,
  *      over NCCL send/recv otherwise (PMG_P2P=0 forces the latter).  V-, W- and F-cycles, nu <= 2; results are
- *      bit-identical to one GPU (the F-cycle needs equally sized slabs: n_ranks a power of two). ------------ */
+ *      bit-identical to one GPU (the F-cycle needs equally sized slabs: n_ranks a power of two).
+ *      Failure semantics: a rank that waits longer than PMG_P2P_TIMEOUT_S (environment, default 30 s of device wall time)
+ *      for a neighbour's rows gives up, the finest level's iterate of that cycle is NOT committed, and the call -- and
+ *      every later call on that handle -- returns PMG_ERR_COMM: the ranks' exchange epochs no longer agree, so the
+ *      solver must be destroyed and re-created on every rank. ------------ */
 #define PMG_COMM_ID_BYTES 128
 pmg_status pmg_comm_unique_id(unsigned char id[PMG_COMM_ID_BYTES]);
 /* must be called (collectively) before pmg_create with cfg.n_ranks > 1 */

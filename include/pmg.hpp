@@ -30,6 +30,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "pmg.h"
@@ -159,28 +160,41 @@ public:
 // ---- 2_part_MG/MultiGrid.hpp:9-183 ---------------------------------------------------------------------------
 // HOST pointers, in-place on phi.  The injected Smoother supplies omega and epsilon (its smooth() is NOT called
 // per level -- the whole cycle runs on the device); v1 = v2 = 1 and N_coarse = 5 as in the reference
-// (MultiGrid.hpp:15-19) and adjustable here.
+// (MultiGrid.hpp:15-19) and adjustable here: the public knobs and the smoother's omega / epsilon are re-read on
+// EVERY call (the hierarchy in HBM is cached per distinct configuration).
+//
+// PERFORMANCE NOTE (epsilon): the reference's smoothers stop early when the un-scaled ||r|| drops below epsilon
+// (Smoother.hpp:84-88; default 1e-6, the runner uses 1e-7).  Reproducing that needs the residual norm on the HOST
+// after every sweep, so any epsilon > 0 selects the operator-granular engine with one read-back per sweep -- faithful,
+// and roughly an order of magnitude slower than the fused engine.  Construct the smoother with epsilon = 0, or set
+// `honour_smoother_eps = false` here, to run the fused passes (identical results whenever the early exit would not
+// have fired, which is the case for every V/W-cycle above the 5x5 level; SURVEY.md 8c "epsilon sensitivity").
 class MultigridSolver {
     Smoother *smoother;
     int alpha;
     int N_final;
-    std::map<int, Solver *> solvers_;  // one HBM hierarchy per grid size seen
+    // (N, v1, v2, N_coarse, prolong_mode, alpha, omega, eps) -> hierarchy
+    typedef std::tuple<int, int, int, int, int, int, double, double> Key;
+    std::map<Key, Solver *> solvers_;
 
     Solver &get(int N)
     {
-        auto it = solvers_.find(N);
+        const double w = smoother ? smoother->omega() : 1.0;
+        const double eps = (smoother && honour_smoother_eps) ? smoother->eps() : 0.0;
+        Key key(N, v1, v2, N_coarse, prolong_mode, alpha, w, eps);
+        auto it = solvers_.find(key);
         if (it != solvers_.end()) return *it->second;
         pmg_config c;
         pmg_config_default(&c, N);
         c.nu1 = v1 + 1;
         c.nu2 = v2 + 1;
-        c.omega = smoother ? smoother->omega() : 1.0;
-        c.smoother_eps = smoother ? smoother->eps() : 0.0;
+        c.omega = w;
+        c.smoother_eps = eps;
         c.gamma = alpha;
         c.n_coarse = N_coarse;
         c.prolong_mode = prolong_mode;
         Solver *s = new Solver(c);
-        solvers_[N] = s;
+        solvers_[key] = s;
         return *s;
     }
 
@@ -197,7 +211,8 @@ public:
     int v1 = 1, v2 = 1;  // reference num_iter values: 2 pre / 2 post sweeps
     int N_coarse = 5;
     int prolong_mode = PMG_PROLONG_REFERENCE;
-    double *final_solution;  // MultiGrid.hpp:20; filled by f_cycle
+    bool honour_smoother_eps = true;  // see the performance note above
+    double *final_solution;           // MultiGrid.hpp:20; filled by f_cycle
 
     explicit MultigridSolver(Smoother *smoother_, int alpha_, int N_final_)
         : smoother(smoother_), alpha(alpha_), N_final(N_final_)
@@ -215,17 +230,29 @@ public:
     void v_cycle(double *phi, const double *f, int N, double /*h*/) { run(PMG_CYCLE_V, phi, f, N); }
     void w_cycle(double *phi, const double *f, int N, double /*h*/) { run(PMG_CYCLE_W, phi, f, N); }
 
-    // MultiGrid.hpp:138-183 called the way the runner calls it (MultiGridTestRunner.hpp:192-205): phi / f are
-    // the N_init x N_init coarse fields; the pass works up to N_final with the analytic right-hand side and
-    // leaves the result in final_solution.  The device path needs the fine-grid iterate the runner restricted
-    // phi from, so use f_cycle_from_fine() below for the whole wrapper; this overload serves N_init == N_final.
-    void f_cycle(double *phi, const double *f, int N_init, double h_init)
+    // MultiGrid.hpp:28-55, same signature and ownership: `coarsest_output` is re-pointed at a fresh
+    // new double[N_coarsest^2] (the caller delete[]s it, MultiGridTestRunner.hpp:204) holding fine_input restricted
+    // by repeated full weighting.  The restrictions run on the device.
+    void compute_coarsest_grid(const double *fine_input, double *&coarsest_output, int N_fine, int N_coarsest)
     {
-        if (N_init != N_final)
-            throw Error(PMG_ERR_UNSUPPORTED, "f_cycle(coarse) : call f_cycle_from_fine(phi_fine, N_final)");
-        (void)f;
-        (void)h_init;
-        std::copy(phi, phi + (size_t)N_final * N_final, final_solution);
+        double *out = new double[(size_t)N_coarsest * N_coarsest];
+        try {
+            check(pmg_restrict_to_level(get(N_fine).get(), fine_input, PMG_MEM_HOST, N_coarsest, out, PMG_MEM_HOST));
+        } catch (...) {
+            delete[] out;
+            throw;
+        }
+        coarsest_output = out;
+    }
+
+    // MultiGrid.hpp:138-183, same signature: nested iteration from the N_init x N_init fields phi / f up to N_final
+    // (per level: 4 sweeps, prolongation into a zeroed finer grid, the analytic right-hand side, one V-cycle); the result
+    // is left in final_solution.  phi and f are not modified.  `h_init` is implied by N_init.
+    void f_cycle(double *phi, const double *f, int N_init, double /*h_init*/)
+    {
+        Solver &s = get(N_final);
+        check(pmg_f_cycle_from(s.get(), phi, f, N_init, PMG_MEM_HOST, nullptr));
+        s.get_solution(final_solution);
     }
     // The runner's F-cycle block (MultiGridTestRunner.hpp:192-205) in one call: restrict phi to N_coarse,
     // nested iteration up to N with the analytic RHS, result in phi and final_solution.
@@ -268,11 +295,11 @@ public:
 // ---- 3_part_parallel/Parallel_Mg.cu:3-102 --------------------------------------------------------------------
 class ParallelMultiGridSolver {
     int alpha;
-    std::map<int, Solver *> solvers_;
+    std::map<std::tuple<int, double, int>, Solver *> solvers_;  // (N, omega, prolong_mode): knobs re-read per call
 
     void run(pmg_cycle_kind kind, double *phi, double *f, int N)
     {
-        Solver *&s = solvers_[N];
+        Solver *&s = solvers_[std::make_tuple(N, omega, prolong_mode)];
         if (!s) {
             pmg_config c;
             pmg_config_default(&c, N);

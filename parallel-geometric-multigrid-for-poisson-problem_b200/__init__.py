@@ -51,8 +51,8 @@ class Config(ctypes.Structure):
 ABI_SYMBOLS = [
     "pmg_version", "pmg_last_error", "pmg_status_string", "pmg_config_default", "pmg_kernel_launches",
     "pmg_create", "pmg_destroy", "pmg_set_rhs", "pmg_set_guess", "pmg_get_solution", "pmg_zero_guess",
-    "pmg_set_rhs_sine", "pmg_residual_norm", "pmg_cycle", "pmg_solve", "pmg_last_device_ms", "pmg_stream",
-    "pmg_jacobi", "pmg_residual", "pmg_restrict_fw", "pmg_prolong_add", "pmg_norm2",
+    "pmg_set_rhs_sine", "pmg_residual_norm", "pmg_cycle", "pmg_restrict_to_level", "pmg_f_cycle_from", "pmg_solve", "pmg_last_device_ms", "pmg_stream",
+    "pmg_jacobi", "pmg_residual", "pmg_restrict_fw", "pmg_prolong_add", "pmg_norm2", "pmg_release_scratch",
     "pmg_device_alloc", "pmg_device_free", "pmg_host_alloc_pinned", "pmg_host_free_pinned", "pmg_memcpy",
     "pmg_device_synchronize", "pmg_device_count",
     "pmg_comm_unique_id", "pmg_comm_init", "pmg_comm_finalize", "pmg_partition_rows",

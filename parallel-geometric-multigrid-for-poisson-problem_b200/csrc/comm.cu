@@ -95,6 +95,15 @@ pmg_status nccl_fail(const char *what, ncclResult_t r)
         ncclResult_t r_ = (call);                       \
         if (r_ != 0) return nccl_fail(#call, r_);       \
     } while (0)
+// between GroupStart and GroupEnd: close the group before reporting, so the communicator is not left inside one
+#define PMG_NCCL_G(call)                                \
+    do {                                                \
+        ncclResult_t r_ = (call);                       \
+        if (r_ != 0) {                                  \
+            g_nccl.GroupEnd();                          \
+            return nccl_fail(#call, r_);                \
+        }                                               \
+    } while (0)
 
 }  // namespace
 
@@ -112,12 +121,12 @@ pmg_status comm_halo_exchange(double *p, int ny, int pitch, int depth, cudaStrea
     double *row0 = p - PADX;  // whole padded rows: keeps every transfer one contiguous block
     PMG_NCCL(g_nccl.GroupStart());
     if (g_rank > 0) {  // upper neighbour: send my rows [0, depth), receive my halo rows [-depth, 0)
-        PMG_NCCL(g_nccl.Send(row0, cnt, ncclFloat64, g_rank - 1, g_comm, st));
-        PMG_NCCL(g_nccl.Recv(row0 - (ptrdiff_t)depth * pitch, cnt, ncclFloat64, g_rank - 1, g_comm, st));
+        PMG_NCCL_G(g_nccl.Send(row0, cnt, ncclFloat64, g_rank - 1, g_comm, st));
+        PMG_NCCL_G(g_nccl.Recv(row0 - (ptrdiff_t)depth * pitch, cnt, ncclFloat64, g_rank - 1, g_comm, st));
     }
     if (g_rank < g_nranks - 1) {  // lower neighbour: send rows [ny-depth, ny), receive halo rows [ny, ny+depth)
-        PMG_NCCL(g_nccl.Send(row0 + (ptrdiff_t)(ny - depth) * pitch, cnt, ncclFloat64, g_rank + 1, g_comm, st));
-        PMG_NCCL(g_nccl.Recv(row0 + (ptrdiff_t)ny * pitch, cnt, ncclFloat64, g_rank + 1, g_comm, st));
+        PMG_NCCL_G(g_nccl.Send(row0 + (ptrdiff_t)(ny - depth) * pitch, cnt, ncclFloat64, g_rank + 1, g_comm, st));
+        PMG_NCCL_G(g_nccl.Recv(row0 + (ptrdiff_t)ny * pitch, cnt, ncclFloat64, g_rank + 1, g_comm, st));
     }
     PMG_NCCL(g_nccl.GroupEnd());
     return PMG_OK;
@@ -132,10 +141,10 @@ pmg_status comm_gather_rows(const double *slab, double *full, int pitch, const i
     PMG_NCCL(g_nccl.GroupStart());
     if (g_rank == 0) {
         for (int r = 1; r < g_nranks; ++r)
-            PMG_NCCL(g_nccl.Recv(full - PADX + (ptrdiff_t)y0s[r] * pitch, (size_t)(y1s[r] - y0s[r]) * pitch,
+            PMG_NCCL_G(g_nccl.Recv(full - PADX + (ptrdiff_t)y0s[r] * pitch, (size_t)(y1s[r] - y0s[r]) * pitch,
                                  ncclFloat64, r, g_comm, st));
     } else {
-        PMG_NCCL(g_nccl.Send(slab - PADX, (size_t)(y1s[g_rank] - y0s[g_rank]) * pitch, ncclFloat64, 0, g_comm, st));
+        PMG_NCCL_G(g_nccl.Send(slab - PADX, (size_t)(y1s[g_rank] - y0s[g_rank]) * pitch, ncclFloat64, 0, g_comm, st));
     }
     PMG_NCCL(g_nccl.GroupEnd());
     if (g_rank == 0) {  // rank 0's own slab: device-to-device copy of its rows
@@ -165,12 +174,12 @@ pmg_status comm_scatter_rows(const double *full, double *slab, int n_rows, int p
         for (int r = 1; r < g_nranks; ++r) {
             int a, b;
             range(r, a, b);
-            PMG_NCCL(g_nccl.Send(full - PADX + (ptrdiff_t)a * pitch, (size_t)(b - a) * pitch, ncclFloat64, r, g_comm, st));
+            PMG_NCCL_G(g_nccl.Send(full - PADX + (ptrdiff_t)a * pitch, (size_t)(b - a) * pitch, ncclFloat64, r, g_comm, st));
         }
     } else {
         int a, b;
         range(g_rank, a, b);
-        PMG_NCCL(g_nccl.Recv(slab - PADX + (ptrdiff_t)(a - y0s[g_rank]) * pitch, (size_t)(b - a) * pitch,
+        PMG_NCCL_G(g_nccl.Recv(slab - PADX + (ptrdiff_t)(a - y0s[g_rank]) * pitch, (size_t)(b - a) * pitch,
                              ncclFloat64, 0, g_comm, st));
     }
     PMG_NCCL(g_nccl.GroupEnd());
@@ -207,17 +216,20 @@ pmg_status comm_ipc_exchange(void *base, unsigned char *handles, cudaStream_t st
     bool have = (e == cudaSuccess);
     if (!have) cudaGetLastError();
     const size_t hb = sizeof(cudaIpcMemHandle_t);
-    unsigned char *d_mine = nullptr, *d_all = nullptr;
-    if (cudaMalloc((void **)&d_mine, hb) != cudaSuccess || cudaMalloc((void **)&d_all, hb * g_nranks) != cudaSuccess) {
-        g_last_error = "cudaMalloc failed";
+    // one allocation for both buffers; if even that fails this process cannot take part in the collective at all
+    // (the other ranks then see the NCCL error / abort of this one rather than a silent hang)
+    unsigned char *d_buf = nullptr;
+    if (cudaMalloc((void **)&d_buf, hb * (g_nranks + 1)) != cudaSuccess) {
+        cudaGetLastError();
+        g_last_error = "cudaMalloc failed (ipc handle exchange)";
         return PMG_ERR_ALLOC;
     }
+    unsigned char *d_mine = d_buf, *d_all = d_buf + hb;
     cudaMemcpyAsync(d_mine, &mine, hb, cudaMemcpyHostToDevice, st);
     ncclResult_t r = g_nccl.AllGather(d_mine, d_all, hb, ncclInt8, g_comm, st);
     cudaMemcpyAsync(handles, d_all, hb * g_nranks, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
-    cudaFree(d_mine);
-    cudaFree(d_all);
+    cudaFree(d_buf);
     if (r != 0) return nccl_fail("ncclAllGather(ipc handles)", r);
     if (e != cudaSuccess) {
         g_last_error = std::string("ipc handle exchange: ") + cudaGetErrorString(e);

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdlib>
 
+#define PMG_NEEDS_PEER_WAIT
 #include "pmg_internal.h"
 
 namespace pmg {
@@ -455,7 +456,7 @@ __global__ void k_halo_signal(int *up_flag, int *dn_flag, int epoch)
 __global__ void __launch_bounds__(256)
     k_halo_pull(double *__restrict__ mine, int ny, int pitch, int depth, const double *__restrict__ up_src,
                 const double *__restrict__ dn_src, const int *flag_from_up, const int *flag_from_dn, int epoch,
-                int *err)
+                int *err, int *abort)
 {
     const bool from_up = blockIdx.y == 0;
     const double *src = from_up ? up_src : dn_src;
@@ -464,7 +465,10 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) ok = wait_flag(from_up ? flag_from_up : flag_from_dn, epoch) ? 1 : 0;
     __syncthreads();
     if (!ok) {
-        if (threadIdx.x == 0) *err = 1;
+        if (threadIdx.x == 0) {
+            *err = 1;
+            if (abort != nullptr) *abort = 1;
+        }
         return;
     }
     // whole padded rows, 16 bytes per thread per step (row starts are 128-byte aligned)
@@ -492,7 +496,7 @@ constexpr int GATHER_ILP = 4;
 __global__ void __launch_bounds__(256)
     k_gather_pull(double *__restrict__ full, int pitch, int rows, const double *const *__restrict__ srcs,
                   const int *inbox, int my_rank, int epoch, int *err, int *const *slots, int n_ranks,
-                  const int *__restrict__ epoch_base)
+                  const int *__restrict__ epoch_base, int *abort)
 {
     const int r = blockIdx.y;
     if (epoch_base != nullptr) epoch += *epoch_base;
@@ -506,7 +510,10 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) ok = (r == my_rank) ? 1 : (wait_flag(inbox + r, epoch) ? 1 : 0);
     __syncthreads();
     if (!ok) {
-        if (threadIdx.x == 0) *err = 1;
+        if (threadIdx.x == 0) {
+            *err = 1;
+            if (abort != nullptr) *abort = 1;
+        }
         return;
     }
     // a remote load costs an NVLink round trip (~2-3 us): keep GATHER_ILP independent loads in flight per thread
@@ -592,8 +599,15 @@ void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pi
         return;
     }
     size_t smem = vcycle_small_smem(n0, n_coarse);
-    static bool once = (cudaFuncSetAttribute(k_vcycle_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
-    (void)once;
+    static unsigned long long smem_mask = 0;  // per-device attribute: once per device ordinal
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((smem_mask >> (dev & 63)) & 1ull)) {
+            cudaFuncSetAttribute(k_vcycle_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            smem_mask |= 1ull << (dev & 63);
+        }
+    }
     const int threads = n0 > 33 ? 1024 : (n0 > 17 ? 512 : 256);
     k_vcycle_small<<<1, threads, smem, st>>>(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps,
                                             prolong_mode == PMG_PROLONG_FULL ? 1 : 2, x_is_zero ? 1 : 0, gamma < 1 ? 1 : gamma, done);
@@ -647,13 +661,13 @@ void launch_halo_signal(int *up_flag, int *dn_flag, int epoch, cudaStream_t st)
 }
 
 void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *up_src, const double *dn_src,
-                      const int *flag_from_up, const int *flag_from_dn, int epoch, int *err, cudaStream_t st)
+                      const int *flag_from_up, const int *flag_from_dn, int epoch, int *err, cudaStream_t st, int *abort)
 {
     size_t n2 = (size_t)depth * pitch / 2;
     int bx = (int)((n2 + 255) / 256);
     if (bx > 64) bx = 64;
     if (bx < 1) bx = 1;
-    k_halo_pull<<<dim3(bx, 2), 256, 0, st>>>(mine, ny, pitch, depth, up_src, dn_src, flag_from_up, flag_from_dn, epoch, err);
+    k_halo_pull<<<dim3(bx, 2), 256, 0, st>>>(mine, ny, pitch, depth, up_src, dn_src, flag_from_up, flag_from_dn, epoch, err, abort);
     count_launch();
 }
 
@@ -675,7 +689,8 @@ void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, c
 }
 
 void launch_gather_pull(double *full, int pitch, int rows, const double *const *srcs, const int *inbox, int n_ranks,
-                        int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots, const int *epoch_base)
+                        int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots, const int *epoch_base,
+                        int *abort)
 {
     size_t n2 = (size_t)rows * pitch / 2;
     int bx = (int)((n2 + 256 * GATHER_ILP - 1) / (256 * GATHER_ILP));  // one trip per thread ...
@@ -684,9 +699,11 @@ void launch_gather_pull(double *full, int pitch, int rows, const double *const *
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     k_gather_pull<<<dim3(bx, n_ranks), 256, 0, st>>>(full, pitch, rows, srcs, inbox, my_rank, epoch, err, slots, n_ranks,
-                                                     epoch_base);
+                                                     epoch_base, abort);
     count_launch();
 }
+
+void basic_set_wait_timeout_ns(unsigned long long ns) { cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof(ns)); }
 
 void launch_residual_norm2_sequential(const double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f,
                                       double h, double *d_out, cudaStream_t st)

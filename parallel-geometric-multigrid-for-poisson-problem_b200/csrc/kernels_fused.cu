@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#define PMG_NEEDS_PEER_WAIT
 #include "pmg_internal.h"
 
 namespace pmg {
@@ -458,7 +459,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             }
             ok = __shfl_sync(0xffffffffu, ok, 0);
             if (!ok) {
-                if (lane == 0) *hp.err = 1;
+                if (lane == 0) {
+                    *hp.err = 1;
+                    if (hp.abort != nullptr) *hp.abort = 1;
+                }
                 return;
             }
         }
@@ -480,7 +484,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                 }
                 ok = __shfl_sync(0xffffffffu, ok, 0);
                 if (!ok) {
-                    if (lane == 0) *hp.err = 1;
+                    if (lane == 0) {
+                        *hp.err = 1;
+                        if (hp.abort != nullptr) *hp.abort = 1;
+                    }
                     return;
                 }
                 const ptrdiff_t up_off = (ptrdiff_t)col - (ptrdiff_t)PADY * g.pitch, dn_off = (ptrdiff_t)col + (ptrdiff_t)g.ny * g.pitch;
@@ -721,23 +728,25 @@ int deep_prefetch_below()
 // measured best per kernel flavour on B200 (tools/tune_fused.py): Pass A, Pass A from x == 0, Pass B, Pass B + norm
 int g_variant_down = 0, g_variant_down_zero = 3, g_variant_up = 1, g_variant_up_norm = 3;
 
+int g_fused_bad_nu = 0;  // last sweep count a launcher was asked for and could not serve (fused_take_bad_nu)
+
 int g_min_chunk_rows = 4;  // even; the pipeline warm-up (4..8 rows) is paid once per chunk
 
-int g_num_sms = 0;
+int g_num_sms[64] = {0};  // per device ordinal
 int num_sms()
 {
 #ifdef PMG_HOST_EMULATION
     return emu_num_sms;
-#endif
-#ifndef PMG_HOST_EMULATION
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+#else
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &v = g_num_sms[dev & 63];
+    if (v == 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
     }
+    return v;
 #endif
-    return g_num_sms;
 }
 
 StripGeom make_geom(const FusedLevel &lv, int stages, const VariantDesc &v, int ext_lo, int ext_hi)
@@ -790,6 +799,28 @@ void set_smem(K kernel, int bytes)
 #define PMG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel, device ordinal),
+// not once per process, so that a second solver on another GPU of the same process launches correctly
+inline int current_device()
+{
+#ifdef PMG_HOST_EMULATION
+    return 0;
+#else
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+#endif
+}
+#define PMG_SMEM_ONCE(k, sm)                         \
+    do {                                             \
+        static unsigned long long mask_ = 0;         \
+        const int d_ = current_device();             \
+        if (!((mask_ >> d_) & 1ull)) {               \
+            set_smem(k, sm);                         \
+            mask_ |= 1ull << d_;                     \
+        }                                            \
+    } while (0)
+
 template <int C, int PF, int MINB, bool SM, int S, bool WEIGHTED>
 void down_launch_w(const FusedLevel &lv, double *cf, int pitch_c, bool x_is_zero, bool resid, const StripGeom &g,
                    int nc, const JacobiCoef &c, double inv, dim3 grid, dim3 block, const int *done, cudaStream_t st)
@@ -800,32 +831,27 @@ void down_launch_w(const FusedLevel &lv, double *cf, int pitch_c, bool x_is_zero
     if (resid && x_is_zero && prologue) {
         auto k = k_down<C, PF, MINB, SM, S, true, true, WEIGHTED, CAN_PROLOGUE>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
-        static bool once = (set_smem(k, sm), true);
-        (void)once;
+        PMG_SMEM_ONCE(k, sm);
         PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
     } else if (resid && prologue) {
         auto k = k_down<C, PF, MINB, SM, S, false, true, WEIGHTED, CAN_PROLOGUE>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
-        static bool once = (set_smem(k, sm), true);
-        (void)once;
+        PMG_SMEM_ONCE(k, sm);
         PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
     } else if (resid && x_is_zero) {
         auto k = k_down<C, PF, MINB, SM, S, true, true, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
-        static bool once = (set_smem(k, sm), true);
-        (void)once;
+        PMG_SMEM_ONCE(k, sm);
         PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
     } else if (resid) {
         auto k = k_down<C, PF, MINB, SM, S, false, true, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
-        static bool once = (set_smem(k, sm), true);
-        (void)once;
+        PMG_SMEM_ONCE(k, sm);
         PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
     } else {
         auto k = k_down<C, PF, MINB, SM, S, false, false, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
-        static bool once = (set_smem(k, sm), true);
-        (void)once;
+        PMG_SMEM_ONCE(k, sm);
         PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, (double *)nullptr, g, 0, nc, c, inv, done, lv.hp);
     }
 }
@@ -853,8 +879,7 @@ void up_launch_k(const FusedLevel &lv, const double *e, int pitch_c, const Strip
 {
     auto k = k_up<C, PF, MINB, SM, S, PROLONG, NORM, WEIGHTED>;
     int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
-    static bool once = (set_smem(k, sm), true);
-    (void)once;
+    PMG_SMEM_ONCE(k, sm);
     PMG_LAUNCH(k, dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st, lv.xb, lv.x, lv.f, e, g, pitch_c, lo, c, inv, d_partials, done);
 }
 
@@ -893,6 +918,12 @@ void up_launch(const FusedLevel &lv, const double *e, int pitch_c, double omega,
 }  // namespace
 
 bool fused_supported(int nu) { return nu >= 1 && nu <= 4; }
+int fused_take_bad_nu()
+{
+    int v = g_fused_bad_nu;
+    g_fused_bad_nu = 0;
+    return v;
+}
 
 int fused_num_variants() { return NUM_VARIANTS; }
 void fused_set_variant(int v)
@@ -913,6 +944,14 @@ int fused_get_variant() { return g_variant_down | (g_variant_up << 8); }
 void fused_set_min_chunk_rows(int r) { g_min_chunk_rows = (r >= 2) ? (r + (r & 1)) : 2; }
 void fused_set_deep_prefetch_below(int n) { g_deep_prefetch_below = n; }
 void fused_set_halo_prologue(int on) { g_halo_prologue = on ? 1 : 0; }
+void fused_set_wait_timeout_ns(unsigned long long ns)
+{
+#ifndef PMG_HOST_EMULATION
+    cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof(ns));
+#else
+    (void)ns;
+#endif
+}
 int fused_halo_prologue() { return g_halo_prologue; }
 
 int fused_max_partials(int n)
@@ -945,6 +984,10 @@ void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int 
                        bool x_is_zero, cudaStream_t st, const int *done)
 {
     bool resid = coarse_f != nullptr;
+    if (!fused_supported(nu1)) {  // callers check fused_supported(); never skip a pass silently
+        g_fused_bad_nu = nu1;
+        return;
+    }
     switch (nu1) {
         case 1: down_launch<2, 3, 4, true, 1>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         case 2: PMG_DISPATCH_S2(lv.n <= deep_prefetch_below() ? 4 : ((x_is_zero && resid) ? g_variant_down_zero : g_variant_down), down_launch, lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
@@ -959,6 +1002,11 @@ void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, 
 {
     bool norm = d_partials != nullptr;
     int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
+    if (!fused_supported(nu2)) {
+        g_fused_bad_nu = nu2;
+        if (n_partials) *n_partials = 0;
+        return;
+    }
     switch (nu2) {
         case 1: up_launch<2, 3, 4, true, 1>(lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;
         case 2: PMG_DISPATCH_S2(lv.n <= deep_prefetch_below() ? 4 : (norm ? g_variant_up_norm : g_variant_up), up_launch, lv, coarse_x, pitch_c, omega, lo, norm, d_partials, n_partials, done, st); break;

@@ -287,10 +287,16 @@ void launch_vcycle_small_v2(double *x, const double *f, int n0, int pitch_x, int
                             int gamma, cudaStream_t st, const int *done)
 {
     const size_t smem = vs2_smem_bytes(n0, n_coarse);
-    static bool once = (cudaFuncSetAttribute(k_vcycle_small2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                        cudaFuncSetAttribute(k_vcycle_small2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                        true);
-    (void)once;
+    {  // per-device attribute: once per device ordinal, not once per process
+        static unsigned long long mask = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((mask >> (dev & 63)) & 1ull)) {
+            cudaFuncSetAttribute(k_vcycle_small2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_vcycle_small2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            mask |= 1ull << (dev & 63);
+        }
+    }
     int shift = 0, rows = 1;
     vs_grid(n0, 1024, shift, rows);
     int threads = (((1 << shift) * rows + 31) / 32) * 32;

@@ -168,19 +168,41 @@ struct HaloPeers {
     double *x_keep;                // local x (writable): where the halo prologue stores the neighbours' x rows
     const int *epoch_base;         // (nullable) device int added to `epoch`: a captured launch keeps its arguments, so
                                    // the host writes the visit's epoch to device memory before each graph replay
+    int *abort;                    // (nullable) the solve's device-side `done` flag: raised together with *err so that
+                                   // the finest level's last pass does not commit an iterate built on stale halo rows
 };
 
-#ifndef PMG_HOST_EMULATION
-// bounded acquire spin on a flag another GPU publishes with st.release.sys (~2 s, then give up)
+#if !defined(PMG_HOST_EMULATION) && defined(PMG_NEEDS_PEER_WAIT)
+// Bounded acquire spin on a flag another GPU publishes with st.release.sys.  The bound is WALL time on the device
+// (%globaltimer), 30 s unless PMG_P2P_TIMEOUT_S says otherwise (pmg_create): ordinary rank skew -- a rank doing host I/O
+// between cycles, first-use graph instantiation, lazy module load -- must never trip it; it exists so that a DEAD
+// neighbour turns into PMG_ERR_COMM instead of a hung GPU.  One copy of the limit per translation unit that waits on
+// peers (the library is built without relocatable device code); each TU exports a setter (…_set_wait_timeout_ns).
+static __device__ unsigned long long g_wait_timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ bool wait_flag(const int *flag, int epoch)
 {
-    for (int it = 0; it < 2000000; ++it) {
+    unsigned long long t0 = 0;
+    unsigned ns = 32;
+    for (unsigned it = 0;; ++it) {
         int v;
         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v >= epoch) return true;
-        __nanosleep(1000);
+        __nanosleep(ns);
+        if (ns < 1000) ns *= 2;  // short polls first (the usual wait is a few microseconds), then back off
+        if ((it & 255u) == 255u) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > g_wait_timeout_ns)
+                return false;
+        }
     }
-    return false;
 }
 #endif
 
@@ -199,6 +221,9 @@ struct FusedLevel {
 // Pass A (down): xb = S^nu1(x);  coarse_f(interior) = R(f - A xb).  x_is_zero: the iterate is known to
 // be identically zero on entry (coarse levels of a V-cycle) so x is not read.
 bool fused_supported(int nu);
+// a launcher called with an unsupported sweep count launches nothing and records the count; returns and clears it
+// (0 = none): the cycle drivers turn it into PMG_ERR_UNSUPPORTED instead of a silently skipped pass
+int fused_take_bad_nu();
 // `done` (nullable): device flag; when set the kernel returns at once (device-side convergence control)
 void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int nu1, double omega,
                        bool x_is_zero, cudaStream_t st, const int *done = nullptr);
@@ -218,10 +243,15 @@ void fused_set_min_chunk_rows(int r);
 constexpr int PMG_DEEP_PREFETCH_DEFAULT = 0;
 void fused_set_deep_prefetch_below(int n);
 // Pass A's fused halo exchange copies the neighbours' halo rows in a prologue (all loads in flight, only the
-// boundary warps wait for the flags) instead of streaming them in place.  Opt-in until validated on 4+ GPUs.
-constexpr int PMG_HALO_PROLOGUE_DEFAULT = 0;
+// boundary warps wait for the flags) instead of streaming them in place.  Default since round 2: bit-identical on
+// 2 and 8 GPUs and, together with the middle graph and no interior/boundary split, 657 -> 566 us per V-cycle at
+// N = 16385 on 8 GPUs (profiles/r2_dist8_latency_options.log).  PMG_HALO_PROLOGUE=0 restores in-place streaming.
+constexpr int PMG_HALO_PROLOGUE_DEFAULT = 1;
 void fused_set_halo_prologue(int on);
 int fused_halo_prologue();
+// limit of the peer-flag waits (wait_flag above), per translation unit that waits
+void fused_set_wait_timeout_ns(unsigned long long ns);
+void basic_set_wait_timeout_ns(unsigned long long ns);
 
 // ---- multi-GPU plumbing (comm.cu): no-ops returning PMG_OK while no communicator exists ---------------
 bool comm_ready();
@@ -251,7 +281,8 @@ void launch_halo_signal(int *up_flag, int *dn_flag, int epoch, cudaStream_t st);
 //   (its ny - depth), dn_src: peer pointer to the lower neighbour's row 0; flags: my inbox {from_up, from_dn};
 //   err: device int raised if the spin times out.
 void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *up_src, const double *dn_src,
-                      const int *flag_from_up, const int *flag_from_dn, int epoch, int *err, cudaStream_t st);
+                      const int *flag_from_up, const int *flag_from_dn, int epoch, int *err, cudaStream_t st,
+                      int *abort = nullptr);
 // All-gather of a slab-partitioned level over NVLink: `slots[r]` = rank r's inbox slot for THIS rank (peer
 // pointers, device array); every rank publishes `epoch` there, then pulls the other ranks' `rows` slab rows
 // (`srcs[r]` = peer pointer to rank r's padded row 0, device array; srcs[my_rank] is local) into `full`.
@@ -260,7 +291,7 @@ void launch_signal_all(int *const *slots, int n_ranks, int my_rank, int epoch, c
 // epoch_base (nullable): device int added to `epoch` (graph replay, see HaloPeers)
 void launch_gather_pull(double *full, int pitch, int rows, const double *const *srcs, const int *inbox, int n_ranks,
                         int my_rank, int epoch, int *err, cudaStream_t st, int *const *slots = nullptr,
-                        const int *epoch_base = nullptr);
+                        const int *epoch_base = nullptr, int *abort = nullptr);
 // dst[i] = vals[i], i < count <= 16 (the epochs of one cycle, written ahead of a graph replay)
 struct IntPack16 {
     int v[16];

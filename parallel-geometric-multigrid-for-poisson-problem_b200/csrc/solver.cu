@@ -122,7 +122,9 @@ struct pmg_solver {
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_passb = nullptr, ev_norm = nullptr;
     bool norm_pending = false;               // an ev_norm has been recorded that the next Pass B(0) must wait for
     bool coarse_redundant = false;           // every rank solves the agglomerated levels (all-gather, no scatter)
-    int split_min_rows = 2048;               // slabs at least this tall overlap the exchange with interior rows
+    int split_min_rows = 2048;               // slabs at least this tall overlap the exchange with interior rows (only
+                                             // without the halo prologue, which makes the split unnecessary)
+    bool split_from_env = false;
     bool p2p = false;                        // halo rows are pulled from the neighbours' memory over NVLink
     bool p2p_fused = true;                   // ... by Pass A itself (no pull kernel, no local copy of the x halo)
     int *d_flags = nullptr;                  // my inbox: [level][from_up, from_dn] epochs published by neighbours
@@ -135,6 +137,7 @@ struct pmg_solver {
     std::vector<void *> agg_maps;            // IPC mappings to close
     int agg_epoch = 0;
     bool p2p_gather = false, cycle_has_collective = false;
+    bool p2p_gather_w = true;                // W-cycles use the NVLink all-gather too (see cycle_dist)
     // the redundant solve of the agglomerated levels (fixed pointers, no communication) replayed as a CUDA graph
     cudaGraphExec_t coarse_graph[2] = {nullptr, nullptr};  // [V, W]
     int coarse_graph_kernels[2] = {0, 0};
@@ -143,11 +146,11 @@ struct pmg_solver {
     // coarse solve and Pass B back up: ~16 launches on one stream, no host-visible events -- replayed as ONE CUDA graph
     // per all-gather buffer parity.  A captured launch keeps its arguments, so the epochs of the visit are written to
     // `d_epochs` ([l] = halo epoch of slab level l, [15] = all-gather epoch) by a tiny kernel ahead of each replay and
-    // the kernels add them in (HaloPeers::epoch_base).  Opt-in (PMG_MID_GRAPH=1) until measured on GPUs.
+    // the kernels add them in (HaloPeers::epoch_base).  Default since round 2 (PMG_MID_GRAPH=0 switches it off).
     int *d_epochs = nullptr;
     cudaGraphExec_t mid_graph[2] = {nullptr, nullptr};
     int mid_graph_kernels[2] = {0, 0};
-    bool mid_graph_on = false;
+    bool mid_graph_on = true;
     bool capturing_mid = false;
 };
 
@@ -380,15 +383,27 @@ static pmg_status run_mid_graph(pmg_solver *s, int lg)
         s->capturing_mid = false;
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamEndCapture(s->stream, &g);
-        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaStreamEndCapture (middle graph): ") + cudaGetErrorString(e));
+        // nothing ran: take back the epochs this visit had claimed, or the next visit would wait for one too many
+        auto roll_back = [&]() {
+            for (int l = lg; l < s->agg_level; ++l) --s->lv[l].halo_epoch;
+            --s->agg_epoch;
+        };
+        if (e != cudaSuccess) {
+            roll_back();
+            return fail(PMG_ERR_CUDA, std::string("cudaStreamEndCapture (middle graph): ") + cudaGetErrorString(e));
+        }
         if (rc != PMG_OK) {
             cudaGraphDestroy(g);
+            roll_back();
             return rc;
         }
         gk = (int)(launches_so_far() - before);
         e = cudaGraphInstantiate(&ge, g, 0);
         cudaGraphDestroy(g);
-        if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaGraphInstantiate (middle graph): ") + cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            roll_back();
+            return fail(PMG_ERR_CUDA, std::string("cudaGraphInstantiate (middle graph): ") + cudaGetErrorString(e));
+        }
         PMG_CUDA(cudaGraphLaunch(ge, s->stream));
         return PMG_OK;
     }
@@ -407,9 +422,13 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     const bool up_nb = s->rank > 0, dn_nb = s->rank < s->n_ranks - 1;
     pmg_status rc;
     trace_mark(s, "begin", l);
-    // NVLink all-gather of the agglomerated level (V form, one collective per cycle keeps the two buffers safe)
+    // NVLink all-gather of the agglomerated level into the double-buffered slab.  Two buffers are enough for ANY
+    // number of gathers per cycle (W form: gamma^l of them): gather k+2 re-uses the buffer of gather k, and a rank
+    // re-writes that buffer (Pass A of the last slab level) only after ITS gather k+1 returned, i.e. after every
+    // rank published epoch k+1, which each rank does from its gather-(k+1) launch -- stream-ordered after its
+    // gather-k launch finished reading.  PMG_P2P_GATHER_W=0 sends W-cycles back to the NCCL all-gather.
     const bool pull_gather = last_slab && s->p2p_gather && s->coarse_redundant && s->cycle_has_collective &&
-                             (!w_form || c.gamma == 1);
+                             (!w_form || c.gamma == 1 || s->p2p_gather_w);
     if (pull_gather) {
         if (!s->capturing_mid) ++s->agg_epoch;  // (run_mid_graph advanced it before the capture / replay)
         s->aslab.f = s->agg_f[s->agg_epoch & 1] + level_origin(s->aslab.n);
@@ -462,10 +481,11 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             hp.epoch = epoch;
             hp.epoch_base = s->capturing_mid ? s->d_epochs + l : nullptr;
             hp.err = s->d_comm_err;
+            hp.abort = &s->d_ctrl->done;  // a timed-out wait also stops Pass B(0) from committing (see below)
         } else if (s->p2p) {  // separate pull kernel: neighbours' rows are copied into the local halo rows
             const bool is_x = (halo_field == L.x);
             launch_halo_pull(halo_field, L.ny, L.pitch, PADY, is_x ? L.up_x : L.up_f, is_x ? L.dn_x : L.dn_f,
-                             s->d_flags + 2 * l, s->d_flags + 2 * l + 1, epoch, s->d_comm_err, xs);
+                             s->d_flags + 2 * l, s->d_flags + 2 * l + 1, epoch, s->d_comm_err, xs, &s->d_ctrl->done);
         } else if ((rc = comm_halo_exchange(halo_field, L.ny, L.pitch, PADY, xs)) != PMG_OK) {
             return rc;
         }
@@ -519,7 +539,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
                 // publishes "my slab is final" to every rank, then pulls theirs (one launch)
                 launch_gather_pull(A.f, A.pitch, y1[0] - y0[0], s->d_agg_srcs[s->agg_epoch & 1], s->d_flags + 32,
                                    s->n_ranks, s->rank, s->capturing_mid ? 0 : s->agg_epoch, s->d_comm_err, s->stream,
-                                   s->d_agg_slots, s->capturing_mid ? s->d_epochs + 15 : nullptr);
+                                   s->d_agg_slots, s->capturing_mid ? s->d_epochs + 15 : nullptr, &s->d_ctrl->done);
             } else if ((rc = comm_allgather_rows(K.f, A.f, y1[0] - y0[0], A.pitch, s->stream)) != PMG_OK) {
                 return rc;
             }
@@ -559,8 +579,11 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
             const Level &A = s->lv[s->agg_level];
             coarse_x = A.x + (ptrdiff_t)s->y0s[s->agg_level][s->rank] * A.pitch;
         }
+        // with peer-memory exchanges the finest level's last pass ALWAYS looks at the control block's flag: a wait
+        // that timed out raises it (HaloPeers::abort), so an iterate built on stale halo rows is never committed
+        const int *guard = done ? done : (s->p2p ? &s->d_ctrl->done : nullptr);
         launch_fused_up(v, coarse_x, K.pitch, c.nu2, c.omega, c.prolong_mode, want_norm ? s->d_partials : nullptr,
-                        n_partials, s->stream, l == 0 ? done : nullptr);
+                        n_partials, s->stream, l == 0 ? guard : nullptr);
     }
     trace_mark(s, "passB", l);
     return PMG_OK;
@@ -631,28 +654,15 @@ static void analytic_rhs(pmg_solver *s, const Level &L, double *f)
     launch_rhs_separable(f, L.pitch, L.n, L.n, factor, L.d_sin, L.d_sin, s->stream);
 }
 
-// The runner's F-cycle wrapper (MultiGridTestRunner.hpp:192-205) + MultigridSolver::f_cycle
-// (MultiGrid.hpp:138-183) + compute_coarsest_grid (:28-55).
-static pmg_status cycle_f(pmg_solver *s)
+// MultigridSolver::f_cycle (MultiGrid.hpp:138-183): nested iteration from level l_init -- whose x / f arrays hold the
+// starting iterate and right-hand side -- up to the finest level, with the ANALYTIC right-hand side on every finer
+// level (:162); the result is the finest level's iterate.
+static pmg_status fmg_up_from(pmg_solver *s, int l_init)
 {
-    pmg_status rc = ensure_fmg(s);
-    if (rc != PMG_OK) return rc;
     const pmg_config &c = s->cfg;
-    const int nl = (int)s->lv.size();
-    int lc = nl - 1;  // index of the coarsest level (n == n_coarse, or the 3x3 grid)
-    if (lc == 0) return PMG_OK;  // N <= N_coarse: f_cycle's while loop never runs (MultiGrid.hpp:150)
-    drop_graphs(s);              // the pass below may swap x/xb roles on levels >= 1
-    // (1) phi restricted down to the coarsest grid; the scratch of level l is its xb array (ring == 0)
-    for (int l = 0; l < lc; ++l) {
-        const Level &L = s->lv[l];
-        Level &K = s->lv[l + 1];
-        launch_restrict(l == 0 ? L.x : L.xb, K.xb, L.n, K.n, L.pitch, K.pitch, s->stream);
-    }
-    if (lc > 0) launch_copy2d(s->lv[lc].x, s->lv[lc].pitch, s->lv[lc].xb, s->lv[lc].pitch, s->lv[lc].n, s->lv[lc].n, s->stream);
-    // (2) nested iteration upwards with the ANALYTIC right-hand side on every level (MultiGrid.hpp:162)
+    pmg_status rc = PMG_OK;
     double *user_f = s->lv[0].f;
-    analytic_rhs(s, s->lv[lc], s->lv[lc].f);  // MultiGridTestRunner.hpp:142
-    for (int l = lc - 1; l >= 0; --l) {
+    for (int l = l_init - 1; l >= 0; --l) {
         Level &K = s->lv[l + 1];
         Level &L = s->lv[l];
         // smoother->smooth(phi_current, f_current, N, N, h, 3)  (:153)
@@ -675,6 +685,35 @@ static pmg_status cycle_f(pmg_solver *s)
     }
     s->lv[0].f = user_f;
     return rc;
+}
+
+// MultigridSolver::compute_coarsest_grid (MultiGrid.hpp:28-55): repeated full weighting from level 0 down to level
+// l_out.  Level 0's input is `src0`; the scratch of every coarser level is its xb array (ring == 0).
+static void restrict_chain(pmg_solver *s, const double *src0, int l_out)
+{
+    for (int l = 0; l < l_out; ++l) {
+        const Level &L = s->lv[l];
+        Level &K = s->lv[l + 1];
+        launch_restrict(l == 0 ? src0 : L.xb, K.xb, L.n, K.n, L.pitch, K.pitch, s->stream);
+    }
+}
+
+// The runner's F-cycle wrapper (MultiGridTestRunner.hpp:192-205) = compute_coarsest_grid + f_cycle from the
+// coarsest level with the analytic coarse right-hand side (:142).
+static pmg_status cycle_f(pmg_solver *s)
+{
+    pmg_status rc = ensure_fmg(s);
+    if (rc != PMG_OK) return rc;
+    const int nl = (int)s->lv.size();
+    int lc = nl - 1;  // index of the coarsest level (n == n_coarse, or the 3x3 grid)
+    if (lc == 0) return PMG_OK;  // N <= N_coarse: f_cycle's while loop never runs (MultiGrid.hpp:150)
+    drop_graphs(s);              // the pass below may swap x/xb roles on levels >= 1
+    // (1) phi restricted down to the coarsest grid
+    restrict_chain(s, s->lv[0].x, lc);
+    launch_copy2d(s->lv[lc].x, s->lv[lc].pitch, s->lv[lc].xb, s->lv[lc].pitch, s->lv[lc].n, s->lv[lc].n, s->stream);
+    // (2) nested iteration upwards
+    analytic_rhs(s, s->lv[lc], s->lv[lc].f);  // MultiGridTestRunner.hpp:142
+    return fmg_up_from(s, lc);
 }
 
 // PMG_CYCLE_FMG: one full-multigrid pass for an arbitrary right-hand side and Dirichlet ring (pmg.h; not a
@@ -885,7 +924,17 @@ static pmg_status run_fused_graph(pmg_solver *s, bool w, int mode)
     return rc;
 }
 
+static pmg_status run_cycle_inner(pmg_solver *s, pmg_cycle_kind kind, bool want_norm);
+
 static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
+{
+    pmg_status rc = run_cycle_inner(s, kind, want_norm);
+    if (const int bad = fused_take_bad_nu())  // a fused launcher was asked for a sweep count it has no instantiation of
+        return fail(PMG_ERR_UNSUPPORTED, "fused engine: no kernel for " + std::to_string(bad) + " sweeps per pass");
+    return rc;
+}
+
+static pmg_status run_cycle_inner(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
 {
     pmg_status rc;
     if (kind == PMG_CYCLE_FMG) {
@@ -902,7 +951,7 @@ static pmg_status run_cycle(pmg_solver *s, pmg_cycle_kind kind, bool want_norm)
     if (kind != PMG_CYCLE_V && kind != PMG_CYCLE_W) return fail(PMG_ERR_INVALID, "unknown cycle kind");
     bool w = (kind == PMG_CYCLE_W);
     if (s->fused && want_norm && s->cfg.norm_mode == PMG_NORM_SEQUENTIAL) {
-        rc = run_cycle(s, kind, false);
+        rc = run_cycle_inner(s, kind, false);
         if (rc == PMG_OK) rc = residual_norm2_async(s);
         return rc;
     }
@@ -1090,11 +1139,22 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         equal = equal && (s->y1s[la][cfg->n_ranks - 1] - s->y0s[la][cfg->n_ranks - 1] == s->y1s[la][0] - s->y0s[la][0] + 1);
         const char *env = getenv("PMG_COARSE_GATHER");
         s->coarse_redundant = equal && !(env && env[0] == '1');
-        if (const char *e2 = getenv("PMG_SPLIT_MIN_ROWS")) s->split_min_rows = atoi(e2);
+        if (const char *e2 = getenv("PMG_SPLIT_MIN_ROWS")) {
+            s->split_min_rows = atoi(e2);
+            s->split_from_env = true;
+        }
         if (const char *e3 = getenv("PMG_P2P_FUSED")) s->p2p_fused = !(e3[0] == '0');
         if (const char *e4 = getenv("PMG_COARSE_GRAPH")) s->coarse_graph_on = !(e4[0] == '0');
         if (const char *e5 = getenv("PMG_HALO_PROLOGUE")) fused_set_halo_prologue(e5[0] == '1');
         if (const char *e6 = getenv("PMG_MID_GRAPH")) s->mid_graph_on = (e6[0] == '1');
+        {  // wall-time limit of a peer-flag wait (pmg_internal.h: wait_flag); generous by default, see ADVICE r1
+            double secs = 30.0;
+            if (const char *e7 = getenv("PMG_P2P_TIMEOUT_S")) secs = atof(e7);
+            if (!(secs > 0.0)) secs = 30.0;
+            const unsigned long long ns = (unsigned long long)(secs * 1e9);
+            fused_set_wait_timeout_ns(ns);
+            basic_set_wait_timeout_ns(ns);
+        }
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
@@ -1208,7 +1268,12 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
             } else {
                 const char *eg = getenv("PMG_P2P_GATHER");
                 s->p2p_gather = want_gather && !(eg && eg[0] == '0');
+                if (const char *ew = getenv("PMG_P2P_GATHER_W")) s->p2p_gather_w = !(ew[0] == '0');
                 s->p2p = true;
+                // With the halo prologue only the boundary warps of Pass A wait for the neighbours and the interior warps
+                // start at once, i.e. the overlap happens INSIDE one launch: the interior / boundary split (three launches
+                // on two streams joined by events) only adds latency.  Measured on 8 GPUs: 623 -> 566 us per cycle.
+                if (!s->split_from_env && s->p2p_fused && fused_halo_prologue()) s->split_min_rows = 1 << 30;
             }
         }
     }
@@ -1349,9 +1414,10 @@ pmg_status pmg_residual_norm(pmg_solver *s, double *norm_out)
 {
     if (!s || !norm_out) return fail(PMG_ERR_INVALID, "null argument");
     PMG_CUDA(cudaSetDevice(s->device));
-    residual_norm2_async(s);
+    pmg_status rc = residual_norm2_async(s);
+    if (rc != PMG_OK) return rc;
     double v = 0.0;
-    pmg_status rc = read_scalar(s, &v);
+    rc = read_scalar(s, &v);
     if (rc != PMG_OK) return rc;
     *norm_out = std::sqrt(v);
     return PMG_OK;
@@ -1363,7 +1429,10 @@ static pmg_status check_comm_err(pmg_solver *s)
     if (!s->p2p) return PMG_OK;
     int err = 0;
     PMG_CUDA(cudaMemcpy(&err, s->d_comm_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err) return fail(PMG_ERR_COMM, "peer-to-peer halo exchange timed out waiting for a neighbour");
+    // sticky on purpose: after a timeout the ranks' epochs no longer agree, so this solver (and its peers') must be
+    // destroyed and re-created; every later call reports the same error (pmg.h, multi-GPU section)
+    if (err) return fail(PMG_ERR_COMM, "peer-to-peer halo exchange timed out waiting for a neighbour (PMG_P2P_TIMEOUT_S); "
+                                       "the solver is unusable, destroy it on every rank");
     return PMG_OK;
 }
 
@@ -1371,6 +1440,8 @@ pmg_status pmg_cycle(pmg_solver *s, pmg_cycle_kind kind, double *res_norm_out)
 {
     if (!s) return fail(PMG_ERR_INVALID, "null argument");
     PMG_CUDA(cudaSetDevice(s->device));
+    if (s->p2p)  // Pass B(0) honours the control block's flag (timed-out peer wait); a finished pmg_solve left it raised
+        PMG_CUDA(cudaMemsetAsync(&s->d_ctrl->done, 0, sizeof(int), s->stream));
     PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
     pmg_status rc = run_cycle(s, kind, res_norm_out != nullptr);
     if (rc != PMG_OK) return rc;
@@ -1388,6 +1459,74 @@ pmg_status pmg_cycle(pmg_solver *s, pmg_cycle_kind kind, double *res_norm_out)
     PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->last_ms = ms;
     return check_comm_err(s);
+}
+
+static int level_of_size(const pmg_solver *s, int n)
+{
+    for (size_t l = 0; l < s->lv.size(); ++l)
+        if (s->lv[l].n == n) return (int)l;
+    return -1;
+}
+
+pmg_status pmg_restrict_to_level(pmg_solver *s, const double *fine, pmg_mem where_in, int n_out, double *out,
+                                 pmg_mem where_out)
+{
+    if (!s || !fine || !out) return fail(PMG_ERR_INVALID, "null argument");
+    if (s->dist) return fail(PMG_ERR_UNSUPPORTED, "pmg_restrict_to_level is single-GPU only");
+    const int lo = level_of_size(s, n_out);
+    if (lo < 0) return fail(PMG_ERR_INVALID, "n_out is not a level of this solver's hierarchy");
+    PMG_CUDA(cudaSetDevice(s->device));
+    Level &L0 = s->lv[0];
+    const cudaMemcpyKind kin = where_in == PMG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind kout = where_out == PMG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    // stage the input in the finest level's ping-pong partner (scratch: every pass re-writes it before reading it)
+    PMG_CUDA(cudaMemcpy2DAsync(L0.xb, (size_t)L0.pitch * sizeof(double), fine, (size_t)L0.n * sizeof(double),
+                               (size_t)L0.n * sizeof(double), (size_t)L0.n, kin, s->stream));
+    restrict_chain(s, L0.xb, lo);
+    const Level &K = s->lv[lo];
+    PMG_CUDA(cudaMemcpy2DAsync(out, (size_t)K.n * sizeof(double), K.xb, (size_t)K.pitch * sizeof(double),
+                               (size_t)K.n * sizeof(double), (size_t)K.n, kout, s->stream));
+    PMG_CUDA(cudaStreamSynchronize(s->stream));
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+pmg_status pmg_f_cycle_from(pmg_solver *s, const double *phi_init, const double *f_init, int n_init, pmg_mem where,
+                            double *res_norm_out)
+{
+    if (!s || !phi_init || !f_init) return fail(PMG_ERR_INVALID, "null argument");
+    if (s->dist) return fail(PMG_ERR_UNSUPPORTED, "pmg_f_cycle_from is single-GPU only (pmg_cycle(PMG_CYCLE_F) shards)");
+    const int li = level_of_size(s, n_init);
+    if (li < 0) return fail(PMG_ERR_INVALID, "n_init is not a level of this solver's hierarchy");
+    PMG_CUDA(cudaSetDevice(s->device));
+    pmg_status rc = ensure_fmg(s);
+    if (rc != PMG_OK) return rc;
+    drop_graphs(s);  // the smoothing below may swap x / xb roles on levels >= 1
+    Level &L = s->lv[li];
+    const cudaMemcpyKind k = where == PMG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    PMG_CUDA(cudaMemcpy2DAsync(L.x, (size_t)L.pitch * sizeof(double), phi_init, (size_t)L.n * sizeof(double),
+                               (size_t)L.n * sizeof(double), (size_t)L.n, k, s->stream));
+    if (li > 0)  // on the finest level the loop body never runs and f is not used (MultiGrid.hpp:150)
+        PMG_CUDA(cudaMemcpy2DAsync(L.f, (size_t)L.pitch * sizeof(double), f_init, (size_t)L.n * sizeof(double),
+                                   (size_t)L.n * sizeof(double), (size_t)L.n, k, s->stream));
+    if ((rc = fmg_up_from(s, li)) != PMG_OK) return rc;
+    if (const int bad = fused_take_bad_nu())
+        return fail(PMG_ERR_UNSUPPORTED, "fused engine: no kernel for " + std::to_string(bad) + " sweeps per pass");
+    if (res_norm_out && (rc = residual_norm2_async(s)) != PMG_OK) return rc;
+    PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    if (res_norm_out) {
+        double v = 0.0;
+        if ((rc = read_scalar(s, &v)) != PMG_OK) return rc;
+        *res_norm_out = std::sqrt(v);
+    } else {
+        PMG_CUDA(cudaStreamSynchronize(s->stream));
+        PMG_CUDA(cudaGetLastError());
+    }
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    return PMG_OK;
 }
 
 /* Fused V/W solve with device-side convergence control: cycles are queued one batch ahead of the host's
@@ -1485,10 +1624,12 @@ static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol,
     if (s->fused && (kind == PMG_CYCLE_V || kind == PMG_CYCLE_W) && s->cfg.norm_mode == PMG_NORM_TREE &&
         s->lv.size() > 1 && s->lv[0].n > s->cfg.n_coarse && (s->dist || fused_graph_ok(s)))
         return solve_fused_async(s, kind == PMG_CYCLE_W, rel_tol, max_cycles, res_history, n_cycles_out);
+    if (s->p2p) PMG_CUDA(cudaMemsetAsync(&s->d_ctrl->done, 0, sizeof(int), s->stream));  // see pmg_cycle
     PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
-    residual_norm2_async(s);
+    pmg_status rc = residual_norm2_async(s);
+    if (rc != PMG_OK) return rc;
     double v = 0.0;
-    pmg_status rc = read_scalar(s, &v);
+    rc = read_scalar(s, &v);
     if (rc != PMG_OK) return rc;
     double r0 = std::sqrt(v);
     if (res_history) res_history[0] = r0;
@@ -1715,19 +1856,35 @@ pmg_status pmg_test_fused_up(const pmg_test_slab *t, const double *coarse_x, int
 int pmg_test_fused_max_partials(int n) { return fused_max_partials(n); }
 
 /* ---- operator level (dense reference layout, device pointers) ------------------------------------------ */
+// Scratch of the operator-level calls, one set PER DEVICE ordinal: reduction partials and the padded buffers of the
+// blocked smoother.  The calls are synchronous, and they hold g_scratch_mu from launch to completion, so concurrent
+// callers (any streams) never share a live scratch.  pmg_release_scratch() frees everything.
 static std::mutex g_scratch_mu;
-static double *g_scratch_partials = nullptr;  // reduce_partials() + 1 doubles, per process
+struct OpScratch {
+    double *partials = nullptr;  // reduce_partials() + 2 doubles
+    int jac_n = 0;
+    double *jac[3] = {nullptr, nullptr, nullptr};
+};
+static OpScratch g_scratch[64];
 
+static OpScratch &scratch_of_current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_scratch[dev & 63];
+}
+
+// caller holds g_scratch_mu
 static pmg_status op_scratch(double **partials)
 {
-    std::lock_guard<std::mutex> lk(g_scratch_mu);
-    if (!g_scratch_partials) {
-        if (cudaMalloc((void **)&g_scratch_partials, (reduce_partials() + 2) * sizeof(double)) != cudaSuccess) {
+    OpScratch &sc = scratch_of_current_device();
+    if (!sc.partials) {
+        if (cudaMalloc((void **)&sc.partials, (reduce_partials() + 2) * sizeof(double)) != cudaSuccess) {
             cudaGetLastError();
             return fail(PMG_ERR_ALLOC, "cudaMalloc failed");
         }
     }
-    *partials = g_scratch_partials;
+    *partials = sc.partials;
     return PMG_OK;
 }
 
@@ -1742,22 +1899,27 @@ static pmg_status require_device()
  * the padded layout once, smoothed 4 sweeps per HBM pass, and copied back -- bit-identical to sweep-by-sweep. */
 static pmg_status jacobi_blocked(double *x, const double *f, int n, double h, double omega, int sweeps, cudaStream_t st)
 {
-    static std::mutex mu;
-    static int cached_n = 0;
-    static double *buf[3] = {nullptr, nullptr, nullptr};
-    std::lock_guard<std::mutex> lk(mu);
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    OpScratch &sc = scratch_of_current_device();
+    double *(&buf)[3] = sc.jac;
     const size_t elems = level_elems(n), o = level_origin(n);
-    if (cached_n != n) {
+    if (sc.jac_n != n) {  // one size cached per device (the benchmark sweeps over sizes); pmg_release_scratch frees it
         for (double *&b : buf) {
             cudaFree(b);
             b = nullptr;
         }
-        cached_n = 0;
+        sc.jac_n = 0;
         for (double *&b : buf) {
             pmg_status rc = alloc_zero(&b, elems);
-            if (rc != PMG_OK) return rc;
+            if (rc != PMG_OK) {
+                for (double *&c : buf) {
+                    cudaFree(c);
+                    c = nullptr;
+                }
+                return rc;
+            }
         }
-        cached_n = n;
+        sc.jac_n = n;
     }
     const int pitch = level_pitch(n);
     FusedLevel v{};
@@ -1818,7 +1980,9 @@ pmg_status pmg_residual(double *r, const double *x, const double *f, int width, 
     if (rc != PMG_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (r) launch_residual(r, x, f, width, height, width, width, width, h, st);
+    std::unique_lock<std::mutex> lk(g_scratch_mu, std::defer_lock);
     if (norm2_out) {
+        lk.lock();  // held until the result has been read back (below)
         double *part = nullptr;
         if ((rc = op_scratch(&part)) != PMG_OK) return rc;
         launch_residual_norm2(x, f, width, height, width, width, h, part, part + reduce_partials(), st);
@@ -1860,12 +2024,36 @@ pmg_status pmg_norm2(const double *v, size_t l, double *norm2_out, void *stream)
     pmg_status rc = require_device();
     if (rc != PMG_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
     double *part = nullptr;
     if ((rc = op_scratch(&part)) != PMG_OK) return rc;
     launch_norm2(v, l, part, part + reduce_partials(), st);
     PMG_CUDA(cudaMemcpyAsync(norm2_out, part + reduce_partials(), sizeof(double), cudaMemcpyDeviceToHost, st));
     PMG_CUDA(cudaStreamSynchronize(st));
     PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+/* frees the per-device scratch the operator-level calls keep between calls (reduction partials, the padded buffers of
+ * the blocked smoother behind pmg_jacobi); safe at any time, the next call re-allocates */
+pmg_status pmg_release_scratch(void)
+{
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    int ndev = pmg_device_count(), cur = 0;
+    if (ndev <= 0) return PMG_OK;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < ndev && d < 64; ++d) {
+        OpScratch &sc = g_scratch[d];
+        if (!sc.partials && !sc.jac[0]) continue;
+        cudaSetDevice(d);
+        cudaFree(sc.partials);
+        for (double *&b : sc.jac) {
+            cudaFree(b);
+            b = nullptr;
+        }
+        sc = OpScratch();
+    }
+    cudaSetDevice(cur);
     return PMG_OK;
 }
 

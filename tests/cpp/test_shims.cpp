@@ -49,6 +49,45 @@ static void run_cycle(const char *name, int n, CycleFunction fn, bool fcycle)
                 norm(err) / norm(u));
 }
 
+// The F-cycle block of MultigridTestRunner::run_cycle, statement for statement (MultiGridTestRunner.hpp:138-146,
+// 192-205): coarse right-hand side and zero iterate on the N_coarse grid, compute_coarsest_grid, f_cycle through the
+// member-function pointer, final_solution copied back.
+static void run_f_cycle_like_the_runner(int n)
+{
+    std::vector<double> phi((size_t)n * n, 0.0), phi_tmp(phi.size()), f(phi.size()), u(phi.size()), err(phi.size());
+    rhs(f, u, n);
+    JacobiSmoother smoother(1e-7);
+    MultigridSolver mg(&smoother, 3, n);
+    int n_coarse = mg.N_coarse;
+    int l_coarse = n_coarse * n_coarse;
+    double h_coarse = 1.0 / (n_coarse - 1);
+    std::vector<double> f_coarse(l_coarse), u_coarse(l_coarse);
+    rhs(f_coarse, u_coarse, n_coarse);
+    CycleFunction cycle_func = &MultigridSolver::f_cycle;
+    {
+        double *phi_coarse = new double[l_coarse];
+        std::fill(phi_coarse, phi_coarse + l_coarse, 0.0);
+        std::copy(phi.begin(), phi.end(), phi_tmp.begin());
+        double *before = phi_coarse;
+        mg.compute_coarsest_grid(phi_tmp.data(), phi_coarse, n, mg.N_coarse);
+        (mg.*cycle_func)(phi_coarse, f_coarse.data(), n_coarse, h_coarse);
+        std::copy(mg.final_solution, mg.final_solution + phi.size(), phi.begin());
+        delete[] phi_coarse;
+        delete[] before;  // (the reference leaks this one)
+    }
+    for (size_t i = 0; i < phi.size(); ++i) err[i] = phi[i] - u[i];
+    std::printf("{\"test\": \"mg_cpu_exec\", \"cycle\": \"F_runner_shape\", \"n\": %d, \"rel_l2_error\": %.17g}\n", n,
+                norm(err) / norm(u));
+    // per-call knobs: a changed public field must take effect on the next call (not a stale cached hierarchy)
+    std::vector<double> a((size_t)n * n, 0.0), b(a.size(), 0.0);
+    mg.v_cycle(a.data(), f.data(), n, 1.0 / (n - 1));
+    mg.prolong_mode = PMG_PROLONG_FULL;
+    mg.v_cycle(b.data(), f.data(), n, 1.0 / (n - 1));
+    bool differ = false;
+    for (size_t i = 0; i < a.size() && !differ; ++i) differ = a[i] != b[i];
+    std::printf("{\"test\": \"knobs\", \"n\": %d, \"prolong_mode_change_seen\": %s}\n", n, differ ? "true" : "false");
+}
+
 static void history(int n)
 {
     std::vector<double> phi((size_t)n * n, 0.0), f(phi.size()), u(phi.size());
@@ -118,6 +157,7 @@ int main()
             run_cycle("V", n, &MultigridSolver::v_cycle, false);
             run_cycle("W", n, &MultigridSolver::w_cycle, false);
             run_cycle("F", n, nullptr, true);
+            run_f_cycle_like_the_runner(n);
         }
         history(257);
         for (int n : {9, 33, 257}) parallel_ops(n);

@@ -70,7 +70,7 @@ def timing(sizes, rank, world, dev):
             s.close()
         L.pmg_dist_trace_enable(0)
     pmg.set_small_vcycle_version(0)
-    pmg.set_halo_prologue(False)
+    pmg.set_halo_prologue(True)  # the default since round 2
     os.environ.pop("PMG_MID_GRAPH", None)
     os.environ.pop("PMG_SPLIT_MIN_ROWS", None)
 
@@ -82,10 +82,12 @@ def main():
         i = args.index("--timing")
         timing_n = [int(v) for v in args[i + 1].split(",")]
         args = args[:i] + args[i + 2:]
-    if "--prologue" in args:  # run the equivalence checks with the halo prologue of Pass A switched on
+    if "--prologue" in args:  # (the halo prologue of Pass A is the default since round 2; flag kept for old commands)
         args.remove("--prologue")
-        pmg.set_halo_prologue(True)
-        print("halo prologue ON", flush=True) if int(os.environ.get("RANK", "0")) == 0 else None
+    if "--no-prologue" in args:  # run the equivalence checks with in-place streaming of the halo rows instead
+        args.remove("--no-prologue")
+        pmg.set_halo_prologue(False)
+        print("halo prologue OFF", flush=True) if int(os.environ.get("RANK", "0")) == 0 else None
     sizes = [int(a) for a in args] or [1025, 4097]
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)

@@ -49,10 +49,13 @@ def test_reference_style_driver_matches_goldens(golden):
         by.setdefault(o["test"], []).append(o)
     # mg_cpu_exec stdout ("Final Relative L2 Error", 1 cycle, alpha=3, eps=1e-7)
     want = {r["n"]: r for r in golden["mg_cpu_exec_rel_l2_error"]}
-    assert len(by["mg_cpu_exec"]) == 6
+    assert len(by["mg_cpu_exec"]) == 8
     for o in by["mg_cpu_exec"]:
-        w = want[o["n"]][o["cycle"]]
+        # "F_runner_shape": compute_coarsest_grid + f_cycle(phi_coarse, f_coarse, n_coarse, h_coarse) called exactly as
+        # MultiGridTestRunner.hpp:192-205 does (3.44973e-4 at N = 257)
+        w = want[o["n"]]["F" if o["cycle"] == "F_runner_shape" else o["cycle"]]
         assert abs(o["rel_l2_error"] - w) <= 1e-12 * w
+    assert all(o["prolong_mode_change_seen"] for o in by["knobs"]) and len(by["knobs"]) == 2
     # residual history through pmg::Solver::solve (BASELINE config 1)
     h = by["history"][0]
     g = [x for x in golden["histories"] if x["n"] == 257 and x["kind"] == "V" and x["eps"] == 0.0

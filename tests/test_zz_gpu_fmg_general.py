@@ -1,7 +1,7 @@
 """GPU half of tests/test_fmg_general.py: libpmg's PMG_CYCLE_FMG (general-RHS full multigrid, not a reference function)
-reproduces its CPU specification bit for bit.  The device path only re-orders launches of kernels that the parity suite
-covers, but it was written while no GPU was available, hence the non-strict xfail guard; the file name makes it the
-LAST GPU test, so that nothing else depends on it."""
+reproduces its CPU specification bit for bit.  (Round 1 guarded this file with a non-strict xfail because the device
+path had been written without GPU access; all five cases passed on the B200 at round end -- GPUTEST_r01 -- so the guard
+is gone and a regression now fails the suite.)"""
 import numpy as np
 import pytest
 
@@ -10,7 +10,6 @@ import pmg_b200 as pmg
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="device path of PMG_CYCLE_FMG written without GPU access this round")
 @pytest.mark.parametrize("n,engine,prolong", [
     (5, pmg.ENGINE_FUSED, pmg.PROLONG_REFERENCE),
     (33, pmg.ENGINE_FUSED, pmg.PROLONG_REFERENCE),
