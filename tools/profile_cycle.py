@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Small driver for ncu: `cycle` runs 1 warm-up + 2 timed V(2,2) cycles at N (graphs off so that every
 kernel is its own launch); `passes` runs the two level-0 fused passes alone (1 warm-up + 2 launches each).
-Usage: python tools/profile_cycle.py {cycle|passes} [N]"""
+`wcycle` is `cycle` with W(gamma = 2) recursion.
+Usage: python tools/profile_cycle.py {cycle|wcycle|passes} [N]"""
 import os
 import sys
 
@@ -10,14 +11,15 @@ import pmg_b200 as pmg  # noqa: E402
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "cycle"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 16385
-s = pmg.Solver(n, omega=2.0 / 3.0, use_graph=0)
+s = pmg.Solver(n, omega=2.0 / 3.0, use_graph=0, gamma=2 if mode == "wcycle" else 1)
 s.set_rhs_sine()
 s.zero_guess()
-if mode == "cycle":
-    s.cycle(pmg.V)
+if mode in ("cycle", "wcycle"):
+    kind = pmg.W if mode == "wcycle" else pmg.V
+    s.cycle(kind)
     t = []
     for _ in range(2):
-        s.cycle(pmg.V)
+        s.cycle(kind)
         t.append(s.last_ms)
     print("N=%d cycle ms (no graph): %s" % (n, t))
 else:
