@@ -384,7 +384,16 @@ def set_deep_prefetch_below(n):
     lib().pmg_fused_set_deep_prefetch_below(n)
 
 
+def set_pdl(on):
+    """Programmatic dependent launch of the cycle kernels (default on; PMG_PDL=0 does the same as set_pdl(False)).
+    Affects solvers created afterwards."""
+    L = lib()
+    L.pmg_set_pdl.restype = None
+    L.pmg_set_pdl.argtypes = [ctypes.c_int]
+    L.pmg_set_pdl(1 if on else 0)
+
+
 def set_halo_prologue(on):
     """Multi-GPU Pass A: copy the neighbours' halo rows in a prologue (only boundary warps wait) instead of
-    streaming them in place.  Opt-in this round (PMG_HALO_PROLOGUE=1 does the same)."""
+    streaming them in place.  Default since round 2 (PMG_HALO_PROLOGUE=0 / set_halo_prologue(False) switch it off)."""
     lib().pmg_fused_set_halo_prologue(1 if on else 0)

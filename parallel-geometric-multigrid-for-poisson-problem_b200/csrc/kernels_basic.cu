@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(1024)
     k_jacobi_small(double *__restrict__ xg, const double *__restrict__ fg, int nx, int ny, int pitch_x,
                    int pitch_f, JacobiCoef c, int sweeps, int x_is_zero, const int *__restrict__ done)
 {
+    pdl_prologue();
     __shared__ double a[SMALL_MAX_POINTS], b[SMALL_MAX_POINTS], fs[SMALL_MAX_POINTS];
     if (done != nullptr && *done) return;
     int l = nx * ny;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(1024)
                    int n_coarse, double h0, double omega, int nu1, int nu2, int coarse_sweeps, int lo,
                    int x_is_zero, int gamma, const int *__restrict__ done)
 {
+    pdl_prologue();
     if (done != nullptr && *done) return;
     constexpr int MAXL = 8;
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, nty = blockDim.x >> 6;
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 __global__ void __launch_bounds__(1024) k_final_sum(const double *__restrict__ partials, int count,
                                                     double *__restrict__ out)
 {
+    pdl_prologue();
     double acc = 0.0;
     for (int i = threadIdx.x; i < count; i += blockDim.x) acc = dadd(acc, partials[i]);
     acc = block_sum(acc);
@@ -366,6 +369,7 @@ __global__ void k_solve_begin(const double *__restrict__ norm2, SolveCtrl *ctrl,
 __global__ void __launch_bounds__(1024)
     k_cycle_finish(const double *__restrict__ partials, int count, SolveCtrl *ctrl, double *__restrict__ hist2)
 {
+    pdl_prologue();
     if (ctrl->done) return;
     double acc = 0.0;
     for (int i = threadIdx.x; i < count; i += blockDim.x) acc = dadd(acc, partials[i]);
@@ -498,6 +502,7 @@ __global__ void __launch_bounds__(256)
                   const int *inbox, int my_rank, int epoch, int *err, int *const *slots, int n_ranks,
                   const int *__restrict__ epoch_base, int *abort)
 {
+    pdl_prologue();
     const int r = blockIdx.y;
     if (epoch_base != nullptr) epoch += *epoch_base;
     // "my slab is final" (everything this stream ran before this launch is complete): published by the first block
@@ -561,7 +566,7 @@ void launch_jacobi_small(double *x, const double *f, int nx, int ny, int pitch_x
 {
     int l = nx * ny;
     int threads = l >= 1024 ? 1024 : ((l + 31) / 32) * 32;
-    k_jacobi_small<<<1, threads, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, make_coef(h, omega), sweeps, x_is_zero ? 1 : 0, done);
+    launch_pdl(k_jacobi_small, dim3(1), dim3(threads), 0, st, x, f, nx, ny, pitch_x, pitch_f, make_coef(h, omega), sweeps, x_is_zero ? 1 : 0, done);
     count_launch();
 }
 
@@ -609,7 +614,7 @@ void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pi
         }
     }
     const int threads = n0 > 33 ? 1024 : (n0 > 17 ? 512 : 256);
-    k_vcycle_small<<<1, threads, smem, st>>>(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps,
+    launch_pdl(k_vcycle_small, dim3(1), dim3(threads), smem, st, x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps,
                                             prolong_mode == PMG_PROLONG_FULL ? 1 : 2, x_is_zero ? 1 : 0, gamma < 1 ? 1 : gamma, done);
     count_launch();
 }
@@ -626,7 +631,7 @@ int reduce_partials() { return RED_BLOCKS; }
 
 void launch_final_sum(const double *d_partials, int count, double *d_out, cudaStream_t st)
 {
-    k_final_sum<<<1, 1024, 0, st>>>(d_partials, count, d_out);
+    launch_pdl(k_final_sum, dim3(1), dim3(1024), 0, st, d_partials, count, d_out);
     count_launch();
 }
 
@@ -639,7 +644,7 @@ void launch_solve_begin(const double *d_norm2, SolveCtrl *ctrl, double *hist2, d
 
 void launch_cycle_finish(const double *d_partials, int count, SolveCtrl *ctrl, double *hist2, cudaStream_t st)
 {
-    k_cycle_finish<<<1, 1024, 0, st>>>(d_partials, count, ctrl, hist2);
+    launch_pdl(k_cycle_finish, dim3(1), dim3(1024), 0, st, d_partials, count, ctrl, hist2);
     count_launch();
 }
 
@@ -673,12 +678,13 @@ void launch_halo_pull(double *mine, int ny, int pitch, int depth, const double *
 
 __global__ void k_set_ints(int *dst, IntPack16 vals, int count)
 {
+    pdl_prologue();
     if ((int)threadIdx.x < count) dst[threadIdx.x] = vals.v[threadIdx.x];
 }
 
 void launch_set_ints(int *dst, const IntPack16 &vals, int count, cudaStream_t st)
 {
-    k_set_ints<<<1, 32, 0, st>>>(dst, vals, count < 16 ? count : 16);
+    launch_pdl(k_set_ints, dim3(1), dim3(32), 0, st, dst, vals, count < 16 ? count : 16);
     count_launch();
 }
 
@@ -698,10 +704,21 @@ void launch_gather_pull(double *full, int pitch, int rows, const double *const *
     if (cap < 16) cap = 16;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    k_gather_pull<<<dim3(bx, n_ranks), 256, 0, st>>>(full, pitch, rows, srcs, inbox, my_rank, epoch, err, slots, n_ranks,
+    launch_pdl(k_gather_pull, dim3(bx, n_ranks), dim3(256), 0, st, full, pitch, rows, srcs, inbox, my_rank, epoch, err, slots, n_ranks,
                                                      epoch_base, abort);
     count_launch();
 }
+
+static int g_pdl = -1;
+bool pdl_enabled()
+{
+    if (g_pdl < 0) {
+        const char *e = getenv("PMG_PDL");
+        g_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl == 1;
+}
+void pdl_set_enabled(int on) { g_pdl = on ? 1 : 0; }
 
 void basic_set_wait_timeout_ns(unsigned long long ns) { cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof(ns)); }
 

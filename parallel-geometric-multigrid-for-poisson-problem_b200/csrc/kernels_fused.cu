@@ -411,6 +411,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
            const int *__restrict__ done, HaloPeers hp)
 {
     using Feed = typename FeedSelect<C, PF, S, !ZEROX, SM>::type;
+    pdl_wait();
+    const bool pdl_early = gridDim.x <= 296u;  // at most two CTAs per SM: a latency-bound level (pmg_internal.h)
+    if (pdl_early) pdl_trigger();
     if (done != nullptr && *done) return;  // device-side convergence control: the solve already stopped
     constexpr int NP = C / 2;  // coarse points per lane (fine columns v0, v2, ...)
     // broadcast from lane 0 so the compiler KNOWS the warp index (hence every loop bound below) is warp-uniform:
@@ -562,6 +565,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             feed.end();
         }
     }
+    if (!pdl_early) pdl_trigger();
     cp_async_wait<0>();
 }
 
@@ -595,6 +599,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
          double *__restrict__ partials, const int *__restrict__ done)
 {
     using Feed = typename FeedSelect<C, PF, S, true, SM>::type;
+    pdl_wait();
+    const bool pdl_early = gridDim.x <= 296u;  // at most two CTAs per SM: a latency-bound level (pmg_internal.h)
+    if (pdl_early) pdl_trigger();
     if (done != nullptr && *done) return;
     static_assert(Feed::UNROLL % 2 == 0, "rows are processed in (even, odd) pairs");
     constexpr int NP = C / 2;
@@ -691,6 +698,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             feed.end();
         }
     }
+    if (!pdl_early) pdl_trigger();
     cp_async_wait<0>();
     if (NORM) {
 #pragma unroll
@@ -796,7 +804,7 @@ void set_smem(K kernel, int bytes)
 {
     if (bytes > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
-#define PMG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define PMG_LAUNCH(kernel, grid, block, smem, stream, ...) launch_pdl(kernel, (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel, device ordinal),

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(1024)
                     int gamma, const int *__restrict__ done)
 {
     __shared__ VsTable T;
+    pdl_prologue();
     if (done != nullptr && *done) return;
     const int t = threadIdx.x;
     if (t == 0) {
@@ -303,11 +304,11 @@ void launch_vcycle_small_v2(double *x, const double *f, int n0, int pitch_x, int
     if (threads > 1024) threads = 1024;
     const int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
     if (omega != 1.0)
-        k_vcycle_small2<true><<<1, threads, smem, st>>>(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2,
-                                                        coarse_sweeps, lo, x_is_zero ? 1 : 0, gamma, done);
+        launch_pdl(k_vcycle_small2<true>, dim3(1), dim3(threads), smem, st, x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1,
+                   nu2, coarse_sweeps, lo, x_is_zero ? 1 : 0, gamma, done);
     else
-        k_vcycle_small2<false><<<1, threads, smem, st>>>(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2,
-                                                         coarse_sweeps, lo, x_is_zero ? 1 : 0, gamma, done);
+        launch_pdl(k_vcycle_small2<false>, dim3(1), dim3(threads), smem, st, x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1,
+                   nu2, coarse_sweeps, lo, x_is_zero ? 1 : 0, gamma, done);
     count_launch();
 }
 

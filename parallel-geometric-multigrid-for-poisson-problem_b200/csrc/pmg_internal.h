@@ -74,6 +74,50 @@ __device__ __forceinline__ double restrict_point(double c, double e, double w, d
     return dadd(dadd(dmul(0.25, c), dmul(0.125, edge)), dmul(0.0625, corner));
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// The kernels of a cycle are short (5-30 us below level 2) and strictly dependent, so the ~2 us between the end of
+// one and the start of the next is a visible part of a cycle (16-30 launches per V-cycle, thousands per W-cycle).  Every
+// kernel on the cycle path is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+// pdl_prologue(): `griddepcontrol.wait` blocks until the preceding kernel has COMPLETED and its writes are visible
+// (so nothing below it can observe a half-finished predecessor), `griddepcontrol.launch_dependents` then lets the
+// NEXT kernel's CTAs be scheduled as this one's drain, where they park on their own wait.  Correctness never depends
+// on it (without the attribute both instructions are no-ops); PMG_PDL=0 launches the classic way.
+// Measured (profiles/r2_pdl_probe.log): 53.3 -> 49.6 us per V-cycle at N = 257, 305 -> 300 us at 4097 -- but a level-0
+// pass at N = 16385 got 5 % SLOWER when its successor's CTAs were made resident early (they take shared memory and
+// slots away from a kernel sized as exactly one resident wave).  So the big streaming passes release their
+// dependents only when a warp has finished its rows (pdl_wait at the top, pdl_trigger at the end); the small
+// kernels do both at the top.
+#ifdef PMG_HOST_EMULATION
+__device__ __forceinline__ void pdl_prologue() {}
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#else
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue()
+{
+    pdl_wait();
+    pdl_trigger();
+}
+bool pdl_enabled();
+void pdl_set_enabled(int on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- launch bookkeeping ---------------------------------------------------------------------------
 void count_launch(int n = 1);
 unsigned long long launches_so_far();

@@ -1702,6 +1702,10 @@ void pmg_dist_trace_dump(int rank_to_print)
 void pmg_small_vcycle_set_version(int v) { vcycle_small_set_version(v); }
 int pmg_small_vcycle_version(void) { return vcycle_small_version(); }
 
+/* programmatic dependent launch of the cycle kernels (pmg_internal.h); takes effect for solvers created afterwards
+ * (captured graphs keep the edges they were captured with) */
+void pmg_set_pdl(int on) { pdl_set_enabled(on); }
+
 int pmg_fused_num_variants(void) { return fused_num_variants(); }
 void pmg_fused_set_variant(int v) { fused_set_variant(v); }
 void pmg_fused_set_min_chunk_rows(int r) { fused_set_min_chunk_rows(r); }

@@ -31,6 +31,7 @@ struct EmuDim3 {
 };
 inline thread_local EmuDim3 threadIdx;
 inline EmuDim3 blockDim;
+inline EmuDim3 gridDim;
 typedef void *cudaStream_t;
 
 inline double __dadd_rn(double a, double b) { return a + b; }
@@ -203,6 +204,7 @@ inline void emu_launch_warps(dim3 grid, dim3 block, const std::function<void()> 
 {
     static thread_local EmuWarp warp;
     blockDim.x = block.x;
+    gridDim.x = grid.x;
     for (unsigned b = 0; b < grid.x; ++b) {
         blockIdx.x = b;
         std::memset(emu_smem, 0xff, EMU_SMEM_BYTES);  // NaN pattern: a slot read before it was written shows up
