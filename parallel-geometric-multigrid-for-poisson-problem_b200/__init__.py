@@ -324,6 +324,14 @@ class Solver:
         return v.value
 
     @property
+    def cluster_top(self):
+        """Level size from which one cluster launch runs the rest of the cycle (0: not in use)."""
+        L = lib()
+        L.pmg_cluster_top.restype = ctypes.c_int
+        L.pmg_cluster_top.argtypes = [ctypes.c_void_p]
+        return L.pmg_cluster_top(self._h)
+
+    @property
     def last_ms(self):
         v = ctypes.c_double()
         check(lib().pmg_last_device_ms(self._h, ctypes.byref(v)))
@@ -382,6 +390,15 @@ def small_vcycle_version():
 def set_deep_prefetch_below(n):
     """Levels with n <= this use the 7-rows-in-flight variant of the nu == 2 fused passes (0: never, -1: default)."""
     lib().pmg_fused_set_deep_prefetch_below(n)
+
+
+def set_cluster_top(n):
+    """Top level of the 16-CTA cluster kernel (kernels_coarse.cu) for solvers created afterwards: 129 (default), 257,
+    0 = off (streaming passes + single-CTA kernel), -1 = back to PMG_CLUSTER / the default."""
+    L = lib()
+    L.pmg_set_cluster_top.restype = None
+    L.pmg_set_cluster_top.argtypes = [ctypes.c_int]
+    L.pmg_set_cluster_top(n)
 
 
 def set_pdl(on):

@@ -582,23 +582,32 @@ size_t vcycle_small_smem(int n0, int n_coarse)
 }
 
 // which generation of the single-CTA small-level kernel runs: 1 = k_vcycle_small (this file), 2 = k_vcycle_small2
-// (kernels_small.cu: per-level thread groups on named barriers).  PMG_SMALL_V2=0/1 overrides the default.
+// (kernels_small.cu: per-level thread groups on named barriers), 3 = k_coarse_local (kernels_coarse.cu: level sizes
+// as template parameters, one-warp deep levels; the default).  PMG_SMALL_VERSION=1/2/3 overrides the default
+// (PMG_SMALL_V2=0/1 is the round-1 spelling of 1/2).
 static int g_small_version = 0;
 int vcycle_small_version()
 {
     if (g_small_version == 0) {
-        const char *e = getenv("PMG_SMALL_V2");
-        g_small_version = (e && e[0] == '1') ? 2 : ((e && e[0] == '0') ? 1 : PMG_SMALL_DEFAULT_VERSION);
+        g_small_version = PMG_SMALL_DEFAULT_VERSION;
+        if (const char *e = getenv("PMG_SMALL_V2")) g_small_version = (e[0] == '1') ? 2 : ((e[0] == '0') ? 1 : g_small_version);
+        if (const char *e = getenv("PMG_SMALL_VERSION"))
+            if (e[0] >= '1' && e[0] <= '3') g_small_version = e[0] - '0';
     }
     return g_small_version;
 }
-void vcycle_small_set_version(int v) { g_small_version = (v == 2) ? 2 : (v == 1 ? 1 : 0); }
+void vcycle_small_set_version(int v) { g_small_version = (v >= 1 && v <= 3) ? v : 0; }
 
 void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0,
                          double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
                          int gamma, cudaStream_t st, const int *done)
 {
-    if (vcycle_small_version() == 2 && vcycle_small_v2_supported(gamma)) {
+    if (vcycle_small_version() == 3 && coarse_local_supported(n0, gamma)) {
+        launch_coarse_local(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps, prolong_mode, x_is_zero,
+                            gamma, st, done);
+        return;
+    }
+    if (vcycle_small_version() >= 2 && vcycle_small_v2_supported(gamma)) {
         launch_vcycle_small_v2(x, f, n0, pitch_x, pitch_f, n_coarse, h0, omega, nu1, nu2, coarse_sweeps, prolong_mode,
                                x_is_zero, gamma, st, done);
         return;

@@ -140,9 +140,14 @@ void launch_vcycle_small(double *x, const double *f, int n0, int pitch_x, int pi
                          double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
                          int gamma, cudaStream_t st, const int *done = nullptr);
 // second generation of the same kernel (kernels_small.cu); launch_vcycle_small dispatches on vcycle_small_version()
-constexpr int PMG_SMALL_DEFAULT_VERSION = 2;
+constexpr int PMG_SMALL_DEFAULT_VERSION = 3;
 int vcycle_small_version();
-void vcycle_small_set_version(int v);  // 1, 2, or 0 = re-read PMG_SMALL_V2 / the default
+void vcycle_small_set_version(int v);  // 1, 2, 3, or 0 = re-read PMG_SMALL_VERSION / the default
+// third generation (kernels_coarse.cu, k_coarse_local): level sizes are template parameters
+bool coarse_local_supported(int n0, int gamma);
+void launch_coarse_local(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0, double omega,
+                         int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero, int gamma, cudaStream_t st,
+                         const int *done = nullptr);
 bool vcycle_small_v2_supported(int gamma);
 void launch_vcycle_small_v2(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0,
                             double omega, int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero,
@@ -195,6 +200,18 @@ void launch_fill2d(double *dst, int pitch_d, int nx, int ny, double v, cudaStrea
 // f(y,x) = (factor * sx[x]) * sy[y]   (DynamicGridUtils.hpp:113-122 with 1-D sine tables)
 void launch_rhs_separable(double *f, int pitch, int nx, int ny, double factor, const double *sx,
                           const double *sy, cudaStream_t st);
+
+// The cluster kernel (kernels_coarse.cu, k_coarse_cluster): the levels n0 (257 or 129) ... n_coarse of one V- or W-cycle
+// in ONE launch of a 16-CTA thread-block cluster, levels >= 33 distributed over the CTAs' shared memories (DSMEM).
+// Returns false -- and launches nothing -- when the configuration or the device cannot run it (the caller then takes
+// the streaming passes + the single-CTA kernel).
+bool coarse_cluster_top(int n);
+bool coarse_cluster_available(int n0);
+// per-level cycle profile of the last coarse-kernel launch on the current device (slot k: level 2^k + 1, slot 0: all)
+void coarse_profile_read(long long out[16]);
+bool launch_coarse_cluster(double *x, const double *f, int n0, int pitch_x, int pitch_f, int n_coarse, double h0, double omega,
+                           int nu1, int nu2, int coarse_sweeps, int prolong_mode, bool x_is_zero, int gamma, cudaStream_t st,
+                           const int *done = nullptr);
 
 // ---- fused streaming kernels (kernels_fused.cu) ---------------------------------------------------
 // Halo rows read straight out of the neighbours' HBM over NVLink (all null on one GPU / when the halo rows are

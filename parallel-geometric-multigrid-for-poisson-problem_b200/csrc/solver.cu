@@ -48,6 +48,7 @@ static int install_debug_signals()
 static int g_debug_signals = install_debug_signals();
 
 thread_local std::string g_last_error;
+static int g_cluster_override = -1;  // pmg_set_cluster_top: -1 = PMG_CLUSTER / the default
 
 static pmg_status fail(pmg_status s, const std::string &msg)
 {
@@ -103,6 +104,9 @@ struct pmg_solver {
     int graph_kernels[2][3] = {{0, 0, 0}, {0, 0, 0}};  // kernel nodes per replay (launch bookkeeping)
     bool fused = false;
     bool small_vcycle = true;  // PMG_SMALL_VCYCLE=0 disables the single-CTA kernel for the levels <= 65
+    int cluster_top = 0;       // level size from which ONE 16-CTA cluster launch runs the rest of the cycle (257 / 129;
+                               // 0: off -- PMG_CLUSTER=0, an unsuitable configuration, or a device that cannot co-schedule
+                               // the cluster)
     // asynchronous solve: device control block + history of squared norms, pinned mirrors, batch events
     SolveCtrl *d_ctrl = nullptr;
     double *d_hist2 = nullptr;
@@ -264,6 +268,11 @@ static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero,
     Level &L = s->lv[l];
     if (L.n <= c.n_coarse || l + 1 == (int)s->lv.size())
         return smooth_operator(s, l, c.coarse_sweeps, x_is_zero, done);
+    // from level 257 (or 129) down: ONE launch of a 16-CTA cluster, levels distributed over the CTAs' shared memories
+    if (l > 0 && L.n == s->cluster_top &&
+        launch_coarse_cluster(L.x, L.f, L.n, L.pitch, L.pitch, c.n_coarse, L.h, c.omega, c.nu1, c.nu2, c.coarse_sweeps,
+                              c.prolong_mode, x_is_zero, w_form ? c.gamma : 1, s->stream, done))
+        return PMG_OK;
     // the small levels (V or W recursion alike) run as ONE single-CTA kernel in shared memory
     if (l > 0 && L.n <= VSMALL_TOP && s->small_vcycle && (int)s->lv.size() - l <= 8 &&
         s->lv.back().n * s->lv.back().n <= SMALL_MAX_POINTS) {
@@ -1072,6 +1081,21 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     };
     (void)fused_max_partials(3);  // warms the cached SM count outside any stream capture
     if (const char *e = getenv("PMG_SMALL_VCYCLE")) s->small_vcycle = !(e[0] == '0');
+    {
+        // cluster kernel: needs the default coarse end of the hierarchy (coarsest level <= 17, reached by halving) and
+        // the fused engine; PMG_CLUSTER=0 switches it off, PMG_CLUSTER=257 makes 257 the top instead of 129 (measured:
+        // 129 is the faster split -- the level-257 visit costs 18 000 cycles in the cluster, about what its two
+        // streaming passes take; profiles/r2_coarse_kernels.md)
+        int want = 129;
+        if (const char *e = getenv("PMG_CLUSTER")) want = (e[0] == '0') ? 0 : (atoi(e) == 257 ? 257 : 129);
+        if (g_cluster_override >= 0) want = g_cluster_override;
+        if (want && s->fused && s->small_vcycle && cfg->n_coarse <= 17 && vcycle_small_version() == 3) {
+            if (cfg->n > want && coarse_cluster_available(want))
+                s->cluster_top = want;
+            else if (cfg->n > 129 && coarse_cluster_available(129))
+                s->cluster_top = 129;
+        }
+    }
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(PMG_ERR_CUDA, "cudaStreamCreate failed"));
     cudaEventCreate(&s->ev0);
@@ -1706,11 +1730,83 @@ int pmg_small_vcycle_version(void) { return vcycle_small_version(); }
  * (captured graphs keep the edges they were captured with) */
 void pmg_set_pdl(int on) { pdl_set_enabled(on); }
 
+/* top level of the 16-CTA cluster kernel for solvers created afterwards: 257, 129, 0 = off, -1 = PMG_CLUSTER / default */
+void pmg_set_cluster_top(int n) { g_cluster_override = (n == 257 || n == 129 || n == 0) ? n : -1; }
+int pmg_cluster_top(const pmg_solver *s) { return s ? s->cluster_top : 0; }
+
 int pmg_fused_num_variants(void) { return fused_num_variants(); }
 void pmg_fused_set_variant(int v) { fused_set_variant(v); }
 void pmg_fused_set_min_chunk_rows(int r) { fused_set_min_chunk_rows(r); }
 void pmg_fused_set_deep_prefetch_below(int n) { fused_set_deep_prefetch_below(n); }
 void pmg_fused_set_halo_prologue(int on) { fused_set_halo_prologue(on); }
+
+/* Times the single-CTA small-level kernel alone (benchmark hook): `reps` launches of one V- (gamma = 1) or W-visit of
+ * the levels n0 (<= 65) ... 5 on scratch arrays, generation `version` (1, 2, 3); *us_avg = average microseconds per
+ * launch, CUDA events on a private stream.  From T(n0, gamma) = own(n0) + gamma * T((n0-1)/2+1, gamma) the cost of one
+ * visit of every level follows (tools/small_kernel_probe.py). */
+pmg_status pmg_bench_small(int n0, int gamma, int reps, int version, double *us_avg)
+{
+    const bool cluster = coarse_cluster_top(n0);  // 129 / 257: the 16-CTA cluster kernel instead
+    if (!us_avg || reps < 1 || gamma < 1 || n0 < 3 || (n0 > VSMALL_TOP && !cluster) || ((n0 - 1) & (n0 - 2)) != 0)
+        return fail(PMG_ERR_INVALID, "bad argument");
+    if (pmg_device_count() <= 0) return fail(PMG_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    const int pitch = level_pitch(n0);
+    double *x = nullptr, *f = nullptr;
+    pmg_status rc = alloc_zero(&x, level_elems(n0));
+    if (rc == PMG_OK) rc = alloc_zero(&f, level_elems(n0));
+    if (rc != PMG_OK) {
+        cudaFree(x);
+        return rc;
+    }
+    launch_fill2d(f + level_origin(n0) + pitch + 1, pitch, n0 - 2, n0 - 2, 1.0, nullptr);
+    const int before = vcycle_small_version();
+    vcycle_small_set_version(version);
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStreamCreate(&st);
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    if (cluster && !coarse_cluster_available(n0)) {
+        cudaFree(x);
+        cudaFree(f);
+        return fail(PMG_ERR_UNSUPPORTED, "a 16-CTA cluster cannot be scheduled on this device");
+    }
+    auto one = [&]() {
+        if (cluster)
+            launch_coarse_cluster(x + level_origin(n0), f + level_origin(n0), n0, pitch, pitch, 5, 1.0 / 1024.0, 2.0 / 3.0, 2, 2,
+                                  11, PMG_PROLONG_REFERENCE, true, gamma, st, nullptr);
+        else
+            launch_vcycle_small(x + level_origin(n0), f + level_origin(n0), n0, pitch, pitch, 5, 1.0 / 1024.0, 2.0 / 3.0, 2, 2,
+                                11, PMG_PROLONG_REFERENCE, true, gamma, st, nullptr);
+    };
+    cudaDeviceSynchronize();
+    one();
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps; ++i) one();
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    vcycle_small_set_version(before);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(st);
+    cudaFree(x);
+    cudaFree(f);
+    if (e != cudaSuccess) return fail(PMG_ERR_CUDA, cudaGetErrorString(e));
+    *us_avg = 1e3 * ms / reps;
+    return PMG_OK;
+}
+
+/* cycles per level of the most recent coarse-kernel launch (k_coarse_local / k_coarse_cluster): slot k = own cycles of all
+ * visits of level 2^k + 1 as seen by thread 0 (of CTA 0), slot 0 = the whole kernel body */
+pmg_status pmg_coarse_profile(long long out[16])
+{
+    if (!out) return fail(PMG_ERR_INVALID, "null argument");
+    PMG_CUDA(cudaDeviceSynchronize());
+    coarse_profile_read(out);
+    return PMG_OK;
+}
 
 /* `sweeps` weighted-Jacobi sweeps on the solver's finest level, `block` sweeps per streaming pass
  * (block = 1: one HBM pass per sweep, 24 B/point -- the "Jacobi sweep GB/s" sub-metric). */

@@ -333,11 +333,12 @@ def test_engines_and_variants_agree_bitwise(n):
     (1025, pmg.W, 2, 2.0 / 3.0, pmg.PROLONG_REFERENCE),
 ])
 def test_small_level_kernel_generations_agree_bitwise(orc, n, kind, gamma, omega, prolong):
-    """Both generations of the single-CTA kernel for the levels <= 65 (k_vcycle_small: whole-CTA barriers;
-    k_vcycle_small2: per-level thread groups on named barriers) against each other and against the oracle."""
+    """All three generations of the single-CTA kernel for the levels <= 65 (k_vcycle_small: whole-CTA barriers;
+    k_vcycle_small2: per-level thread groups on named barriers; k_coarse_local: level sizes as template parameters,
+    one-warp deep levels -- the default) against each other and against the oracle."""
     f = cc.random_rhs(n, seed=61)
     got = {}
-    for version in (1, 2):
+    for version in (1, 2, 3):
         pmg.set_small_vcycle_version(version)
         assert pmg.small_vcycle_version() == version
         with pmg.Solver(n, omega=omega, gamma=gamma, prolong_mode=prolong) as s:
@@ -346,13 +347,50 @@ def test_small_level_kernel_generations_agree_bitwise(orc, n, kind, gamma, omega
             norms = [s.cycle(kind) for _ in range(3)]
             got[version] = (norms, s.get_solution())
     pmg.set_small_vcycle_version(0)
-    assert np.array_equal(got[1][1], got[2][1])
-    assert got[1][0] == got[2][0]
+    assert np.array_equal(got[1][1], got[2][1]) and np.array_equal(got[1][1], got[3][1])
+    assert got[1][0] == got[2][0] == got[3][0]
     if n <= 129:
         want = np.zeros((n, n))
         for _ in range(3):
             orc.cycle(want, f, kind=cc.W if kind == pmg.W else cc.V, omega=omega, eps=0.0, alpha=gamma, prolong=prolong)
         assert np.array_equal(got[2][1], want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,kind,gamma,omega,prolong,nu", [
+    (257, pmg.V, 1, 2.0 / 3.0, pmg.PROLONG_REFERENCE, (2, 2)),
+    (513, pmg.W, 2, 2.0 / 3.0, pmg.PROLONG_REFERENCE, (2, 2)),
+    (513, pmg.W, 3, 1.0, pmg.PROLONG_FULL, (1, 2)),
+    (1025, pmg.V, 1, 0.8, pmg.PROLONG_FULL, (3, 1)),
+    (1025, pmg.F, 1, 2.0 / 3.0, pmg.PROLONG_REFERENCE, (2, 2)),
+])
+def test_cluster_kernel_matches_streaming_path_and_oracle(orc, n, kind, gamma, omega, prolong, nu):
+    """The 16-CTA cluster kernel (kernels_coarse.cu: levels 129 or 257 and below in ONE launch, distributed over the
+    CTAs' shared memories) against the path it replaces (streaming passes + the single-CTA kernel) and, at sizes the
+    oracle finishes quickly, against the oracle: iterates bit-identical, norms equal."""
+    f = cc.random_rhs(n, seed=67)
+    phi0 = np.random.default_rng(68).standard_normal((n, n))
+    got = {}
+    for top in (0, 129, 257):
+        if top >= n:
+            continue
+        pmg.set_cluster_top(top)
+        with pmg.Solver(n, omega=omega, gamma=gamma, prolong_mode=prolong, nu1=nu[0], nu2=nu[1]) as s:
+            assert s.cluster_top == top, "a B200 can co-schedule a 16-CTA cluster"
+            s.set_rhs(f)
+            s.set_guess(phi0)
+            norms = [s.cycle(kind) for _ in range(2)]
+            got[top] = (norms, s.get_solution())
+    pmg.set_cluster_top(-1)
+    for top in got:
+        assert np.array_equal(got[top][1], got[0][1]), top
+        assert got[top][0] == got[0][0], top
+    if n <= 513:
+        want = phi0.copy()
+        for _ in range(2):
+            orc.cycle(want, f, kind={pmg.V: cc.V, pmg.W: cc.W, pmg.F: cc.F}[kind], omega=omega, eps=0.0, alpha=gamma,
+                      v1=nu[0] - 1, v2=nu[1] - 1, prolong=prolong)
+        assert np.array_equal(got[129][1], want)
 
 
 def test_scaling_by_two_is_exact():

@@ -3,6 +3,7 @@
   * the single-CTA small-level kernel generation (1 / 2), and
   * the deep-prefetch variant of the fused passes for levels n <= threshold,
 at sizes where the whole cycle is latency-bound (N = 257 ... 4097), V and W(gamma = 2), plus the headline sizes.
+(the second tuple entry is now the top level of the 16-CTA cluster kernel: 0 = off)
 Every combination must give the same bits (checked against the first one); prints one JSON line per run.
 
   python tools/latency_probe.py [quick]
@@ -17,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pmg_b200 as pmg  # noqa: E402
 
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-combos = [(1, 0), (2, 0), (2, 1025), (2, 2049), (2, 4097), (1, 4097)]
+combos = [(2, 0), (3, 0), (3, 129), (3, 257)]  # (small-kernel generation, cluster-kernel top level)
 cases = [(257, pmg.V, 1), (1025, pmg.V, 1), (4097, pmg.V, 1), (1025, pmg.W, 2), (4097, pmg.W, 2)]
 if not quick:
     cases += [(16385, pmg.V, 1), (16385, pmg.W, 2)]
@@ -25,10 +26,10 @@ ok = True
 for n, kind, gamma in cases:
     ref = None
     for small, deep in combos:
-        if n == 16385 and (small, deep) not in ((1, 0), (2, 0), (2, 2049)):
+        if n <= deep:
             continue
         pmg.set_small_vcycle_version(small)
-        pmg.set_deep_prefetch_below(deep)
+        pmg.set_cluster_top(deep)
         s = pmg.Solver(n, omega=2.0 / 3.0, gamma=gamma)
         s.set_rhs_sine()
         best = None
@@ -46,9 +47,9 @@ for n, kind, gamma in cases:
             same = (k == ref[0]) and np.array_equal(hist, ref[1]) and (phi is None or np.array_equal(phi, ref[2]))
         ok &= same
         print(json.dumps({"n": n, "cycle": "V" if kind == pmg.V else "W2", "small_kernel": small,
-                          "deep_prefetch_below": deep, "cycles": k, "solve_ms": round(best, 4),
+                          "cluster_top": deep, "cycles": k, "solve_ms": round(best, 4),
                           "us_per_cycle": round(1e3 * best / k, 2), "bit_identical_to_first": bool(same)}), flush=True)
 pmg.set_small_vcycle_version(0)
-pmg.set_deep_prefetch_below(-1)
+pmg.set_cluster_top(-1)
 print("latency_probe:", "OK" if ok else "MISMATCH", flush=True)
 sys.exit(0 if ok else 1)
