@@ -350,6 +350,69 @@ def workload_config(args, n_gpus):
             "parallelism": "1 GPU" if n_gpus == 1 else "row slabs x%d" % n_gpus}
 
 
+def e2e_measure(pmg, s, n, ny, args, fill_f, max_cycles, fence=None, reduce_max=None):
+    """The same solve measured end to end through the C ABI with pinned HOST buffers: every step copies its right-hand
+    side host -> device and its solution device -> host inside the timed region (phi0 = 0 is pmg_set_guess(NULL): no
+    zeros cross PCIe).  Two figures:
+      value / ms_per_step   a stream of problems with the overlapped transfers of include/pmg.h (pmg_stage_rhs /
+                            pmg_commit_rhs / pmg_fetch_solution_begin / _wait): the copies of step k+1 and k-1 run on
+                            their own streams beside the solve of step k -- every step still moves all its bytes;
+      serial                one problem at a time: H2D, solve, D2H strictly one after the other (latency of a single
+                            solve including its copies; round 1 reported only this, with 2.1 GB of zeros uploaded too).
+    ny: rows of this rank's slab (n on one GPU)."""
+    fence = fence or (lambda: pmg.check(pmg.lib().pmg_device_synchronize()))
+    rmax = reduce_max or (lambda v: v)
+    f_host, pf = pinned(pmg, (ny, n))
+    out_host, po = pinned(pmg, (ny, n))
+    fill_f(f_host)
+    e_steps = max(2, min(args.steps, 8))
+
+    def serial_step():
+        s.set_rhs(f_host)
+        s.set_guess(None)
+        kk, _ = s.solve(pmg.V, rel_tol=REL_TOL, max_cycles=max_cycles)
+        s.get_solution(out_host)
+        return kk
+
+    serial_step()
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        ke = serial_step()
+    fence()
+    serial_wall = rmax((time.perf_counter() - t0) / e_steps)
+
+    def pipelined(steps):
+        s.stage_rhs(f_host)
+        kk = 0
+        for k in range(steps):
+            s.commit_rhs()
+            if k + 1 < steps:
+                s.stage_rhs(f_host)       # H2D of step k+1 beside the solve of step k
+            s.set_guess(None)
+            kk, _ = s.solve(pmg.V, rel_tol=REL_TOL, max_cycles=max_cycles)
+            s.fetch_solution_wait()       # D2H of step k-1 (long done) before its snapshot is re-used
+            s.fetch_solution_begin(out_host)
+        s.fetch_solution_wait()
+        return kk
+
+    pipelined(2)
+    fence()
+    t0 = time.perf_counter()
+    ke = pipelined(e_steps)
+    fence()
+    pipe_wall = rmax((time.perf_counter() - t0) / e_steps)
+    out_ok = bool(np.isfinite(out_host[ny // 2, n // 2]) and out_host[ny // 2, n // 2] != 0.0)
+    for p in (pf, po):
+        pmg.lib().pmg_host_free_pinned(p)
+    return {"value": n * n / pipe_wall / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * n * 8,
+            "d2h_bytes_per_step": n * n * 8 + (ke + 1) * 8, "ms_per_step": 1e3 * pipe_wall, "cycles": ke,
+            "mode": "overlapped transfers (pmg_stage_rhs / pmg_fetch_solution_begin), %d problems back to back" % e_steps,
+            "serial": {"value": n * n / serial_wall / 1e9, "ms_per_step": 1e3 * serial_wall,
+                       "what": "H2D f, solve, D2H phi strictly one after the other"},
+            "phi0": "zero start via pmg_set_guess(NULL)", "result_read_back": out_ok}
+
+
 # ------------------------------------------------------------------------------------------------------
 def run_single(args):
     import pmg_b200 as pmg
@@ -401,29 +464,7 @@ def run_single(args):
     jac_blocked_gbs = 24.0 * n * n * 12 / (s.last_ms * 1e-3) / 1e9
 
     # ---- e2e through the C ABI with pinned HOST buffers ----
-    f_host, pf = pinned(pmg, (n, n))
-    x_host, px = pinned(pmg, (n, n))
-    out_host, po = pinned(pmg, (n, n))
-    sine_rhs(n, f_host)
-    x_host[:] = 0.0
-
-    def e2e_step():
-        s.set_rhs(f_host)
-        s.set_guess(x_host)
-        kk, hh = s.solve(pmg.V, rel_tol=REL_TOL, max_cycles=max_cycles)
-        s.get_solution(out_host)
-        return kk
-
-    e2e_step()
-    e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        ke = e2e_step()
-    e_wall = (time.perf_counter() - t0) / e_steps
-    e2e = {"value": n * n / e_wall / 1e9, "unit": UNIT, "h2d_bytes_per_step": 2 * n * n * 8,
-           "d2h_bytes_per_step": n * n * 8 + (ke + 1) * 8, "ms_per_step": 1e3 * e_wall, "cycles": ke}
-    for p in (pf, px, po):
-        pmg.lib().pmg_host_free_pinned(p)
+    e2e = e2e_measure(pmg, s, n, n, args, lambda out: sine_rhs(n, out), max_cycles)
     s.close()
 
     # ---- parity of the timed configuration against the reference's CPU history (committed golden) ----

@@ -12,12 +12,32 @@ import numpy as np
 import bench
 
 
+def pin_to_gpu_numa_node(local):
+    """Run this rank on the CPU cores next to ITS GPU before anything is allocated, so that the pinned host buffers
+    of the e2e leg are first touched -- hence placed -- on the GPU's own NUMA node.  (Round 1: 8 ranks with default
+    placement reached 16.8 GB/s per rank over PCIe.)"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "rank pinned to the %d cores NVML lists for GPU %d (%d-%d)" % (len(cpus), local, cpus[0], cpus[-1])
+        return "NVML affinity empty; default placement"
+    except Exception as e:  # noqa: BLE001
+        return "default placement (%s)" % repr(e)[:80]
+
+
 def run(args):
     import torch
     import torch.distributed as dist
     import pmg_b200 as pmg
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_note = pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world, dev = pmg.init_distributed_from_torch(local)
@@ -68,34 +88,20 @@ def run(args):
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_down, t_upn = float(tt[0]), float(tt[1])
 
-    # e2e: every rank pushes ITS slab of f and phi0 from pinned host memory and pulls its slab of phi back
-    f_host, pf = bench.pinned(pmg, (ny, n))
-    x_host, px = bench.pinned(pmg, (ny, n))
-    out_host, po = bench.pinned(pmg, (ny, n))
-    h = 1.0 / (n - 1)
-    sx = np.sin(np.pi * (np.arange(n) * h))
-    np.multiply((2.0 * np.pi * np.pi * sx)[None, :], sx[y0:y1, None], out=f_host)
-    x_host[:] = 0.0
+    # e2e: every rank pushes ITS slab of f from pinned host memory and pulls its slab of phi back
+    def fill_f(out):
+        h = 1.0 / (n - 1)
+        sx = np.sin(np.pi * (np.arange(n) * h))
+        np.multiply((2.0 * np.pi * np.pi * sx)[None, :], sx[y0:y1, None], out=out)
 
-    def e2e_step():
-        s.set_rhs(f_host)
-        s.set_guess(x_host)
-        kk, _ = s.solve(pmg.V, rel_tol=bench.REL_TOL, max_cycles=max_cycles)
-        s.get_solution(out_host)
-        return kk
+    def reduce_max_early(v):
+        tv = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return float(tv[0])
 
-    e2e_step()
-    fence()
-    e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        ke = e2e_step()
-    fence()
-    te = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e_wall = float(te[0])
-    for p in (pf, px, po):
-        pmg.lib().pmg_host_free_pinned(p)
+    e2e = bench.e2e_measure(pmg, s, n, ny, args, fill_f, max_cycles, fence, reduce_max_early)
+    e2e["d2h_bytes_per_step"] = n * n * 8 + (e2e["cycles"] + 1) * 8 * world
+    e2e["numa"] = numa_note
     s.close()
 
     # the other BASELINE configs on the same ranks (W and F at N = 16385, N = 4097, the N = 32769 weak-scaling point)
@@ -137,8 +143,7 @@ def run(args):
                              "vcycle_effective_gbs_at_69.3B_per_dof": cycle_gbs,
                              "vcycle_frac_of_aggregate_peak": cycle_gbs / (peak * world)},
                 "cpu_baseline": None,
-                "e2e": {"value": n * n / e_wall / 1e9, "unit": bench.UNIT, "h2d_bytes_per_step": 2 * n * n * 8,
-                        "d2h_bytes_per_step": n * n * 8 + (ke + 1) * 8 * world, "ms_per_step": 1e3 * e_wall, "cycles": ke},
+                "e2e": e2e,
                 "gpu_launches": int(lt[0]), "clocks": clk}
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -124,8 +124,24 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out);
 void pmg_destroy(pmg_solver *s);
 /* f / phi: n*n doubles in the reference layout, in host or device memory */
 pmg_status pmg_set_rhs(pmg_solver *s, const double *f, pmg_mem where);
+/* phi == NULL: the zero start, same as pmg_zero_guess (nothing crosses PCIe) */
 pmg_status pmg_set_guess(pmg_solver *s, const double *phi, pmg_mem where);
 pmg_status pmg_get_solution(pmg_solver *s, double *phi, pmg_mem where);
+/* Overlapped host transfers for a STREAM of problems on one hierarchy (the reference's runners solve one problem after
+ * the other, MultiGridTestRunner.hpp:66-109): both PCIe directions run on copy streams of their own beside the solver.
+ *   pmg_stage_rhs            starts copying the NEXT right-hand side (PINNED host memory, n x n or this rank's rows)
+ *                            into a staging array and returns at once;
+ *   pmg_commit_rhs           makes the staged array the solver's right-hand side (device-side wait + device copy;
+ *                            with n_ranks > 1 also the halo exchange) -- call it before the solve that uses it;
+ *   pmg_fetch_solution_begin snapshots the iterate on the device (so the next solve may overwrite it) and starts
+ *                            copying the snapshot to PINNED host memory; returns at once;
+ *   pmg_fetch_solution_wait  blocks until that copy has arrived (call it before the next _begin and before reading).
+ * Typical loop:  stage(f0); for k: { commit(); stage(f_{k+1}); set_guess(NULL); solve(); fetch_wait(); fetch_begin(out_k); }
+ * Costs two extra level-0 arrays and two device copies (1.4 ms each at N = 16385) per problem. */
+pmg_status pmg_stage_rhs(pmg_solver *s, const double *f_host);
+pmg_status pmg_commit_rhs(pmg_solver *s);
+pmg_status pmg_fetch_solution_begin(pmg_solver *s, double *phi_host);
+pmg_status pmg_fetch_solution_wait(pmg_solver *s);
 /* phi = 0 (DynamicGridUtils::initialize_zeros, DynamicGridUtils.hpp:14-18) */
 pmg_status pmg_zero_guess(pmg_solver *s);
 /* f = 2 pi^2 sin(pi x) sin(pi y) generated on the device (DynamicGridUtils::compute_rhs, :111-124,

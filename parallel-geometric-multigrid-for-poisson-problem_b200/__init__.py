@@ -51,6 +51,7 @@ class Config(ctypes.Structure):
 ABI_SYMBOLS = [
     "pmg_version", "pmg_last_error", "pmg_status_string", "pmg_config_default", "pmg_kernel_launches",
     "pmg_create", "pmg_destroy", "pmg_set_rhs", "pmg_set_guess", "pmg_get_solution", "pmg_zero_guess",
+    "pmg_stage_rhs", "pmg_commit_rhs", "pmg_fetch_solution_begin", "pmg_fetch_solution_wait",
     "pmg_set_rhs_sine", "pmg_residual_norm", "pmg_cycle", "pmg_restrict_to_level", "pmg_f_cycle_from", "pmg_solve", "pmg_last_device_ms", "pmg_stream",
     "pmg_jacobi", "pmg_residual", "pmg_restrict_fw", "pmg_prolong_add", "pmg_norm2", "pmg_release_scratch",
     "pmg_device_alloc", "pmg_device_free", "pmg_host_alloc_pinned", "pmg_host_free_pinned", "pmg_memcpy",
@@ -276,8 +277,24 @@ class Solver:
         check(lib().pmg_set_rhs_sine(self._h))
 
     def set_guess(self, phi):
+        if phi is None:  # the zero start
+            check(lib().pmg_set_guess(self._h, None, MEM_HOST))
+            return
         p, m = _ptr_and_mem(phi)
         check(lib().pmg_set_guess(self._h, p, m))
+
+    # overlapped host transfers (pinned numpy buffers): see include/pmg.h
+    def stage_rhs(self, f_pinned):
+        check(lib().pmg_stage_rhs(self._h, ctypes.c_void_p(f_pinned.ctypes.data)))
+
+    def commit_rhs(self):
+        check(lib().pmg_commit_rhs(self._h))
+
+    def fetch_solution_begin(self, out_pinned):
+        check(lib().pmg_fetch_solution_begin(self._h, ctypes.c_void_p(out_pinned.ctypes.data)))
+
+    def fetch_solution_wait(self):
+        check(lib().pmg_fetch_solution_wait(self._h))
 
     def zero_guess(self):
         check(lib().pmg_zero_guess(self._h))

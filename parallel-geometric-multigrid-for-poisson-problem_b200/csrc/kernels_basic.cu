@@ -365,6 +365,23 @@ __global__ void k_solve_begin(const double *__restrict__ norm2, SolveCtrl *ctrl,
     ctrl->done = (max_cycles <= 0) ? 1 : 0;
 }
 
+// The solve's control block (and, at the end, its history) written into MAPPED PINNED host memory by a kernel instead
+// of a cudaMemcpyAsync: a device-to-host copy would queue on the DMA engine behind whatever bulk transfer another stream
+// has in flight (pmg_fetch_solution_begin: 2 GB, ~36 ms), and the host would learn that the solve has converged that
+// much later.  A store from a kernel does not pass through the copy engines.
+__global__ void __launch_bounds__(1024)
+    k_ctrl_to_host(const SolveCtrl *__restrict__ ctrl, SolveCtrl *host_ctrl, const double *__restrict__ hist2,
+                   double *host_hist, int hist_cap)
+{
+    pdl_prologue();
+    if (host_hist != nullptr) {
+        const int k = ctrl->cycles;
+        for (int i = threadIdx.x; i <= k && i < hist_cap; i += blockDim.x) host_hist[i] = hist2[i];
+    }
+    if (threadIdx.x == 0) *host_ctrl = *ctrl;
+    __threadfence_system();
+}
+
 // Last kernel of a cycle (MultiGridTestRunner.hpp:210-211 + the relative stopping test the reference lacks)
 __global__ void __launch_bounds__(1024)
     k_cycle_finish(const double *__restrict__ partials, int count, SolveCtrl *ctrl, double *__restrict__ hist2)
@@ -648,6 +665,13 @@ void launch_solve_begin(const double *d_norm2, SolveCtrl *ctrl, double *hist2, d
                         cudaStream_t st)
 {
     k_solve_begin<<<1, 1, 0, st>>>(d_norm2, ctrl, hist2, rel_tol, max_cycles);
+    count_launch();
+}
+
+void launch_ctrl_to_host(const SolveCtrl *ctrl, SolveCtrl *host_ctrl, const double *hist2, double *host_hist, int hist_cap,
+                         cudaStream_t st)
+{
+    launch_pdl(k_ctrl_to_host, dim3(1), dim3(host_hist ? 1024 : 32), 0, st, ctrl, host_ctrl, hist2, host_hist, hist_cap);
     count_launch();
 }
 

@@ -181,6 +181,10 @@ void launch_solve_begin(const double *d_norm2, SolveCtrl *ctrl, double *hist2, d
                         cudaStream_t st);
 // hist2[++cycles] = fixed-order sum of the partials; convergence test (skipped when already done)
 void launch_cycle_finish(const double *d_partials, int count, SolveCtrl *ctrl, double *hist2, cudaStream_t st);
+// *host_ctrl = *ctrl and (host_hist != nullptr) host_hist[0..cycles] = hist2[...], both in mapped pinned host memory,
+// written by a kernel: no copy engine involved (see k_ctrl_to_host)
+void launch_ctrl_to_host(const SolveCtrl *ctrl, SolveCtrl *host_ctrl, const double *hist2, double *host_hist, int hist_cap,
+                         cudaStream_t st);
 void launch_restrict(const double *fine, double *coarse, int nf, int nc, int pitch_f, int pitch_c,
                      cudaStream_t st);
 void launch_prolong_add(const double *coarse, double *fine, int nc, int nf, int pitch_c, int pitch_f,

@@ -33,7 +33,7 @@ def timing(sizes, rank, world, dev):
     ref_hist = {}
     for n in sizes:
         # (small-level kernel generation, halo prologue, middle graph [+ no interior/boundary split], phase trace)
-        combos = [(1, 0, 0, 0), (2, 0, 0, 0), (2, 1, 0, 0), (2, 0, 1, 0), (2, 1, 1, 0), (2, 1, 2, 0), (2, 0, 0, 1), (2, 1, 0, 1)]
+        combos = [(2, 0, 0, 0), (3, 0, 0, 0), (3, 1, 0, 0), (3, 1, 1, 0), (2, 1, 2, 0), (3, 1, 2, 0), (3, 1, 2, 1)]
         for small, prologue, graph, trace in combos:
             pmg.set_small_vcycle_version(small)
             pmg.set_halo_prologue(prologue)

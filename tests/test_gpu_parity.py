@@ -393,6 +393,57 @@ def test_cluster_kernel_matches_streaming_path_and_oracle(orc, n, kind, gamma, o
         assert np.array_equal(got[129][1], want)
 
 
+def _pinned(shape):
+    import ctypes
+    nbytes = int(np.prod(shape)) * 8
+    p = ctypes.c_void_p()
+    pmg.check(pmg.lib().pmg_host_alloc_pinned(ctypes.byref(p), nbytes))
+    buf = (ctypes.c_double * (nbytes // 8)).from_address(p.value)
+    return np.frombuffer(buf, dtype=np.float64).reshape(shape), p
+
+
+def test_overlapped_transfers_match_plain_path():
+    """pmg_stage_rhs / pmg_commit_rhs / pmg_fetch_solution_begin / _wait (both PCIe directions on copy streams of their
+    own beside the solver) over a stream of three different problems: every solution bit-identical to the plain
+    set_rhs / solve / get_solution path, and pmg_set_guess(NULL) is the zero start."""
+    n = 1025
+    fs = [cc.random_rhs(n, seed=80 + i) for i in range(3)]
+    plain = []
+    with pmg.Solver(n, omega=2.0 / 3.0) as s:
+        for f in fs:
+            s.set_rhs(f)
+            s.zero_guess()
+            k, hist = s.solve(pmg.V, rel_tol=1e-8, max_cycles=60)
+            plain.append((k, hist, s.get_solution()))
+    f_pin = [_pinned((n, n)) for _ in range(2)]
+    out_pin = [_pinned((n, n)) for _ in range(2)]
+    got = []
+    with pmg.Solver(n, omega=2.0 / 3.0) as s:
+        s.set_guess(np.ones((n, n)))  # must be replaced by the zero start below
+        f_pin[0][0][:] = fs[0]
+        s.stage_rhs(f_pin[0][0])
+        for k in range(3):
+            s.commit_rhs()
+            if k + 1 < 3:
+                f_pin[(k + 1) % 2][0][:] = fs[k + 1]
+                s.stage_rhs(f_pin[(k + 1) % 2][0])
+            s.set_guess(None)
+            kk, hist = s.solve(pmg.V, rel_tol=1e-8, max_cycles=60)
+            s.fetch_solution_wait()
+            if k > 0:
+                got[-1] = got[-1] + (out_pin[(k - 1) % 2][0].copy(),)
+            s.fetch_solution_begin(out_pin[k % 2][0])
+            got.append((kk, hist))
+        s.fetch_solution_wait()
+        got[-1] = got[-1] + (out_pin[2 % 2][0].copy(),)
+        with pytest.raises(pmg.PmgError):
+            s.commit_rhs()  # nothing staged
+    for (k0, h0, x0), (k1, h1, x1) in zip(plain, got):
+        assert k0 == k1 and np.array_equal(h0, h1) and np.array_equal(x0, x1)
+    for _, p in f_pin + out_pin:
+        pmg.lib().pmg_host_free_pinned(p)
+
+
 def test_scaling_by_two_is_exact():
     """Linearity in a form floating point honours exactly: f -> 2f doubles every iterate bit for bit."""
     n = 4097
