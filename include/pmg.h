@@ -78,6 +78,25 @@ typedef enum pmg_mem { PMG_MEM_HOST = 0, PMG_MEM_DEVICE = 1 } pmg_mem;
  * per norm and exists for validation. */
 typedef enum pmg_norm_mode { PMG_NORM_TREE = 0, PMG_NORM_SEQUENTIAL = 1 } pmg_norm_mode;
 
+/* Smoothers behind the reference's `Smoother` interface (Smoother.hpp:8-31), injected into the cycles like
+ * MultigridSolver's Smoother* (MultiGrid.hpp:12,22):
+ *   JACOBI     weighted Jacobi (omega = 1: JacobiSmoother, Smoother.hpp:33-117) -- the only one the fused engine runs;
+ *   RBGS       Gauss-Seidel in red-black order, the parallel form of GaussSeidelSmoother: same update expression
+ *              (Smoother.hpp:141-143), points with (x + y) even first, then the odd ones;
+ *   GS_LEX     GaussSeidelSmoother EXACTLY, lexicographic order included (anti-diagonal wavefront on one CTA): bit-identical
+ *              to the reference, a validation path -- ~2n dependent steps per sweep;
+ *   CHEBYSHEV  Chebyshev-Jacobi: the Jacobi sweep with per-sweep weights w_k = 1 / (d - c cos(pi (2k+1) / (2 nu))) for the
+ *              eigenvalue range [1/2, 2] of D^-1 A (d = 5/4, c = 3/4); omega is ignored.
+ * All but JACOBI run on the operator engine (one kernel per sweep / half sweep), single GPU.  Sweep counts are TRUE counts
+ * for every smoother (the reference's GaussSeidelSmoother loops `iter < num_iter`, its Jacobi `<=`; the C++ shims do the
+ * mapping). */
+typedef enum pmg_smoother {
+    PMG_SMOOTHER_JACOBI = 0,
+    PMG_SMOOTHER_RBGS = 1,
+    PMG_SMOOTHER_GS_LEX = 2,
+    PMG_SMOOTHER_CHEBYSHEV = 3
+} pmg_smoother;
+
 typedef enum pmg_engine {
     PMG_ENGINE_FUSED = 0,   /* temporally blocked streaming kernels (2 HBM passes per level visit)  */
     PMG_ENGINE_OPERATOR = 1 /* one kernel per reference operator (Parallel::Compute* granularity)  */
@@ -102,7 +121,11 @@ typedef struct pmg_config {
     int rank, n_ranks;
     int agglomerate_below; /* levels with n <= this are all-gathered and solved redundantly by every rank (513) */
     int norm_mode;       /* pmg_norm_mode: how the per-cycle residual norm is summed                */
-    int reserved[7];
+    int smoother;        /* pmg_smoother (0 = weighted Jacobi)                                       */
+    int smoother_fp32;   /* EXPERIMENT: 1 = the Jacobi smoother computes in fp32 (fields, residual */
+                         /* and grid transfers stay fp64; operator engine, one GPU).  Not parity: it shows  */
+                         /* where an fp32 smoother stops converging.  0 = fp64 (default)                    */
+    int reserved[5];
 } pmg_config;
 
 typedef struct pmg_solver pmg_solver; /* opaque */
@@ -169,6 +192,13 @@ pmg_status pmg_f_cycle_from(pmg_solver *s, const double *phi_init, const double 
  * output" the reference computes and discards (MultiGridTestRunner.hpp:210-212). */
 pmg_status pmg_solve(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max_cycles,
                      double *res_history, int *n_cycles_out);
+/* Conjugate gradients on A x = f from the current iterate, preconditioned by ONE multigrid cycle of this solver from a
+ * zero start (precond = 1: the solver's V-cycle -- smoother, sweep counts, prolongation as configured; use
+ * PMG_PROLONG_FULL, the reference prolongation is not the transpose of the restriction) or not at all (precond = 0: the
+ * iteration of ConjugateGradientSmoother, Smoother.hpp:170-256, from the given start).  res_history (nullable,
+ * max_iter + 1 doubles): [0] = ||r0||, [k] = ||r_k|| (recurrence residual); stops when ||r_k|| < rel_tol ||r0||.
+ * Single GPU.  SURVEY.md 8f-3: "CG as an outer Krylov wrapper preconditioned by one V-cycle". */
+pmg_status pmg_pcg(pmg_solver *s, int precond, double rel_tol, int max_iter, double *res_history, int *n_iter_out);
 /* device time of the last pmg_solve / pmg_cycle in milliseconds (CUDA events on the solver stream) */
 pmg_status pmg_last_device_ms(pmg_solver *s, double *ms_out);
 /* the CUDA stream (cudaStream_t) the solver launches on, for callers that time with their own events */
@@ -182,6 +212,10 @@ void *pmg_stream(pmg_solver *s);
  * but race-free (double buffered) unlike jacobi_kernel (Parallel_Method.cu:6-24). */
 pmg_status pmg_jacobi(double *x, const double *f, int width, int height, double h, double omega,
                       int sweeps, double *scratch, void *stream);
+/* `sweeps` Gauss-Seidel sweeps in place, GaussSeidelSmoother's update (Smoother.hpp:134-145): ordering 0 = lexicographic
+ * (the reference's, bit-identical; one CTA walks the anti-diagonals), 1 = red-black (parallel) */
+pmg_status pmg_gauss_seidel(double *x, const double *f, int width, int height, double h, int sweeps, int ordering,
+                            void *stream);
 /* r = f - A x on the interior (ring of r untouched); norm2_out (nullable, HOST pointer) = sum r^2 */
 pmg_status pmg_residual(double *r, const double *x, const double *f, int width, int height, double h,
                         double *norm2_out, void *stream);
@@ -189,6 +223,9 @@ pmg_status pmg_residual(double *r, const double *x, const double *f, int width, 
 pmg_status pmg_restrict_fw(const double *fine, double *coarse, int nf, int nc, void *stream);
 /* fine += P coarse (MultiGrid.hpp:208-226) */
 pmg_status pmg_prolong_add(const double *coarse, double *fine, int nc, int nf, int mode, void *stream);
+/* sum (a[i] - b[i])^2 and sum b[i]^2 over l entries -> HOST doubles: the pieces of Smoother::smooth's `errors` output,
+ * ||x - x_true|| / ||x_true|| (Smoother.hpp:92-98; DynamicGridUtils::compute_error + norm) */
+pmg_status pmg_diff_norm2(const double *a, const double *b, size_t l, double *diff2_out, double *b2_out, void *stream);
 /* sum v[i]^2 over l entries -> HOST double (DynamicGridUtils::norm squared, :21-27) */
 pmg_status pmg_norm2(const double *v, size_t l, double *norm2_out, void *stream);
 

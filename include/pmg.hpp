@@ -25,8 +25,13 @@
 #ifndef PMG_HPP
 #define PMG_HPP
 
+#include <sys/stat.h>
+#include <sys/types.h>
+
 #include <algorithm>
 #include <cmath>
+#include <fstream>
+#include <iostream>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -88,6 +93,45 @@ public:
 
 namespace compat {
 
+// ---- save_vector_err_file.hpp:10-92 -- the error-field dumps of the reference, same names, same file format ----
+// ./OUTPUT_RESULT/ERR_VECTOR/iteration_<10 i>.txt (one file per snapshot: the vector length on the first line, then one
+// component per line, default ostream formatting) and iteration_last_{cpu,gpu}.txt (every snapshot written to the same
+// file, so the last one survives -- as in the reference).
+inline void create_directory_if_not_exists_2(const std::string &path)
+{
+    struct stat info;
+    if (stat(path.c_str(), &info) != 0) mkdir(path.c_str(), 0777);
+}
+inline void write_error_vector_(const std::string &path, const std::vector<double> &v)
+{
+    std::ofstream file(path);
+    if (!file.is_open()) {
+        std::cerr << "Unable to open file for writing Jacobian errors.\n";
+        return;
+    }
+    file << v.size() << "\n";
+    for (const auto &e : v) file << e << "\n";
+}
+inline void save_errors_vector_to_file(const std::vector<std::vector<double>> &err_vect_iteration)
+{
+    create_directory_if_not_exists_2("./OUTPUT_RESULT");
+    create_directory_if_not_exists_2("./OUTPUT_RESULT/ERR_VECTOR");
+    for (size_t i = 0; i < err_vect_iteration.size(); i++)
+        write_error_vector_("./OUTPUT_RESULT/ERR_VECTOR/iteration_" + std::to_string(i * 10) + ".txt", err_vect_iteration[i]);
+}
+inline void save_errors_vector_to_file_last_iteration_cpu(const std::vector<std::vector<double>> &err_vect_iteration)
+{
+    create_directory_if_not_exists_2("./OUTPUT_RESULT");
+    create_directory_if_not_exists_2("./OUTPUT_RESULT/ERR_VECTOR");
+    for (const auto &v : err_vect_iteration) write_error_vector_("./OUTPUT_RESULT/ERR_VECTOR/iteration_last_cpu.txt", v);
+}
+inline void save_errors_vector_to_file_last_iteration_gpu(const std::vector<std::vector<double>> &err_vect_iteration)
+{
+    create_directory_if_not_exists_2("./OUTPUT_RESULT");
+    create_directory_if_not_exists_2("./OUTPUT_RESULT/ERR_VECTOR");
+    for (const auto &v : err_vect_iteration) write_error_vector_("./OUTPUT_RESULT/ERR_VECTOR/iteration_last_gpu.txt", v);
+}
+
 // ---- Smoother.hpp:8-31 ---------------------------------------------------------------------------------------
 class Smoother {
 protected:
@@ -99,6 +143,11 @@ public:
     void switch_test_mode() { test = true; }
     double eps() const { return epsilon; }
     virtual double omega() const { return 1.0; }
+    // which device smoother a MultigridSolver runs when this object is injected (pmg_smoother), and how many sweeps the
+    // reference's `num_iter` means for it: JacobiSmoother loops `iter <= num_iter` (Smoother.hpp:59), GaussSeidelSmoother
+    // and ConjugateGradientSmoother `iter < num_iter` (:134, :200)
+    virtual int kind() const { return PMG_SMOOTHER_JACOBI; }
+    virtual int sweeps_of(int num_iter) const { return num_iter + 1; }
     virtual void smooth(double *x, double *f, int width, int height, double h, int num_iter,
                         double *x_true = nullptr, std::vector<double> *residuals = nullptr,
                         std::vector<double> *errors = nullptr) = 0;
@@ -106,27 +155,48 @@ public:
 };
 
 // Smoother.hpp:33-117 with the weight the reference lacks; omega == 1 is JacobiSmoother bit for bit.
-// HOST pointers.  num_iter+1 sweeps; after every sweep ||f - A x|| is appended to `residuals` and the loop
-// stops early when it drops below epsilon (Smoother.hpp:75-88).  `errors` / x_true / test are plotting hooks
-// of the part-1 study and are not produced here (out of scope).
+// HOST pointers.  num_iter+1 sweeps; after every sweep ||f - A x|| is appended to `residuals` and the loop stops early
+// when it drops below epsilon (Smoother.hpp:75-88).  With x_true: ||x - x_true|| / ||x_true|| after every sweep goes to
+// `errors` (:92-98); in test mode (switch_test_mode) the error FIELD x - x_true is snapshotted before the first sweep and
+// after every sweep whose index is a multiple of 10 and written with save_errors_vector_to_file at the end (:50-57,
+// :100-115).  All of it is computed on the device; only the snapshots and the final x cross PCIe.
 class WeightedJacobiSmoother : public Smoother {
     double w_;
 
 public:
     explicit WeightedJacobiSmoother(double eps = 1e-6, double omega = 1.0) : Smoother(eps), w_(omega) {}
     double omega() const override { return w_; }
-    void smooth(double *x, double *f, int width, int height, double h, int num_iter, double * = nullptr,
-                std::vector<double> *residuals = nullptr, std::vector<double> * = nullptr) override
+    void smooth(double *x, double *f, int width, int height, double h, int num_iter, double *x_true = nullptr,
+                std::vector<double> *residuals = nullptr, std::vector<double> *errors = nullptr) override
     {
-        const size_t bytes = (size_t)width * height * sizeof(double);
-        void *dx = nullptr, *df = nullptr, *ds = nullptr;
-        check(pmg_device_alloc(&dx, bytes));
-        check(pmg_device_alloc(&df, bytes));
-        check(pmg_device_alloc(&ds, bytes));
+        const size_t l = (size_t)width * height, bytes = l * sizeof(double);
+        void *dx = nullptr, *df = nullptr, *ds = nullptr, *dt = nullptr;
+        const bool want_err = x_true != nullptr && (errors != nullptr || test);
+        std::vector<std::vector<double>> err_vect_iteration;
+        auto cleanup = [&]() {
+            pmg_device_free(dx);
+            pmg_device_free(df);
+            pmg_device_free(ds);
+            pmg_device_free(dt);
+        };
         try {
+            check(pmg_device_alloc(&dx, bytes));
+            check(pmg_device_alloc(&df, bytes));
+            check(pmg_device_alloc(&ds, bytes));
             check(pmg_memcpy(dx, x, bytes, 1, 0));
             check(pmg_memcpy(df, f, bytes, 1, 0));
-            const bool per_sweep = residuals != nullptr || epsilon > 0.0;
+            if (want_err) {
+                check(pmg_device_alloc(&dt, bytes));
+                check(pmg_memcpy(dt, x_true, bytes, 1, 0));
+            }
+            auto snapshot = [&]() {  // error field x - x_true (DynamicGridUtils::compute_error)
+                std::vector<double> cur(l);
+                check(pmg_memcpy(cur.data(), dx, bytes, 0, 1));
+                for (size_t i = 0; i < l; ++i) cur[i] -= x_true[i];
+                err_vect_iteration.push_back(std::move(cur));
+            };
+            if (test && x_true) snapshot();
+            const bool per_sweep = residuals != nullptr || epsilon > 0.0 || want_err;
             if (!per_sweep) {
                 check(pmg_jacobi((double *)dx, (double *)df, width, height, h, w_, num_iter + 1, (double *)ds, nullptr));
             } else {
@@ -137,24 +207,101 @@ public:
                     double rn = std::sqrt(n2);
                     if (residuals) residuals->push_back(rn);
                     if (rn < epsilon) break;
+                    if (errors && x_true) {
+                        double d2 = 0.0, t2 = 0.0;
+                        check(pmg_diff_norm2((double *)dx, (double *)dt, l, &d2, &t2, nullptr));
+                        errors->push_back(std::sqrt(d2) / std::sqrt(t2));
+                    }
+                    if (test && x_true && it % 10 == 0) snapshot();
                 }
             }
             check(pmg_memcpy(x, dx, bytes, 0, 1));
         } catch (...) {
-            pmg_device_free(dx);
-            pmg_device_free(df);
-            pmg_device_free(ds);
+            cleanup();
             throw;
         }
-        pmg_device_free(dx);
-        pmg_device_free(df);
-        pmg_device_free(ds);
+        cleanup();
+        if (test && x_true) save_errors_vector_to_file(err_vect_iteration);
     }
 };
 
 class JacobiSmoother : public WeightedJacobiSmoother {
 public:
     explicit JacobiSmoother(double eps = 1e-6) : WeightedJacobiSmoother(eps, 1.0) {}
+};
+
+// ---- Smoother.hpp:119-168 ------------------------------------------------------------------------------------
+// GaussSeidelSmoother, EXACT: the reference's lexicographic order is reproduced on the device (anti-diagonal wavefront),
+// so x and the per-sweep residuals are the reference's bit for bit -- a validation path (2n dependent steps per sweep).
+// HOST pointers; `num_iter` sweeps; after every sweep ||f - A x|| goes to `residuals` and the loop stops below epsilon.
+class GaussSeidelSmoother : public Smoother {
+protected:
+    int ordering_ = 0;  // pmg_gauss_seidel: 0 lexicographic, 1 red-black
+
+public:
+    explicit GaussSeidelSmoother(double eps = 1e-6) : Smoother(eps) {}
+    int kind() const override { return PMG_SMOOTHER_GS_LEX; }
+    int sweeps_of(int num_iter) const override { return num_iter; }
+    void smooth(double *x, double *f, int width, int height, double h, int num_iter, double * = nullptr,
+                std::vector<double> *residuals = nullptr, std::vector<double> * = nullptr) override
+    {
+        const size_t bytes = (size_t)width * height * sizeof(double);
+        void *dx = nullptr, *df = nullptr;
+        check(pmg_device_alloc(&dx, bytes));
+        if (pmg_device_alloc(&df, bytes) != PMG_OK) {
+            pmg_device_free(dx);
+            throw Error(PMG_ERR_ALLOC, "device allocation failed");
+        }
+        try {
+            check(pmg_memcpy(dx, x, bytes, 1, 0));
+            check(pmg_memcpy(df, f, bytes, 1, 0));
+            for (int it = 0; it < num_iter; ++it) {  // Smoother.hpp:134: `<`
+                check(pmg_gauss_seidel((double *)dx, (double *)df, width, height, h, 1, ordering_, nullptr));
+                double n2 = 0.0;
+                check(pmg_residual(nullptr, (double *)dx, (double *)df, width, height, h, &n2, nullptr));
+                const double rn = std::sqrt(n2);
+                if (residuals) residuals->push_back(rn);
+                if (rn < epsilon) break;
+            }
+            check(pmg_memcpy(x, dx, bytes, 0, 1));
+        } catch (...) {
+            pmg_device_free(dx);
+            pmg_device_free(df);
+            throw;
+        }
+        pmg_device_free(dx);
+        pmg_device_free(df);
+    }
+};
+
+// The parallel form of the same smoother: red-black ordering (not in the reference; same update expression).
+class RedBlackGaussSeidelSmoother : public GaussSeidelSmoother {
+public:
+    explicit RedBlackGaussSeidelSmoother(double eps = 0.0) : GaussSeidelSmoother(eps) { ordering_ = 1; }
+    int kind() const override { return PMG_SMOOTHER_RBGS; }
+};
+
+// Chebyshev-Jacobi (not in the reference): num_iter + 1 Jacobi sweeps with the Chebyshev weights of pmg.h.
+class ChebyshevJacobiSmoother : public Smoother {
+public:
+    explicit ChebyshevJacobiSmoother() : Smoother(0.0) {}
+    int kind() const override { return PMG_SMOOTHER_CHEBYSHEV; }
+    static std::vector<double> weights(int n)
+    {
+        std::vector<double> w((size_t)n);
+        const double d = 1.25, c = 0.75;
+        for (int k = 0; k < n; ++k) w[(size_t)k] = 1.0 / (d - c * std::cos(M_PI * (2 * k + 1) / (2.0 * n)));
+        return w;
+    }
+    void smooth(double *x, double *f, int width, int height, double h, int num_iter, double * = nullptr,
+                std::vector<double> *residuals = nullptr, std::vector<double> * = nullptr) override
+    {
+        const std::vector<double> w = weights(num_iter + 1);
+        for (double wk : w) {
+            WeightedJacobiSmoother one(0.0, wk);
+            one.smooth(x, f, width, height, h, 0, nullptr, residuals);
+        }
+    }
 };
 
 // ---- 2_part_MG/MultiGrid.hpp:9-183 ---------------------------------------------------------------------------
@@ -173,21 +320,28 @@ class MultigridSolver {
     Smoother *smoother;
     int alpha;
     int N_final;
-    // (N, v1, v2, N_coarse, prolong_mode, alpha, omega, eps) -> hierarchy
-    typedef std::tuple<int, int, int, int, int, int, double, double> Key;
+    // (N, v1, v2, N_coarse, prolong_mode, alpha, omega, eps, smoother kind) -> hierarchy
+    typedef std::tuple<int, int, int, int, int, int, double, double, int> Key;
     std::map<Key, Solver *> solvers_;
 
     Solver &get(int N)
     {
         const double w = smoother ? smoother->omega() : 1.0;
-        const double eps = (smoother && honour_smoother_eps) ? smoother->eps() : 0.0;
-        Key key(N, v1, v2, N_coarse, prolong_mode, alpha, w, eps);
+        const int kind = smoother ? smoother->kind() : PMG_SMOOTHER_JACOBI;
+        const bool has_eps = kind == PMG_SMOOTHER_JACOBI || kind == PMG_SMOOTHER_GS_LEX;  // the reference's two
+        const double eps = (smoother && honour_smoother_eps && has_eps) ? smoother->eps() : 0.0;
+        Key key(N, v1, v2, N_coarse, prolong_mode, alpha, w, eps, kind);
         auto it = solvers_.find(key);
         if (it != solvers_.end()) return *it->second;
         pmg_config c;
         pmg_config_default(&c, N);
-        c.nu1 = v1 + 1;
-        c.nu2 = v2 + 1;
+        // the cycles call smoother->smooth(..., v1) / (..., v2) / (..., 10) / (..., 3) (MultiGrid.hpp:66,89,61,153): what
+        // those counts mean is the injected smoother's business
+        c.nu1 = smoother ? smoother->sweeps_of(v1) : v1 + 1;
+        c.nu2 = smoother ? smoother->sweeps_of(v2) : v2 + 1;
+        c.coarse_sweeps = smoother ? smoother->sweeps_of(10) : 11;
+        c.fmg_sweeps = smoother ? smoother->sweeps_of(3) : 4;
+        c.smoother = kind;
         c.omega = w;
         c.smoother_eps = eps;
         c.gamma = alpha;
@@ -264,6 +418,39 @@ public:
     // Not in the reference: one full-multigrid pass for an arbitrary right-hand side f and the Dirichlet ring of phi
     // (PMG_CYCLE_FMG in pmg.h); phi's interior is restarted from zero.  Same signature as v_cycle.
     void fmg_cycle(double *phi, const double *f, int N, double /*h*/) { run(PMG_CYCLE_FMG, phi, f, N); }
+};
+
+// ---- Smoother.hpp:170-256 ------------------------------------------------------------------------------------
+// ConjugateGradientSmoother: x is ZEROED (:186), then at most num_iter CG steps; `residuals` receives ||r|| before the
+// first and after every step, the loop stops when it drops below epsilon.  HOST pointers, square fields (the device
+// hierarchy is square).  Same Krylov iterates as the reference; it recomputes r = f - A x after every step where the
+// device wrapper (pmg_pcg, precond = 0) carries the recurrence, so the numbers agree to rounding (~1e-10), not bit for
+// bit.  precondition_with_vcycle = true is the wrapper SURVEY.md 8f-3 asks for: one V-cycle per step as preconditioner.
+class ConjugateGradientSmoother : public Smoother {
+public:
+    bool precondition_with_vcycle = false;
+    double omega_precond = 2.0 / 3.0;
+    explicit ConjugateGradientSmoother(double eps = 1e-6) : Smoother(eps) {}
+    int sweeps_of(int num_iter) const override { return num_iter; }
+    void smooth(double *x, double *f, int width, int height, double /*h*/, int num_iter, double * = nullptr,
+                std::vector<double> *residuals = nullptr, std::vector<double> * = nullptr) override
+    {
+        if (width != height) throw Error(PMG_ERR_UNSUPPORTED, "ConjugateGradientSmoother: square grids only");
+        pmg_config c;
+        pmg_config_default(&c, width);
+        c.omega = omega_precond;
+        c.prolong_mode = PMG_PROLONG_FULL;
+        Solver s(c);
+        s.set_rhs(f);
+        s.set_guess(nullptr);
+        const double r0 = s.residual_norm();
+        std::vector<double> hist((size_t)num_iter + 1);
+        int k = 0;
+        const double rel = (epsilon > 0.0 && r0 > 0.0) ? epsilon / r0 : 0.0;
+        check(pmg_pcg(s.get(), precondition_with_vcycle ? 1 : 0, rel, num_iter, hist.data(), &k));
+        if (residuals) residuals->insert(residuals->end(), hist.begin(), hist.begin() + k + 1);
+        s.get_solution(x);
+    }
 };
 
 // ---- 3_part_parallel/Parallel_Method.cu:140-199 -----------------------------------------------------------------

@@ -60,6 +60,33 @@ enum { ORC_PROLONG_REFERENCE = 0, ORC_PROLONG_FULL = 1 };
 ORC_DECLARE(orc_)
 ORC_DECLARE(ref_)
 
+/* ---- smoothers beyond weighted Jacobi and the Krylov wrapper: pmg_oracle_smoothers.c ------------- */
+enum { ORC_SMOOTHER_JACOBI = 0, ORC_SMOOTHER_RBGS = 1, ORC_SMOOTHER_GS_LEX = 2, ORC_SMOOTHER_CHEBYSHEV = 3 };
+/* Chebyshev-Jacobi smooths the upper part of the spectrum of D^-1 A (eigenvalues in (0, 2)): [1/2, 2] in 2-D */
+#define ORC_CHEB_LO 0.5
+#define ORC_CHEB_HI 2.0
+#define ORC_DECLARE_SMOOTHERS(P)                                                                                      \
+    /* GaussSeidelSmoother::smooth (Smoother.hpp:119-168): num_iter lexicographic sweeps (its loop is `<`), eps    */ \
+    /* exit; residuals (nullable) gets the per-sweep ||r||; returns the sweeps done                                */ \
+    int P##gs(double *x, const double *f, int width, int height, double h, int num_iter, double eps,                  \
+              double *residuals);                                                                                     \
+    /* one V- or W-cycle with the smoother injected through the reference's Smoother* slot; TRUE sweep counts;     */ \
+    /* -1 where the library has no such smoother                                                                   */ \
+    int P##cycle_s(double *phi, const double *f, int n, double h, int kind, int smoother, double omega, int alpha,     \
+                   int nu1, int nu2, int coarse_sweeps, int prolong_mode);                                            \
+    /* ConjugateGradientSmoother::smooth (Smoother.hpp:170-256): x is zeroed, num_iter CG steps, eps exit;          */ \
+    /* residuals gets ||r|| before the first and after every step; returns how many were written                   */ \
+    int P##cg(double *x, const double *f, int width, int height, double h, int num_iter, double eps,                  \
+              double *residuals);
+ORC_DECLARE_SMOOTHERS(orc_)
+ORC_DECLARE_SMOOTHERS(ref_)
+/* not in the reference (the ref_ library has no counterpart) */
+int orc_rbgs(double *x, const double *f, int width, int height, double h, int sweeps);
+int orc_jacobi_weights(double *x, const double *f, int width, int height, double h, const double *w, int sweeps);
+void orc_chebyshev_weights(double lo, double hi, int n, double *w);
+int orc_pcg(double *x, const double *f, int n, double h, int precond, int smoother, double omega, int nu1, int nu2,
+            int coarse_sweeps, int prolong_mode, double rel_tol, int max_iter, double *hist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -208,6 +208,45 @@ int ref_solve(double *phi, const double *f, int n, int kind, double omega, doubl
     return k;
 }
 
+/* ---- smoothers beyond Jacobi: the reference's own classes (Smoother.hpp:119-256), unmodified ---- */
+int ref_gs(double *x, const double *f, int width, int height, double h, int num_iter, double eps, double *residuals)
+{
+    GaussSeidelSmoother gs(eps);
+    std::vector<double> res;
+    gs.smooth(x, const_cast<double *>(f), width, height, h, num_iter, nullptr, &res);
+    if (residuals) std::copy(res.begin(), res.end(), residuals);
+    return (int)res.size();
+}
+
+/* MultigridSolver with a GaussSeidelSmoother injected (MultiGrid.hpp:12,22).  The reference hard-codes the coarsest
+ * solve as smooth(..., 10) (:61), which for this smoother means 10 sweeps: only that count is available. */
+int ref_cycle_s(double *phi, const double *f, int n, double h, int kind, int smoother, double omega, int alpha, int nu1,
+                int nu2, int coarse_sweeps, int prolong_mode)
+{
+    (void)omega;
+    if (smoother != ORC_SMOOTHER_GS_LEX || prolong_mode != ORC_PROLONG_REFERENCE || coarse_sweeps != 10) return -1;
+    if (kind != ORC_CYCLE_V && kind != ORC_CYCLE_W) return -1;
+    GaussSeidelSmoother gs(0.0);
+    MultigridSolver mg(&gs, alpha, n);
+    mg.v1 = nu1;  /* GaussSeidelSmoother's loop is `iter < num_iter`: num_iter IS the sweep count */
+    mg.v2 = nu2;
+    if (kind == ORC_CYCLE_V)
+        mg.v_cycle(phi, f, n, h);
+    else
+        mg.w_cycle(phi, f, n, h);
+    delete[] mg.final_solution;
+    return 0;
+}
+
+int ref_cg(double *x, const double *f, int width, int height, double h, int num_iter, double eps, double *residuals)
+{
+    ConjugateGradientSmoother cg(eps);
+    std::vector<double> res;
+    cg.smooth(x, const_cast<double *>(f), width, height, h, num_iter, nullptr, &res);
+    if (residuals) std::copy(res.begin(), res.end(), residuals);
+    return (int)res.size();
+}
+
 /* general-RHS FMG is not a reference function (oracle.h) */
 int ref_fmg_general(double *, const double *, int, double, double, int, int, int) { return -1; }
 

@@ -26,6 +26,7 @@ PROLONG_REFERENCE, PROLONG_FULL = 0, 1
 ENGINE_FUSED, ENGINE_OPERATOR = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 NORM_TREE, NORM_SEQUENTIAL = 0, 1
+SMOOTHER_JACOBI, SMOOTHER_RBGS, SMOOTHER_GS_LEX, SMOOTHER_CHEBYSHEV = 0, 1, 2, 3
 OK = 0
 STATUS_NAMES = {0: "PMG_OK", 1: "PMG_ERR_INVALID", 2: "PMG_ERR_CUDA", 3: "PMG_ERR_NO_DEVICE",
                 4: "PMG_ERR_ALLOC", 5: "PMG_ERR_COMM", 6: "PMG_ERR_UNSUPPORTED"}
@@ -44,7 +45,7 @@ class Config(ctypes.Structure):
                 ("prolong_mode", ctypes.c_int), ("engine", ctypes.c_int),
                 ("smoother_eps", ctypes.c_double), ("device", ctypes.c_int), ("use_graph", ctypes.c_int),
                 ("rank", ctypes.c_int), ("n_ranks", ctypes.c_int), ("agglomerate_below", ctypes.c_int),
-                ("norm_mode", ctypes.c_int), ("reserved", ctypes.c_int * 7)]
+                ("norm_mode", ctypes.c_int), ("smoother", ctypes.c_int), ("smoother_fp32", ctypes.c_int), ("reserved", ctypes.c_int * 5)]
 
 
 # every symbol include/pmg.h declares (tests/test_abi.py checks the library exports all of them)
@@ -52,8 +53,8 @@ ABI_SYMBOLS = [
     "pmg_version", "pmg_last_error", "pmg_status_string", "pmg_config_default", "pmg_kernel_launches",
     "pmg_create", "pmg_destroy", "pmg_set_rhs", "pmg_set_guess", "pmg_get_solution", "pmg_zero_guess",
     "pmg_stage_rhs", "pmg_commit_rhs", "pmg_fetch_solution_begin", "pmg_fetch_solution_wait",
-    "pmg_set_rhs_sine", "pmg_residual_norm", "pmg_cycle", "pmg_restrict_to_level", "pmg_f_cycle_from", "pmg_solve", "pmg_last_device_ms", "pmg_stream",
-    "pmg_jacobi", "pmg_residual", "pmg_restrict_fw", "pmg_prolong_add", "pmg_norm2", "pmg_release_scratch",
+    "pmg_set_rhs_sine", "pmg_residual_norm", "pmg_cycle", "pmg_restrict_to_level", "pmg_f_cycle_from", "pmg_solve", "pmg_pcg", "pmg_last_device_ms", "pmg_stream",
+    "pmg_jacobi", "pmg_gauss_seidel", "pmg_residual", "pmg_restrict_fw", "pmg_prolong_add", "pmg_diff_norm2", "pmg_norm2", "pmg_release_scratch",
     "pmg_device_alloc", "pmg_device_free", "pmg_host_alloc_pinned", "pmg_host_free_pinned", "pmg_memcpy",
     "pmg_device_synchronize", "pmg_device_count",
     "pmg_comm_unique_id", "pmg_comm_init", "pmg_comm_finalize", "pmg_partition_rows",
@@ -330,6 +331,17 @@ class Solver:
         check(lib().pmg_solve(self._h, kind, rel_tol, max_cycles, hist, ctypes.byref(k)))
         return k.value, np.array(hist[: k.value + 1])
 
+    def pcg(self, precond=1, rel_tol=1e-8, max_iter=100):
+        """Conjugate gradients from the current iterate, preconditioned by one cycle of this solver (precond = 1) or not
+        at all (0); returns (iterations, history)."""
+        hist = (ctypes.c_double * (max_iter + 1))()
+        k = ctypes.c_int()
+        L = lib()
+        L.pmg_pcg.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                              ctypes.POINTER(ctypes.c_int)]
+        check(L.pmg_pcg(self._h, precond, rel_tol, max_iter, hist, ctypes.byref(k)))
+        return k.value, np.array(hist[: k.value + 1])
+
     def smooth(self, sweeps, block=1):
         check(lib().pmg_smooth(self._h, sweeps, block))
 
@@ -370,6 +382,14 @@ def residual(r, x, f, h, want_norm2=False):
     check(lib().pmg_residual(r.ptr if r is not None else None, x.ptr, f.ptr, x.shape[1], x.shape[0], h,
                              ctypes.byref(v) if want_norm2 else None, None))
     return v.value if want_norm2 else None
+
+
+def gauss_seidel(x, f, h, sweeps=1, ordering=0):
+    """Gauss-Seidel sweeps in place: ordering 0 = lexicographic (the reference's GaussSeidelSmoother, exact), 1 = red-black."""
+    L = lib()
+    L.pmg_gauss_seidel.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    check(L.pmg_gauss_seidel(x.ptr, f.ptr, x.shape[1], x.shape[0], h, sweeps, ordering, None))
 
 
 def restrict_fw(fine, coarse):

@@ -464,6 +464,158 @@ __global__ void __launch_bounds__(BX *BY)
     if (x < nx && y < ny) f[(size_t)y * pitch + x] = dmul(dmul(factor, sx[x]), sy[y]);
 }
 
+// ---- smoothers beyond weighted Jacobi ----------------------------------------------------------
+// GaussSeidelSmoother's update (Smoother.hpp:141-143): x = 0.25 * (x[i-1] + x[i+1] + x[i-width] + x[i+width] + h*h*f)
+__device__ __forceinline__ double gs_point(double h2, double f, double xw, double xe, double xs, double xn)
+{
+    return dmul(0.25, dadd(dadd(dadd(dadd(xw, xe), xs), xn), dmul(h2, f)));
+}
+
+// one colour of a red-black Gauss-Seidel sweep, in place: the points with (x + y) & 1 == colour read only points of the
+// other colour, so every point of a colour can be updated at once -- the parallel form of the reference's smoother
+__global__ void __launch_bounds__(BX *BY)
+    k_rbgs_half(double *__restrict__ x, const double *__restrict__ f, int nx, int ny, int pitch_x, int pitch_f, double h2,
+                int colour)
+{
+    const int y = blockIdx.y * BY + threadIdx.y;
+    const int xx = 2 * (blockIdx.x * BX + threadIdx.x) + ((y + colour) & 1);
+    if (xx < 1 || xx > nx - 2 || y < 1 || y > ny - 2) return;
+    double *c = x + (size_t)y * pitch_x + xx;
+    *c = gs_point(h2, f[(size_t)y * pitch_f + xx], c[-1], c[1], c[-pitch_x], c[pitch_x]);
+}
+
+// GaussSeidelSmoother::smooth (Smoother.hpp:134-145) EXACTLY, lexicographic order included: the points of one
+// anti-diagonal x + y = d depend only on diagonal d-1 (new west and south values) and d+1 (old east and north values), so
+// a sweep is 2n-5 dependent steps, each parallel along its diagonal.  One CTA walks the diagonals with a barrier in
+// between -- a validation path for the reference's part-1 smoother (its sizes are N <= 129), not a fast smoother:
+// use the red-black ordering for that.
+__global__ void __launch_bounds__(1024)
+    k_gs_lex(double *__restrict__ x, const double *__restrict__ f, int nx, int ny, int pitch_x, int pitch_f, double h2,
+             int sweeps)
+{
+    for (int s = 0; s < sweeps; ++s)
+        for (int d = 2; d <= (nx - 2) + (ny - 2); ++d) {
+            const int ylo = max(1, d - (nx - 2)), yhi = min(ny - 2, d - 1);
+            for (int y = ylo + (int)threadIdx.x; y <= yhi; y += (int)blockDim.x) {
+                double *c = x + (size_t)y * pitch_x + (d - y);
+                *c = gs_point(h2, f[(size_t)y * pitch_f + (d - y)], c[-1], c[1], c[-pitch_x], c[pitch_x]);
+            }
+            __syncthreads();
+        }
+}
+
+// Mixed-precision EXPERIMENT: the weighted-Jacobi sweep evaluated in fp32 -- operands rounded to float,
+// the reference's expression order kept, result widened again -- while the fields stay fp64 in HBM and the residual and
+// the grid transfers stay fp64.  It answers "what would fp32 smoothing do to the convergence history" without an fp32
+// copy of the hierarchy; it does not save bandwidth (an fp32 hierarchy would halve the 24 B/point of a sweep).
+__global__ void __launch_bounds__(BX *BY)
+    k_jacobi_sweep_f32(double *__restrict__ out, const double *__restrict__ in, const double *__restrict__ f, int nx, int ny,
+                       int pitch_x, int pitch_f, float h2, float omega, float om1, int weighted)
+{
+    const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    const size_t i = (size_t)y * pitch_x + x;
+    if (x == 0 || y == 0 || x == nx - 1 || y == ny - 1) {
+        out[i] = in[i];
+        return;
+    }
+    const float xc = (float)in[i], xw = (float)in[i - 1], xe = (float)in[i + 1], xs = (float)in[i - pitch_x],
+                xn = (float)in[i + pitch_x], ff = (float)f[(size_t)y * pitch_f + x];
+    const float acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(h2, ff), xw), xe), xs), xn);
+    const float jac = __fmul_rn(0.25f, acc);
+    out[i] = (double)(weighted ? __fadd_rn(__fmul_rn(om1, xc), __fmul_rn(omega, jac)) : jac);
+}
+
+// sum over l entries of (a[i] - b[i])^2 and of b[i]^2: the relative error norm of Smoother::smooth's `errors` output
+// (Smoother.hpp:92-98: ||x - x_true|| / ||x_true||, DynamicGridUtils::compute_error + norm)
+__global__ void __launch_bounds__(RED_THREADS)
+    k_diff_norm2(const double *__restrict__ a, const double *__restrict__ b, size_t l, double *__restrict__ partials_d,
+                 double *__restrict__ partials_b)
+{
+    double accd = 0.0, accb = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < l; i += (size_t)gridDim.x * blockDim.x) {
+        const double d = dsub(a[i], b[i]);
+        accd = dadd(accd, dmul(d, d));
+        accb = dadd(accb, dmul(b[i], b[i]));
+    }
+    accd = block_sum(accd);
+    accb = block_sum(accb);
+    if (threadIdx.x == 0) {
+        partials_d[blockIdx.x] = accd;
+        partials_b[blockIdx.x] = accb;
+    }
+}
+
+// ---- vector kernels of the preconditioned conjugate gradient wrapper (pmg_pcg); padded 2-D arrays, interior only ----
+// ap = A p = (4p - W - E - S - N) / (h*h)  (DynamicGridUtils::apply_laplacian, DynamicGridUtils.hpp:46-56: a DIVISION),
+// and the partial sums of p . ap
+__global__ void __launch_bounds__(RED_THREADS)
+    k_apply_a_dot(const double *__restrict__ p, double *__restrict__ ap, int nx, int ny, int pitch, double h2,
+                  double *__restrict__ partials)
+{
+    double acc = 0.0;
+    const int chunks_x = (nx + RED_THREADS - 1) / RED_THREADS;
+    for (long c = blockIdx.x; c < (long)chunks_x * ny; c += gridDim.x) {
+        const int y = (int)(c / chunks_x), xx = (int)(c % chunks_x) * RED_THREADS + threadIdx.x;
+        if (xx >= 1 && xx <= nx - 2 && y >= 1 && y <= ny - 2) {
+            const double *q = p + (size_t)y * pitch + xx;
+            const double t = dsub(dsub(dsub(dsub(dmul(4.0, q[0]), q[-1]), q[1]), q[-pitch]), q[pitch]);
+            const double v = __ddiv_rn(t, h2);
+            ap[(size_t)y * pitch + xx] = v;
+            acc = dadd(acc, dmul(q[0], v));
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// partial sums of a . b over the interior
+__global__ void __launch_bounds__(RED_THREADS)
+    k_dot_interior(const double *__restrict__ a, const double *__restrict__ b, int nx, int ny, int pitch,
+                   double *__restrict__ partials)
+{
+    double acc = 0.0;
+    const int chunks_x = (nx + RED_THREADS - 1) / RED_THREADS;
+    for (long c = blockIdx.x; c < (long)chunks_x * ny; c += gridDim.x) {
+        const int y = (int)(c / chunks_x), xx = (int)(c % chunks_x) * RED_THREADS + threadIdx.x;
+        if (xx >= 1 && xx <= nx - 2 && y >= 1 && y <= ny - 2)
+            acc = dadd(acc, dmul(a[(size_t)y * pitch + xx], b[(size_t)y * pitch + xx]));
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// x += alpha p ; r -= alpha ap ; partial sums of r . r
+__global__ void __launch_bounds__(RED_THREADS)
+    k_pcg_update(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p, const double *__restrict__ ap,
+                 int nx, int ny, int pitch, double alpha, double *__restrict__ partials)
+{
+    double acc = 0.0;
+    const int chunks_x = (nx + RED_THREADS - 1) / RED_THREADS;
+    for (long c = blockIdx.x; c < (long)chunks_x * ny; c += gridDim.x) {
+        const int y = (int)(c / chunks_x), xx = (int)(c % chunks_x) * RED_THREADS + threadIdx.x;
+        if (xx >= 1 && xx <= nx - 2 && y >= 1 && y <= ny - 2) {
+            const size_t i = (size_t)y * pitch + xx;
+            x[i] = dadd(x[i], dmul(alpha, p[i]));
+            const double rv = dsub(r[i], dmul(alpha, ap[i]));
+            r[i] = rv;
+            acc = dadd(acc, dmul(rv, rv));
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// p = z + beta p  (beta == 0 with first == 1: p = z)
+__global__ void __launch_bounds__(BX *BY)
+    k_pcg_direction(double *__restrict__ p, const double *__restrict__ z, int nx, int ny, int pitch, double beta, int first)
+{
+    const int xx = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y;
+    if (xx < 1 || xx > nx - 2 || y < 1 || y > ny - 2) return;
+    const size_t i = (size_t)y * pitch + xx;
+    p[i] = first ? z[i] : dadd(z[i], dmul(beta, p[i]));
+}
+
 // ---- NVLink peer-to-peer halo exchange ----------------------------------------------------------------------
 __global__ void k_halo_signal(int *up_flag, int *dn_flag, int epoch)
 {
@@ -770,6 +922,82 @@ void launch_norm2(const double *v, size_t l, double *d_partials, double *d_out, 
     k_norm2<<<blocks, RED_THREADS, 0, st>>>(v, l, d_partials);
     count_launch();
     launch_final_sum(d_partials, blocks, d_out, st);
+}
+
+void launch_jacobi_sweep_f32(double *out, const double *in, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h,
+                             double omega, cudaStream_t st)
+{
+    k_jacobi_sweep_f32<<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(out, in, f, nx, ny, pitch_x, pitch_f, (float)(h * h),
+                                                                  (float)omega, (float)(1.0 - omega), omega != 1.0 ? 1 : 0);
+    count_launch();
+}
+
+// d_out[0] = sum (a - b)^2, d_out[1] = sum b^2 ; d_partials: 2 * reduce_partials() doubles
+void launch_diff_norm2(const double *a, const double *b, size_t l, double *d_partials, double *d_out, cudaStream_t st)
+{
+    size_t want = (l + RED_THREADS - 1) / RED_THREADS;
+    int blocks = (int)(want < (size_t)RED_BLOCKS ? want : (size_t)RED_BLOCKS);
+    if (blocks < 1) blocks = 1;
+    k_diff_norm2<<<blocks, RED_THREADS, 0, st>>>(a, b, l, d_partials, d_partials + RED_BLOCKS);
+    count_launch();
+    launch_final_sum(d_partials, blocks, d_out, st);
+    launch_final_sum(d_partials + RED_BLOCKS, blocks, d_out + 1, st);
+}
+
+void launch_rbgs_half(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h, int colour,
+                      cudaStream_t st)
+{
+    k_rbgs_half<<<grid2d((nx + 1) / 2 + 1, ny), dim3(BX, BY), 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, h * h, colour);
+    count_launch();
+}
+
+void launch_gs_lex(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h, int sweeps, cudaStream_t st)
+{
+    if (sweeps <= 0) return;
+    int threads = ((min(nx, ny) + 31) / 32) * 32;
+    threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
+    k_gs_lex<<<1, threads, 0, st>>>(x, f, nx, ny, pitch_x, pitch_f, h * h, sweeps);
+    count_launch();
+}
+
+static int red_blocks_for(int nx, int ny)
+{
+    long chunks = (long)((nx + RED_THREADS - 1) / RED_THREADS) * ny;
+    int blocks = (int)(chunks < RED_BLOCKS ? chunks : RED_BLOCKS);
+    return blocks < 1 ? 1 : blocks;
+}
+
+void launch_apply_a_dot(const double *p, double *ap, int nx, int ny, int pitch, double h, double *d_partials, double *d_out,
+                        cudaStream_t st)
+{
+    const int blocks = red_blocks_for(nx, ny);
+    k_apply_a_dot<<<blocks, RED_THREADS, 0, st>>>(p, ap, nx, ny, pitch, h * h, d_partials);
+    count_launch();
+    launch_final_sum(d_partials, blocks, d_out, st);
+}
+
+void launch_dot_interior(const double *a, const double *b, int nx, int ny, int pitch, double *d_partials, double *d_out,
+                         cudaStream_t st)
+{
+    const int blocks = red_blocks_for(nx, ny);
+    k_dot_interior<<<blocks, RED_THREADS, 0, st>>>(a, b, nx, ny, pitch, d_partials);
+    count_launch();
+    launch_final_sum(d_partials, blocks, d_out, st);
+}
+
+void launch_pcg_update(double *x, double *r, const double *p, const double *ap, int nx, int ny, int pitch, double alpha,
+                       double *d_partials, double *d_out, cudaStream_t st)
+{
+    const int blocks = red_blocks_for(nx, ny);
+    k_pcg_update<<<blocks, RED_THREADS, 0, st>>>(x, r, p, ap, nx, ny, pitch, alpha, d_partials);
+    count_launch();
+    launch_final_sum(d_partials, blocks, d_out, st);
+}
+
+void launch_pcg_direction(double *p, const double *z, int nx, int ny, int pitch, double beta, bool first, cudaStream_t st)
+{
+    k_pcg_direction<<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(p, z, nx, ny, pitch, beta, first ? 1 : 0);
+    count_launch();
 }
 
 void launch_restrict(const double *fine, double *coarse, int nf, int nc, int pitch_f, int pitch_c, cudaStream_t st)

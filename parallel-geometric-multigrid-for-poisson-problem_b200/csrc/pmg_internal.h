@@ -181,6 +181,26 @@ void launch_solve_begin(const double *d_norm2, SolveCtrl *ctrl, double *hist2, d
                         cudaStream_t st);
 // hist2[++cycles] = fixed-order sum of the partials; convergence test (skipped when already done)
 void launch_cycle_finish(const double *d_partials, int count, SolveCtrl *ctrl, double *hist2, cudaStream_t st);
+// ---- smoothers beyond weighted Jacobi and the vector kernels of pmg_pcg (kernels_basic.cu) ----
+// mixed-precision experiment: one weighted-Jacobi sweep with fp32 arithmetic on the fp64 fields
+void launch_jacobi_sweep_f32(double *out, const double *in, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h,
+                             double omega, cudaStream_t st);
+// d_out[0] = sum (a - b)^2, d_out[1] = sum b^2 over l entries; d_partials: 2 * reduce_partials() doubles
+void launch_diff_norm2(const double *a, const double *b, size_t l, double *d_partials, double *d_out, cudaStream_t st);
+// one colour ((x + y) & 1 == colour) of a red-black Gauss-Seidel sweep, in place; GaussSeidelSmoother's expression
+void launch_rbgs_half(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h, int colour,
+                      cudaStream_t st);
+// `sweeps` lexicographic Gauss-Seidel sweeps exactly as Smoother.hpp:134-145 (anti-diagonal wavefront, one CTA)
+void launch_gs_lex(double *x, const double *f, int nx, int ny, int pitch_x, int pitch_f, double h, int sweeps, cudaStream_t st);
+// ap = A p (interior) and *d_out = p . ap ; *d_out = a . b ; x += alpha p, r -= alpha ap, *d_out = r . r ; p = z + beta p
+void launch_apply_a_dot(const double *p, double *ap, int nx, int ny, int pitch, double h, double *d_partials, double *d_out,
+                        cudaStream_t st);
+void launch_dot_interior(const double *a, const double *b, int nx, int ny, int pitch, double *d_partials, double *d_out,
+                         cudaStream_t st);
+void launch_pcg_update(double *x, double *r, const double *p, const double *ap, int nx, int ny, int pitch, double alpha,
+                       double *d_partials, double *d_out, cudaStream_t st);
+void launch_pcg_direction(double *p, const double *z, int nx, int ny, int pitch, double beta, bool first, cudaStream_t st);
+
 // *host_ctrl = *ctrl and (host_hist != nullptr) host_hist[0..cycles] = hist2[...], both in mapped pinned host memory,
 // written by a kernel: no copy engine involved (see k_ctrl_to_host)
 void launch_ctrl_to_host(const SolveCtrl *ctrl, SolveCtrl *host_ctrl, const double *hist2, double *host_hist, int hist_cap,

@@ -110,6 +110,7 @@ struct pmg_solver {
     cudaStream_t copy_in_stream = nullptr, copy_out_stream = nullptr;
     cudaEvent_t ev_staged = nullptr, ev_snap = nullptr, ev_fetched = nullptr, ev_consumed = nullptr;
     bool staged = false, fetching = false;
+    double *pcg_base[4] = {nullptr, nullptr, nullptr, nullptr};  // r, z, p, A p of pmg_pcg (level-0 layout; lazily allocated)
     int cluster_top = 0;       // level size from which ONE 16-CTA cluster launch runs the rest of the cycle (257 / 129;
                                // 0: off -- PMG_CLUSTER=0, an unsuitable configuration, or a device that cannot co-schedule
                                // the cluster)
@@ -216,10 +217,57 @@ static pmg_status alloc_zero(double **p, size_t elems)
 
 // ---- smoothing on one level (Smoother::smooth, Smoother.hpp:38-116) -----------------------------------
 // Operator-granular: ping-pong sweeps; with smoother_eps > 0 the reference's per-sweep absolute-norm exit.
+// Chebyshev-Jacobi weights for `n` sweeps on the eigenvalue range [1/2, 2] of D^-1 A (pmg.h); the expression is the CPU
+// checker's (orc_chebyshev_weights), evaluated by the same libm
+static void chebyshev_weights(int n, double *w)
+{
+    const double lo = 0.5, hi = 2.0;
+    const double d = 0.5 * (hi + lo), c = 0.5 * (hi - lo);
+    for (int k = 0; k < n; ++k) w[k] = 1.0 / (d - c * std::cos(M_PI * (2 * k + 1) / (2.0 * n)));
+}
+
+// the smoothers beyond weighted Jacobi (operator-granular; pmg.h: pmg_smoother)
+static pmg_status smooth_other(pmg_solver *s, int l, int sweeps, bool x_is_zero)
+{
+    Level &L = s->lv[l];
+    const pmg_config &c = s->cfg;
+    if (sweeps <= 0) return PMG_OK;
+    if (x_is_zero) launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);
+    if (c.smoother == PMG_SMOOTHER_RBGS) {
+        for (int it = 0; it < sweeps; ++it) {
+            launch_rbgs_half(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, 0, s->stream);
+            launch_rbgs_half(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, 1, s->stream);
+        }
+    } else if (c.smoother == PMG_SMOOTHER_GS_LEX) {
+        if (c.smoother_eps > 0.0) {  // GaussSeidelSmoother's absolute-norm exit (Smoother.hpp:147-159), tested per sweep
+            for (int it = 0; it < sweeps; ++it) {
+                launch_gs_lex(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, 1, s->stream);
+                launch_residual_norm2(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
+                PMG_CUDA(cudaMemcpyAsync(s->h_scalar, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+                PMG_CUDA(cudaStreamSynchronize(s->stream));
+                if (std::sqrt(*s->h_scalar) < c.smoother_eps) break;
+            }
+        } else {
+            launch_gs_lex(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, sweeps, s->stream);
+        }
+    } else {  // PMG_SMOOTHER_CHEBYSHEV
+        if (sweeps > 64) return fail(PMG_ERR_UNSUPPORTED, "Chebyshev-Jacobi: at most 64 sweeps per smoothing step");
+        double w[64];
+        chebyshev_weights(sweeps, w);
+        for (int it = 0; it < sweeps; ++it) {
+            launch_jacobi_sweep(L.xb, L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, w[it], s->stream);
+            std::swap(L.x, L.xb);
+            std::swap(L.base_x, L.base_xb);
+        }
+    }
+    return PMG_OK;
+}
+
 static pmg_status smooth_operator(pmg_solver *s, int l, int sweeps, bool x_is_zero, const int *done = nullptr)
 {
     Level &L = s->lv[l];
     const pmg_config &c = s->cfg;
+    if (c.smoother != PMG_SMOOTHER_JACOBI) return smooth_other(s, l, sweeps, x_is_zero);
     if (x_is_zero && !(c.smoother_eps <= 0.0 && L.n * L.n <= SMALL_MAX_POINTS))
         launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);
     if (c.smoother_eps > 0.0) {
@@ -234,12 +282,16 @@ static pmg_status smooth_operator(pmg_solver *s, int l, int sweeps, bool x_is_ze
         }
         return PMG_OK;
     }
-    if (L.n * L.n <= SMALL_MAX_POINTS) {
+    if (L.n * L.n <= SMALL_MAX_POINTS && !c.smoother_fp32) {
         launch_jacobi_small(L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, sweeps, x_is_zero, s->stream, done);
         return PMG_OK;
     }
+    if (x_is_zero && c.smoother_fp32 && L.n * L.n <= SMALL_MAX_POINTS) launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);
     for (int it = 0; it < sweeps; ++it) {
-        launch_jacobi_sweep(L.xb, L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, s->stream);
+        if (c.smoother_fp32)
+            launch_jacobi_sweep_f32(L.xb, L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, s->stream);
+        else
+            launch_jacobi_sweep(L.xb, L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.h, c.omega, s->stream);
         std::swap(L.x, L.xb);
         std::swap(L.base_x, L.base_xb);
     }
@@ -1055,6 +1107,14 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     if (!(cfg->omega > 0.0)) return fail(PMG_ERR_INVALID, "omega must be positive");
     if (cfg->norm_mode != PMG_NORM_TREE && cfg->norm_mode != PMG_NORM_SEQUENTIAL)
         return fail(PMG_ERR_INVALID, "bad norm_mode");
+    if (cfg->smoother < PMG_SMOOTHER_JACOBI || cfg->smoother > PMG_SMOOTHER_CHEBYSHEV)
+        return fail(PMG_ERR_INVALID, "bad smoother");
+    if (cfg->smoother_fp32 && (cfg->smoother != PMG_SMOOTHER_JACOBI || cfg->n_ranks > 1 || cfg->smoother_eps > 0.0))
+        return fail(PMG_ERR_UNSUPPORTED, "smoother_fp32: weighted Jacobi without the eps exit, one GPU (an experiment)");
+    if (cfg->smoother != PMG_SMOOTHER_JACOBI && cfg->n_ranks > 1)
+        return fail(PMG_ERR_UNSUPPORTED, "multi-GPU: weighted Jacobi only (the other smoothers run on the operator engine)");
+    if (cfg->smoother_eps > 0.0 && (cfg->smoother == PMG_SMOOTHER_RBGS || cfg->smoother == PMG_SMOOTHER_CHEBYSHEV))
+        return fail(PMG_ERR_UNSUPPORTED, "smoother_eps: the reference's early exit exists for its Jacobi and Gauss-Seidel smoothers only");
     const bool dist = cfg->n_ranks > 1;
     if (dist) {
         if (!comm_ready() || comm_size() != cfg->n_ranks || comm_rank() != cfg->rank)
@@ -1080,7 +1140,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     s->cfg = *cfg;
     s->device = dev;
     s->fused = (cfg->engine == PMG_ENGINE_FUSED) && fused_supported(cfg->nu1) && fused_supported(cfg->nu2) &&
-               !(cfg->smoother_eps > 0.0);
+               !(cfg->smoother_eps > 0.0) && cfg->smoother == PMG_SMOOTHER_JACOBI && !cfg->smoother_fp32;
     pmg_status rc = PMG_OK;
     auto bail = [&](pmg_status st) {
         pmg_destroy(s);
@@ -1344,6 +1404,7 @@ void pmg_destroy(pmg_solver *s)
         cudaFree(L.d_sin);
     }
     cudaFree(s->base_f_fmg0);
+    for (double *b : s->pcg_base) cudaFree(b);
     cudaFree(s->base_f_stage);
     cudaFree(s->base_x_snap);
     for (cudaStream_t st : {s->copy_in_stream, s->copy_out_stream})
@@ -1782,6 +1843,89 @@ static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol,
     return check_comm_err(s);
 }
 
+// ---- preconditioned conjugate gradients (pmg.h; specification: the CPU checker's orc_pcg) -----------------------------
+static pmg_status pcg_impl(pmg_solver *s, int precond, double rel_tol, int max_iter, double *res_history, int *n_iter_out)
+{
+    if (!s || max_iter < 0 || (precond != 0 && precond != 1)) return fail(PMG_ERR_INVALID, "bad argument");
+    if (s->dist) return fail(PMG_ERR_UNSUPPORTED, "pmg_pcg is single-GPU only");
+    PMG_CUDA(cudaSetDevice(s->device));
+    Level &L = s->lv[0];
+    for (double *&b : s->pcg_base)
+        if (!b) {
+            pmg_status rc = alloc_zero(&b, L.elems);
+            if (rc != PMG_OK) return rc;
+        }
+    const size_t o = level_origin(L.n);
+    double *r = s->pcg_base[0] + o, *z_arr = s->pcg_base[1] + o, *p = s->pcg_base[2] + o, *ap = s->pcg_base[3] + o;
+    auto scalar = [&](double *out) -> pmg_status { return read_scalar(s, out); };
+    PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    // r = f - A x on the interior (the padding and the ring of r stay zero)
+    launch_residual(r, L.x, L.f, L.n, L.n, L.pitch, L.pitch, L.pitch, L.h, s->stream);
+    launch_dot_interior(r, r, L.n, L.n, L.pitch, s->d_partials, s->d_scalar, s->stream);
+    double rr = 0.0;
+    pmg_status rc = scalar(&rr);
+    if (rc != PMG_OK) return rc;
+    const double r0 = std::sqrt(rr);
+    if (res_history) res_history[0] = r0;
+    int k = 0;
+    double rz = 0.0, rnorm = r0;
+    while (k < max_iter && !(rnorm < rel_tol * r0) && r0 > 0.0) {
+        const double *z = r;
+        if (precond) {
+            // z = M r: one cycle on (z, r) from z = 0 -- the finest level temporarily works on the PCG arrays
+            double *sx = L.x, *sxb = L.xb, *sbx = L.base_x, *sbxb = L.base_xb;
+            double *sf = L.f, *sbf = L.base_f;
+            PMG_CUDA(cudaMemsetAsync(s->pcg_base[1], 0, L.elems * sizeof(double), s->stream));
+            L.x = z_arr;
+            L.base_x = s->pcg_base[1];
+            L.f = r;
+            L.base_f = s->pcg_base[0];
+            rc = s->fused ? cycle_fused(s, 0, false, false, false, nullptr) : cycle_operator(s, 0, false, false);
+            z = L.x;  // (the operator engine may have left the result in the ping-pong partner)
+            L.x = sx;
+            L.xb = sxb;
+            L.base_x = sbx;
+            L.base_xb = sbxb;
+            L.f = sf;
+            L.base_f = sbf;
+            if (rc != PMG_OK) return rc;
+            if (const int bad = fused_take_bad_nu())
+                return fail(PMG_ERR_UNSUPPORTED, "fused engine: no kernel for " + std::to_string(bad) + " sweeps per pass");
+        }
+        double rz_new = 0.0;
+        launch_dot_interior(r, z, L.n, L.n, L.pitch, s->d_partials, s->d_scalar, s->stream);
+        if ((rc = scalar(&rz_new)) != PMG_OK) return rc;
+        launch_pcg_direction(p, z, L.n, L.n, L.pitch, k == 0 ? 0.0 : rz_new / rz, k == 0, s->stream);
+        rz = rz_new;
+        double pap = 0.0;
+        launch_apply_a_dot(p, ap, L.n, L.n, L.pitch, L.h, s->d_partials, s->d_scalar, s->stream);
+        if ((rc = scalar(&pap)) != PMG_OK) return rc;
+        const double alpha = rz / pap;
+        launch_pcg_update(L.x, r, p, ap, L.n, L.n, L.pitch, alpha, s->d_partials, s->d_scalar, s->stream);
+        if ((rc = scalar(&rr)) != PMG_OK) return rc;
+        ++k;
+        rnorm = std::sqrt(rr);
+        if (res_history) res_history[k] = rnorm;
+    }
+    PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    PMG_CUDA(cudaEventSynchronize(s->ev1));
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    if (n_iter_out) *n_iter_out = k;
+    if (precond) drop_graphs(s);  // the operator engine's coarse solves may have swapped x / xb roles below level 0
+    return PMG_OK;
+}
+
+pmg_status pmg_pcg(pmg_solver *s, int precond, double rel_tol, int max_iter, double *res_history, int *n_iter_out)
+{
+    try {
+        return pcg_impl(s, precond, rel_tol, max_iter, res_history, n_iter_out);
+    } catch (const std::exception &e) {
+        return fail(PMG_ERR_ALLOC, std::string("exception in pmg_pcg: ") + e.what());
+    }
+}
+
 pmg_status pmg_last_device_ms(pmg_solver *s, double *ms_out)
 {
     if (!s || !ms_out) return fail(PMG_ERR_INVALID, "null argument");
@@ -2176,6 +2320,27 @@ pmg_status pmg_jacobi(double *x, const double *f, int width, int height, double 
     return PMG_OK;
 }
 
+pmg_status pmg_gauss_seidel(double *x, const double *f, int width, int height, double h, int sweeps, int ordering,
+                            void *stream)
+{
+    if (!x || !f || width < 3 || height < 3 || sweeps < 0 || (ordering != 0 && ordering != 1))
+        return fail(PMG_ERR_INVALID, "bad argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ordering == 0) {
+        launch_gs_lex(x, f, width, height, width, width, h, sweeps, st);
+    } else {
+        for (int it = 0; it < sweeps; ++it) {
+            launch_rbgs_half(x, f, width, height, width, width, h, 0, st);
+            launch_rbgs_half(x, f, width, height, width, width, h, 1, st);
+        }
+    }
+    PMG_CUDA(cudaStreamSynchronize(st));
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
 pmg_status pmg_residual(double *r, const double *x, const double *f, int width, int height, double h,
                         double *norm2_out, void *stream)
 {
@@ -2219,6 +2384,30 @@ pmg_status pmg_prolong_add(const double *coarse, double *fine, int nc, int nf, i
     launch_prolong_add(coarse, fine, nc, nf, nc, nf, mode, st);
     PMG_CUDA(cudaStreamSynchronize(st));
     PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+pmg_status pmg_diff_norm2(const double *a, const double *b, size_t l, double *diff2_out, double *b2_out, void *stream)
+{
+    if (!a || !b || !diff2_out || !b2_out) return fail(PMG_ERR_INVALID, "null argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *part = nullptr, *out = nullptr;
+    if (cudaMalloc((void **)&part, (2 * reduce_partials() + 2) * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PMG_ERR_ALLOC, "cudaMalloc failed");
+    }
+    out = part + 2 * reduce_partials();
+    launch_diff_norm2(a, b, l, part, out, st);
+    double h[2] = {0.0, 0.0};
+    cudaError_t e = cudaMemcpyAsync(h, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(part);
+    if (e != cudaSuccess) return fail(PMG_ERR_CUDA, cudaGetErrorString(e));
+    *diff2_out = h[0];
+    *b2_out = h[1];
     return PMG_OK;
 }
 

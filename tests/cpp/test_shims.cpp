@@ -172,6 +172,34 @@ int main()
             std::printf("{\"test\": \"smoother\", \"n\": %d, \"sweeps\": %d, \"res0\": %.17g, \"res1\": %.17g, \"x_mid\": %.17g}\n",
                         n, (int)res.size(), res[0], res[1], x[(size_t)(n / 2) * n + n / 2]);
         }
+        // the other smoothers of Smoother.hpp behind the same interface: injected into MultigridSolver and called directly
+        {
+            int n = 65;
+            std::vector<double> f((size_t)n * n), u(f.size());
+            rhs(f, u, n);
+            GaussSeidelSmoother gs(0.0);
+            RedBlackGaussSeidelSmoother rb;
+            ChebyshevJacobiSmoother ch;
+            Smoother *all[3] = {&gs, &rb, &ch};
+            const char *names[3] = {"gs_lex", "rbgs", "chebyshev"};
+            for (int i = 0; i < 3; ++i) {
+                std::vector<double> phi((size_t)n * n, 0.0), err(phi.size());
+                MultigridSolver mg(all[i], 2, n);
+                mg.v_cycle(phi.data(), f.data(), n, 1.0 / (n - 1));
+                for (size_t q = 0; q < phi.size(); ++q) err[q] = phi[q] - u[q];
+                std::printf("{\"test\": \"injected\", \"smoother\": \"%s\", \"n\": %d, \"rel_l2_error\": %.17g, \"phi_mid\": %.17g}\n",
+                            names[i], n, norm(err) / norm(u), phi[(size_t)(n / 2) * n + n / 2]);
+            }
+            std::vector<double> x((size_t)n * n, 0.0), res;
+            gs.smooth(x.data(), f.data(), n, n, 1.0 / (n - 1), 3, nullptr, &res);
+            std::printf("{\"test\": \"gs_smooth\", \"n\": %d, \"sweeps\": %d, \"res_last\": %.17g, \"x_mid\": %.17g}\n", n,
+                        (int)res.size(), res.back(), x[(size_t)(n / 2) * n + n / 2]);
+            ConjugateGradientSmoother cg(0.0);
+            std::vector<double> y((size_t)n * n, 7.0), cres;  // the reference zeroes x first
+            cg.smooth(y.data(), f.data(), n, n, 1.0 / (n - 1), 10, nullptr, &cres);
+            std::printf("{\"test\": \"cg_smooth\", \"n\": %d, \"entries\": %d, \"res0\": %.17g, \"res_last\": %.17g}\n", n,
+                        (int)cres.size(), cres.front(), cres.back());
+        }
     } catch (const pmg::Error &e) {
         std::printf("{\"test\": \"error\", \"status\": %d, \"what\": \"%s\"}\n", (int)e.status, e.what());
         return 3;

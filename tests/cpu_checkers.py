@@ -18,6 +18,7 @@ REF_SO = os.path.join(ORACLE_DIR, "_ref", "libpmg_ref.so")
 
 V, W, F = 0, 1, 2
 PROLONG_REFERENCE, PROLONG_FULL = 0, 1
+SMOOTHER_JACOBI, SMOOTHER_RBGS, SMOOTHER_GS_LEX, SMOOTHER_CHEBYSHEV = 0, 1, 2, 3
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _i, _d, _l = ctypes.c_int, ctypes.c_double, ctypes.c_long
@@ -54,6 +55,22 @@ class Checker:
         g("solve").argtypes = [_dp, _dp, _i, _i, _d, _d, _i, _i, _i, _i, _d, _i, _dp]
         g("fmg_general").restype = _i
         g("fmg_general").argtypes = [_dp, _dp, _i, _d, _d, _i, _i, _i]
+        # smoothers beyond weighted Jacobi + the Krylov wrapper (oracle/pmg_oracle_smoothers.c, ref_driver.cpp)
+        g("gs").restype = _i
+        g("gs").argtypes = [_dp, _dp, _i, _i, _d, _i, _d, _dp]
+        g("cycle_s").restype = _i
+        g("cycle_s").argtypes = [_dp, _dp, _i, _d, _i, _i, _d, _i, _i, _i, _i, _i]
+        g("cg").restype = _i
+        g("cg").argtypes = [_dp, _dp, _i, _i, _d, _i, _d, _dp]
+        if prefix == "orc_":
+            lib.orc_rbgs.restype = _i
+            lib.orc_rbgs.argtypes = [_dp, _dp, _i, _i, _d, _i]
+            lib.orc_jacobi_weights.restype = _i
+            lib.orc_jacobi_weights.argtypes = [_dp, _dp, _i, _i, _d, _dp, _i]
+            lib.orc_chebyshev_weights.restype = None
+            lib.orc_chebyshev_weights.argtypes = [_d, _d, _i, _dp]
+            lib.orc_pcg.restype = _i
+            lib.orc_pcg.argtypes = [_dp, _dp, _i, _d, _i, _i, _d, _i, _i, _i, _i, _d, _i, _dp]
         self._g = g
 
     def jacobi(self, x, f, h, omega=1.0, num_iter=1, eps=0.0):
@@ -109,6 +126,50 @@ class Checker:
         if rc != 0:
             raise NotImplementedError("fmg_general not available in %s" % self.prefix)
         return phi
+
+    # ---- smoothers beyond weighted Jacobi ----
+    def gs(self, x, f, h, num_iter, eps=0.0):
+        """GaussSeidelSmoother::smooth: num_iter lexicographic sweeps in place; returns the per-sweep ||r|| list."""
+        res = np.zeros(max(num_iter, 1))
+        n = self._g("gs")(_p(x), _p(f), x.shape[1], x.shape[0], h, num_iter, eps, _p(res))
+        return res[:n]
+
+    def rbgs(self, x, f, h, sweeps):
+        self.lib.orc_rbgs(_p(x), _p(f), x.shape[1], x.shape[0], h, sweeps)
+        return x
+
+    def chebyshev_weights(self, n, lo=0.5, hi=2.0):
+        w = np.zeros(n)
+        self.lib.orc_chebyshev_weights(lo, hi, n, _p(w))
+        return w
+
+    def jacobi_weights(self, x, f, h, w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        self.lib.orc_jacobi_weights(_p(x), _p(f), x.shape[1], x.shape[0], h, _p(w), len(w))
+        return x
+
+    def cycle_s(self, phi, f, kind=V, smoother=SMOOTHER_JACOBI, omega=2.0 / 3.0, alpha=2, nu1=2, nu2=2, coarse_sweeps=11,
+                prolong=PROLONG_REFERENCE):
+        n = phi.shape[0]
+        rc = self._g("cycle_s")(_p(phi), _p(f), n, 1.0 / (n - 1), kind, smoother, omega, alpha, nu1, nu2, coarse_sweeps,
+                                prolong)
+        if rc != 0:
+            raise NotImplementedError("cycle_s configuration not available in %s" % self.prefix)
+        return phi
+
+    def cg(self, x, f, h, num_iter, eps=0.0):
+        """ConjugateGradientSmoother::smooth: x zeroed, num_iter steps; returns the ||r|| list (before + after each step)."""
+        res = np.zeros(num_iter + 2)
+        n = self._g("cg")(_p(x), _p(f), x.shape[1], x.shape[0], h, num_iter, eps, _p(res))
+        return res[:n]
+
+    def pcg(self, x, f, precond=1, smoother=SMOOTHER_JACOBI, omega=2.0 / 3.0, nu1=2, nu2=2, coarse_sweeps=11,
+            prolong=PROLONG_FULL, rel_tol=1e-8, max_iter=100):
+        n = x.shape[0]
+        hist = np.zeros(max_iter + 1)
+        k = self.lib.orc_pcg(_p(x), _p(f), n, 1.0 / (n - 1), precond, smoother, omega, nu1, nu2, coarse_sweeps, prolong,
+                             rel_tol, max_iter, _p(hist))
+        return k, hist[: k + 1].copy()
 
     def solve(self, phi, f, kind=V, omega=2.0 / 3.0, eps=0.0, alpha=2, v1=1, v2=1,
               prolong=PROLONG_REFERENCE, rel_tol=1e-8, max_cycles=100):

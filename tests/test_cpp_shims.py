@@ -75,6 +75,27 @@ def test_reference_style_driver_matches_goldens(golden):
     assert abs(sm["res0"] - g["smoother_residuals"][0]) <= 1e-12 * sm["res0"]
     assert abs(sm["res1"] - g["smoother_residuals"][1]) <= 1e-12 * sm["res1"]
     assert len(by["gpu_exec_v3"]) == 3
+    # the other Smoother.hpp classes behind the same interface, against the CPU checkers (pinned to the reference classes
+    # in tests/test_oracle_smoothers.py)
+    import cpu_checkers as cc
+    orc = cc.load("orc")
+    n = 65
+    f = orc.rhs(n)
+    kinds = {"gs_lex": (cc.SMOOTHER_GS_LEX, 1, 10), "rbgs": (cc.SMOOTHER_RBGS, 1, 10), "chebyshev": (cc.SMOOTHER_CHEBYSHEV, 2, 11)}
+    for o in by["injected"]:
+        sm, nu, coarse = kinds[o["smoother"]]
+        want = np.zeros((n, n))
+        orc.cycle_s(want, f, kind=cc.V, smoother=sm, alpha=2, nu1=nu, nu2=nu, coarse_sweeps=coarse)
+        assert o["phi_mid"] == want[n // 2, n // 2], o["smoother"]
+    x = np.zeros((n, n))
+    res = orc.gs(x, f, 1.0 / (n - 1), 3)
+    g = by["gs_smooth"][0]
+    assert g["sweeps"] == 3 and g["x_mid"] == x[n // 2, n // 2] and abs(g["res_last"] - res[-1]) <= 1e-12 * res[-1]
+    cres = orc.cg(np.zeros((n, n)), f, 1.0 / (n - 1), 10)
+    c = by["cg_smooth"][0]
+    # (the manufactured right-hand side is an eigenvector of A: CG is done after one step and the later entries are
+    # rounding noise on both sides -- tests/test_gpu_smoothers.py compares whole CG histories on random right-hand sides)
+    assert c["entries"] == 11 and abs(c["res0"] - cres[0]) <= 1e-12 * cres[0] and c["res_last"] < 1e-9 * c["res0"]
 
 
 @pytest.mark.gpu
@@ -100,3 +121,46 @@ def test_pmg_runner_writes_reference_output_formats(golden, tmp_path):
     for name in ("residual", "jacobi", "restriction", "prolungator"):
         rows = [l.split() for l in open(os.path.join(out, "timings_%s_gpu.txt" % name)).read().splitlines()]
         assert [r[:2] for r in rows] == [["32", "257"], ["32", "1025"]] and all(float(r[2]) > 0 for r in rows)
+
+
+@pytest.mark.gpu
+def test_pmg_runner_smoother_study_and_error_field_dumps(orc, tmp_path):
+    """SURVEY.md 8f-4: the Smoother::test hook (Smoother.hpp:50-57,100-115) and the `errors` output through the shims:
+    per-sweep residual and relative-error norms against the CPU checker, error FIELDS in the reference's
+    save_vector_err_file.hpp format (length on the first line, one component per line, 6 significant digits)."""
+    exe = os.path.join(PKG, "pmg_runner")
+    n, sweeps = 33, 21
+    p = subprocess.run([exe, "smoother", "--smoother", "jacobi", "--n", str(n), "--iters", str(sweeps), "--out", "out"],
+                       capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    f, u = orc.rhs(n), orc.exact(n)
+    x = np.zeros((n, n))
+    res = orc.jacobi(x, f, 1.0 / (n - 1), omega=1.0, num_iter=sweeps - 1)
+    rows = [l.split() for l in open(tmp_path / "out" / ("smoother_jacobi_N%d.txt" % n)).read().splitlines()]
+    assert len(rows) == sweeps
+    got = np.array([float(r[1]) for r in rows])
+    assert np.max(np.abs(got - res) / res) <= 1e-12
+    # relative error after the LAST sweep (x now holds it)
+    assert abs(float(rows[-1][2]) - orc.norm(x - u) / orc.norm(u)) <= 1e-12
+    # error fields: before the first sweep, after sweeps 0, 10, 20
+    vec = tmp_path / "OUTPUT_RESULT" / "ERR_VECTOR"
+    for i in (0, 10, 20, 30):
+        lines = open(vec / ("iteration_%d.txt" % i)).read().split()
+        assert int(lines[0]) == n * n and len(lines) == n * n + 1
+    first = np.array([float(v) for v in open(vec / "iteration_0.txt").read().split()[1:]]).reshape(n, n)
+    assert np.allclose(first, -u, rtol=1e-5, atol=1e-12)  # x = 0: the error is -u, printed with 6 digits
+    last = np.array([float(v) for v in open(vec / "iteration_30.txt").read().split()[1:]]).reshape(n, n)
+    assert np.allclose(last, x - u, rtol=1e-5, atol=1e-12)
+    # the multigrid runner's error-field dump (flag_err_vector_iteration)
+    p = subprocess.run([exe, "err_vector", "--n", "65", "--iters", "2", "--omega", "0.6666666666666666", "--eps", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    lines = open(vec / "iteration_last_gpu.txt").read().split()
+    assert int(lines[0]) == 65 * 65 and len(lines) == 65 * 65 + 1
+    # the other smoothers through the same study
+    for name in ("gs", "rbgs", "chebyshev", "cg"):
+        p = subprocess.run([exe, "smoother", "--smoother", name, "--n", "33", "--iters", "6", "--out", "out"],
+                           capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+        assert p.returncode == 0, (name, p.stderr)
+        rows = open(tmp_path / "out" / ("smoother_%s_N33.txt" % name)).read().splitlines()
+        assert len(rows) == (7 if name == "cg" else 6)

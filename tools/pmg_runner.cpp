@@ -13,6 +13,13 @@
 //   ops        ParallelTestRunner::plotTimeSequentialVsParallel (:98-125), device side only
 //                                                              timings_{residual,jacobi,restriction,prolungator}_gpu.txt
 //                                                                                                           "num_thread N seconds"
+//   err_vector ...::run_all_cycles with flag_err_vector_iteration (MultiGridTestRunner.hpp:150-160, 214-222, 247-248): the error
+//              FIELD phi - phi_exact before the first and after every cycle, written with
+//              save_errors_vector_to_file_last_iteration_gpu (save_vector_err_file.hpp:67-89)
+//                                                              ERR_VECTOR/iteration_last_gpu.txt (under ./OUTPUT_RESULT)
+//   smoother   SolverRunner-style study of one smoother (Smoother::test hook, Smoother.hpp:50-57,100-115): --smoother
+//              jacobi|gs|rbgs|chebyshev|cg, --iters sweeps; residual and error norms per sweep to
+//              smoother_<name>_N<n>.txt "sweep residual relerr", error fields to ERR_VECTOR/iteration_<10 i>.txt (jacobi)
 //   history    (new) residual history to a relative tolerance (V, W, FMG-then-V): history_<cycle>_N<n>.txt  "cycle norm"
 //
 // usage: pmg_runner <mode> [--n 33,65,...] [--iters K] [--alpha A] [--omega W] [--eps E] [--tol T]
@@ -39,6 +46,7 @@ struct Options {
     std::vector<int> n_list = {33, 65, 129, 257, 513, 1025};
     int iters = 1, alpha = 3, prolong = PMG_PROLONG_REFERENCE;
     double omega = 1.0, eps = 1e-7, tol = 1e-8;
+    std::string smoother = "jacobi";
 };
 
 static void manufactured(std::vector<double> &f, std::vector<double> &u, int n)
@@ -145,6 +153,7 @@ int main(int argc, char **argv)
         else if (a == "--eps") o.eps = std::atof(argv[++i]);
         else if (a == "--tol") o.tol = std::atof(argv[++i]);
         else if (a == "--out") o.out = argv[++i];
+        else if (a == "--smoother") o.smoother = argv[++i];
         else if (a == "--prolong") o.prolong = std::strcmp(argv[++i], "full") == 0 ? PMG_PROLONG_FULL : PMG_PROLONG_REFERENCE;
     }
     mkdir(o.out.c_str(), 0755);
@@ -254,6 +263,70 @@ int main(int argc, char **argv)
                 pmg_device_free(c.f);
                 pmg_device_free(c.r);
                 pmg_device_free(c.c);
+            }
+        } else if (o.mode == "err_vector") {
+            for (int n : o.n_list)
+                for (int k = 0; k < 3; ++k) {
+                    std::vector<double> phi((size_t)n * n, 0.0), f(phi.size()), u(phi.size());
+                    manufactured(f, u, n);
+                    WeightedJacobiSmoother smoother(o.eps, o.omega);
+                    MultigridSolver mg(&smoother, o.alpha, n);
+                    mg.prolong_mode = o.prolong;
+                    std::vector<std::vector<double>> err_vect_iteration;
+                    auto snap = [&]() {
+                        std::vector<double> e(phi.size());
+                        for (size_t i = 0; i < phi.size(); ++i) e[i] = phi[i] - u[i];
+                        err_vect_iteration.push_back(std::move(e));
+                    };
+                    snap();
+                    for (int it = 0; it < o.iters; ++it) {
+                        if (k == 2)
+                            mg.f_cycle_from_fine(phi.data(), f.data(), n);
+                        else if (k == 1)
+                            mg.w_cycle(phi.data(), f.data(), n, 1.0 / (n - 1));
+                        else
+                            mg.v_cycle(phi.data(), f.data(), n, 1.0 / (n - 1));
+                        snap();
+                    }
+                    save_errors_vector_to_file_last_iteration_gpu(err_vect_iteration);
+                    std::cout << names[k] << " N = " << n << ": error field after " << o.iters
+                              << " cycle(s) in ./OUTPUT_RESULT/ERR_VECTOR/iteration_last_gpu.txt, ||e||/||u|| = "
+                              << rel_error(phi, u) << "\n";
+                }
+        } else if (o.mode == "smoother") {
+            for (int n : o.n_list) {
+                std::vector<double> x((size_t)n * n, 0.0), f(x.size()), u(x.size()), res, err;
+                manufactured(f, u, n);
+                const double h = 1.0 / (n - 1);
+                WeightedJacobiSmoother jac(0.0, o.omega);
+                GaussSeidelSmoother gs(0.0);
+                RedBlackGaussSeidelSmoother rb;
+                ChebyshevJacobiSmoother ch;
+                ConjugateGradientSmoother cg(0.0);
+                if (o.smoother == "jacobi") {
+                    jac.switch_test_mode();  // error fields every 10 sweeps -> ./OUTPUT_RESULT/ERR_VECTOR/iteration_<10 i>.txt
+                    jac.smooth(x.data(), f.data(), n, n, h, o.iters - 1, u.data(), &res, &err);
+                } else if (o.smoother == "gs") {
+                    gs.smooth(x.data(), f.data(), n, n, h, o.iters, u.data(), &res);
+                } else if (o.smoother == "rbgs") {
+                    rb.smooth(x.data(), f.data(), n, n, h, o.iters, u.data(), &res);
+                } else if (o.smoother == "chebyshev") {
+                    ch.smooth(x.data(), f.data(), n, n, h, o.iters - 1, u.data(), &res);
+                } else if (o.smoother == "cg") {
+                    cg.smooth(x.data(), f.data(), n, n, h, o.iters, u.data(), &res);
+                } else {
+                    std::fprintf(stderr, "unknown smoother %s\n", o.smoother.c_str());
+                    return 2;
+                }
+                std::ofstream out(o.out + "/smoother_" + o.smoother + "_N" + std::to_string(n) + ".txt");
+                out.precision(17);
+                for (size_t i = 0; i < res.size(); ++i) {
+                    out << i << " " << res[i];
+                    if (i < err.size()) out << " " << err[i];
+                    out << "\n";
+                }
+                std::cout << o.smoother << " N = " << n << ": " << res.size() << " residual norms, last " << res.back()
+                          << ", final relative L2 error " << rel_error(x, u) << "\n";
             }
         } else if (o.mode == "history") {
             for (int n : o.n_list) {
