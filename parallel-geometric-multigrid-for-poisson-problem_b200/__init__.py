@@ -438,6 +438,19 @@ def set_cluster_top(n):
     L.pmg_set_cluster_top(n)
 
 
+def set_cross_cycle(on, minb=None):
+    """Cross-cycle solve on level 0 (Pass B of cycle k fused with Pass A of cycle k+1) for solvers created afterwards:
+    True / False, or -1 = PMG_CROSS / the default (on).  minb: CTAs per SM of the cross pass (2, 3, 4)."""
+    L = lib()
+    L.pmg_set_cross_cycle.restype = None
+    L.pmg_set_cross_cycle.argtypes = [ctypes.c_int]
+    L.pmg_set_cross_cycle(-1 if on == -1 else (1 if on else 0))
+    if minb is not None:
+        L.pmg_fused_set_cross_minb.restype = None
+        L.pmg_fused_set_cross_minb.argtypes = [ctypes.c_int]
+        L.pmg_fused_set_cross_minb(minb)
+
+
 def set_pdl(on):
     """Programmatic dependent launch of the cycle kernels (default on; PMG_PDL=0 does the same as set_pdl(False)).
     Affects solvers created afterwards."""

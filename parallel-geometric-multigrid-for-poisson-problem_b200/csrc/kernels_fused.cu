@@ -707,6 +707,209 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cross-cycle pass (level 0 of a V-cycle solve): Pass B of cycle k and Pass A of cycle k+1 in ONE sweep over HBM.
+//   x_k      = S^nu2(xb_k + P e_k)                            -> xk   (write-only: the pipeline keeps using its registers)
+//   norm_k   = sum over the interior of (f - A x_k)^2        -> partials (the history entry of cycle k)
+//   xb_{k+1} = S^nu1(x_k)                                    -> xo   (an array other than xb)
+//   f_coarse = R(f - A xb_{k+1})                             -> cf
+// Two back-to-back passes over the same array read xb, e, f and write x, then read x, f and write xb, cf: 52 B/point.
+// Fused, x_k is never read back: 8 (xb) + 8 (f) + 2 (e) + 8 (xb') + 2 (cf) = 28 B/point, plus 8 when x_k is written.
+//   * xk == nullptr (one GPU): x_k stays in the registers.  The solve keeps the INPUT array of the last pass that ran, and
+//     when the device-side control reports "cycle k converged", xb_k and e_k are both intact (everything queued after
+//     `done` returns at once): one ordinary Pass B produces the iterate.  A B200 under its 1 kW cap is ENERGY-bound in
+//     this solve, so the 8 B/point matter: 3.31 -> 3.04 ms per cycle at N = 16385 without the store, 3.31 with it.
+//   * xk != nullptr (row slabs): the coarse levels of the next cycle run before the norm of this one is known, so e_k does
+//     not survive; x_k is written every cycle instead (the pass of the next cycle honours `done` and leaves it alone).
+// Same arithmetic, same order as the two passes: every value is bit-identical.  On row slabs (several GPUs) the input's halo rows -- 6 above, 4 below -- are copied from the
+// neighbours' arrays in the halo prologue, exactly as Pass A does for the iterate.
+// ---------------------------------------------------------------------------------------------------
+template <int C, int PF, int MINB, int S2, int S1, bool WEIGHTED>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
+    k_cross(const double *__restrict__ xb, double *__restrict__ xo, double *__restrict__ xk, const double *__restrict__ f,
+            const double *__restrict__ e, double *__restrict__ cf, StripGeom g, int pitch_c, int lo, int nc, JacobiCoef coef,
+            double inv_h2, double *__restrict__ partials, const int *__restrict__ done, HaloPeers hp)
+{
+    constexpr int S = S2 + S1;
+    using Feed = SmemFeed<C, PF, S, true>;
+    pdl_wait();
+    if (done != nullptr && *done) return;
+    static_assert(Feed::UNROLL % 2 == 0, "rows are processed in (even, odd) pairs");
+    constexpr int NP = C / 2;
+    const int wid = __shfl_sync(0xffffffffu, (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (wid >= g.n_strips * g.n_chunks) return;
+    int col, r0, r1;
+    bool owner, cin[C];
+    strip_setup<C>(g, wid, lane, col, r0, r1, owner, cin);
+
+    // rows this chunk must finish: xb' on [r0, r1) and, for the coarse rows it owns, r' on [2jc-1, 2jc+1]
+    int j_start = min(r0, max(r0, 0) - 2) - S;
+    j_start -= (j_start & 1);  // even, so that the row parity of the prolongation is static in the unrolled body
+    const int j_end = max(r1 - 1, min(r1, g.ny)) + S;  // inclusive
+
+    SweepStage<C> st[S];
+    ResidualStage<C> rs_norm, rs;
+#pragma unroll
+    for (int k = 0; k < S; ++k) st[k].init();
+    rs_norm.init();
+    rs.init();
+    double acc = 0.0;
+    double s_mid[NP], s_cor[NP], c_mid[NP], c_ew[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) s_mid[q] = s_cor[q] = c_mid[q] = c_ew[q] = 0.0;
+    bool cprol[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) cprol[k] = (col + k >= lo) && (col + k <= g.n - 2);
+
+    // row slabs: tell the neighbours that my rows of the input array are final, then copy their boundary rows into my
+    // halo rows (halo prologue: only the warps whose rows reach into a neighbour's slab wait for its flag)
+    if (hp.flag_up != nullptr || hp.flag_dn != nullptr || hp.pub_up != nullptr || hp.pub_dn != nullptr) {
+        const int epoch = hp.epoch + (hp.epoch_base != nullptr ? *hp.epoch_base : 0);
+        if ((hp.pub_up != nullptr || hp.pub_dn != nullptr) && blockIdx.x == 0 && threadIdx.x == 0) {
+            __threadfence_system();
+            if (hp.pub_up != nullptr) publish_epoch(hp.pub_up, epoch);
+            if (hp.pub_dn != nullptr) publish_epoch(hp.pub_dn, epoch);
+        }
+        const bool need_up = hp.flag_up != nullptr && j_start < 0;
+        const bool need_dn = hp.flag_dn != nullptr && j_end >= g.ny;
+        if (need_up || need_dn) {
+            int ok = 1;
+            if (lane == 0) {
+                if (need_up) ok = wait_flag(hp.flag_up, epoch) ? ok : 0;
+                if (need_dn) ok = wait_flag(hp.flag_dn, epoch) ? ok : 0;
+            }
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (!ok) {
+                if (lane == 0) {
+                    *hp.err = 1;
+                    if (hp.abort != nullptr) *hp.abort = 1;
+                }
+                return;
+            }
+            const ptrdiff_t up_off = (ptrdiff_t)col - (ptrdiff_t)PADY * g.pitch, dn_off = (ptrdiff_t)col + (ptrdiff_t)g.ny * g.pitch;
+            if (need_up && hp.x_up != nullptr) copy_halo_rows<C>(hp.x_up + up_off, hp.x_keep + up_off, g.pitch);
+            if (need_dn && hp.x_dn != nullptr) copy_halo_rows<C>(hp.x_dn + col, hp.x_keep + dn_off, g.pitch);
+        }
+    }
+    Feed feed;
+    feed.init(xb, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5, HaloPeers{}, g.ny);
+
+    const int cc = col >> 1;
+    const int nc_last_row = ((g.ny - 1) >> 1) + PADY;
+    CoarseRow<C> ec, en, eb;
+#pragma unroll
+    for (int q = 0; q <= NP; ++q) ec.v[q] = en.v[q] = eb.v[q] = 0.0;
+    {
+        const int jc0 = j_start >> 1;
+        ec = load_coarse<C>(e + (ptrdiff_t)jc0 * pitch_c + cc);
+        ec.v[NP] = __shfl_down_sync(0xffffffffu, ec.v[0], 1);
+        eb = load_coarse<C>(e + (ptrdiff_t)(jc0 + 1) * pitch_c + cc);
+    }
+    const int ycoarse = g.yoff >> 1;
+
+    for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
+#pragma unroll
+        for (int u = 0; u < Feed::UNROLL; ++u) {
+            const int jj = j + u;  // u even: fine row 2jc, u odd: 2jc+1
+            Row<C> cur = feed.begin(u, jj);
+            {   // prolongation-and-add (MultiGrid.hpp:86)
+                const bool rowp = (jj + g.yoff >= lo) && (jj + g.yoff <= g.n - 2);
+                double corr[C];
+                if ((u & 1) == 0) {
+                    en = eb;
+                    en.v[NP] = __shfl_down_sync(0xffffffffu, eb.v[0], 1);
+                    int nr = min((jj >> 1) + 2, nc_last_row);
+                    eb = load_coarse<C>(e + (ptrdiff_t)nr * pitch_c + cc);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        corr[2 * q] = ec.v[q];
+                        corr[2 * q + 1] = dmul(0.5, dadd(ec.v[q], ec.v[q + 1]));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        corr[2 * q] = dmul(0.5, dadd(ec.v[q], en.v[q]));
+                        corr[2 * q + 1] = dmul(0.25, dadd(dadd(dadd(ec.v[q], ec.v[q + 1]), en.v[q]), en.v[q + 1]));
+                    }
+                    ec = en;
+                }
+#pragma unroll
+                for (int k = 0; k < C; ++k)
+                    if (rowp && cprol[k]) cur.v[k] = dadd(cur.v[k], corr[k]);
+            }
+            // post-smoothing of cycle k (:89): stage k finishes x row jj-k-1
+#pragma unroll
+            for (int k = 0; k < S2; ++k) {
+                const int out_row = jj - k - 1 + g.yoff;
+                cur = st[k].template step<WEIGHTED>(u & 1, cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
+            }
+            {   // cur = x_k row jj - S2: the iterate of cycle k, written for the case that cycle k is the last one
+                const int krow = jj - S2;
+                if (xk != nullptr && owner && krow >= r0 && krow < r1) store_row<C>(xk + (ptrdiff_t)krow * g.pitch + col, cur);
+                // the runner's residual norm of cycle k (MultiGridTestRunner.hpp:210-211): r of x row jj - S2 - 1
+                Row<C> r = rs_norm.step(u & 1, cur, feed.f_row(S2 + 1), inv_h2);
+                const int rrow = jj - S2 - 1;
+                if (owner && rrow >= r0 && rrow < r1 && rrow >= 0 && rrow < g.ny && rrow + g.yoff > 0 &&
+                    rrow + g.yoff < g.n - 1) {
+#pragma unroll
+                    for (int k = 0; k < C; ++k)
+                        if (cin[k]) acc = dadd(acc, dmul(r.v[k], r.v[k]));
+                }
+            }
+            // pre-smoothing of cycle k+1 (:66)
+#pragma unroll
+            for (int k = S2; k < S; ++k) {
+                const int out_row = jj - k - 1 + g.yoff;
+                cur = st[k].template step<WEIGHTED>(u & 1, cur, feed.f_row(k), coef, out_row > 0 && out_row < g.n - 1, cin);
+            }
+            const int xrow = jj - S;
+            if (owner && xrow >= r0 && xrow < r1) store_row<C>(xo + (ptrdiff_t)xrow * g.pitch + col, cur);
+            {   // residual + full weighting of cycle k+1 (:69-78), as in k_down
+                Row<C> r = rs.step(u & 1, cur, feed.f_row(S + 1), inv_h2);
+                const int rrow = jj - S - 1;
+                double left = __shfl_up_sync(0xffffffffu, r.v[C - 1], 1);
+                if (rrow & 1) {
+                    const int jc = (rrow - 1) >> 1;
+                    const int ic = col >> 1;
+                    double o[NP];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        double west = (q == 0) ? left : r.v[q == 0 ? 0 : 2 * q - 1];
+                        double edge = dadd(dadd(c_ew[q], r.v[2 * q]), s_mid[q]);
+                        double corner = dadd(dadd(s_cor[q], west), r.v[2 * q + 1]);
+                        double val = dadd(dadd(dmul(0.25, c_mid[q]), dmul(0.125, edge)), dmul(0.0625, corner));
+                        o[q] = (ic + q >= 1 && ic + q < nc - 1) ? val : 0.0;
+                        s_mid[q] = r.v[2 * q];
+                        s_cor[q] = dadd(west, r.v[2 * q + 1]);
+                    }
+                    if (owner && jc + ycoarse >= 1 && jc + ycoarse < nc - 1 && 2 * jc >= r0 && 2 * jc < r1 && jc >= 0 &&
+                        2 * jc < g.ny) {
+                        double *dst = cf + (ptrdiff_t)jc * pitch_c + ic;
+                        if (NP == 2)
+                            *reinterpret_cast<double2 *>(dst) = make_double2(o[0], o[NP - 1]);
+                        else
+                            *dst = o[0];
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        double west = (q == 0) ? left : r.v[q == 0 ? 0 : 2 * q - 1];
+                        c_mid[q] = r.v[2 * q];
+                        c_ew[q] = dadd(r.v[2 * q + 1], west);
+                    }
+                }
+            }
+            feed.end();
+        }
+    }
+    pdl_trigger();
+    cp_async_wait<0>();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = dadd(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if (lane == 0) partials[wid] = acc;
+}
+
 // ---- run-time variant table ---------------------------------------------------------------------
 struct VariantDesc {
     int c, pf, minb, sm;
@@ -757,7 +960,7 @@ int num_sms()
 #endif
 }
 
-StripGeom make_geom(const FusedLevel &lv, int stages, const VariantDesc &v, int ext_lo, int ext_hi)
+StripGeom make_geom(const FusedLevel &lv, int stages, const VariantDesc &v, int ext_lo, int ext_hi, int halo = -1)
 {
     const int n = lv.n;
     StripGeom g;
@@ -771,7 +974,7 @@ StripGeom make_geom(const FusedLevel &lv, int stages, const VariantDesc &v, int 
         g.row_hi = lv.span_hi;
     }
     g.pitch = lv.pitch;
-    g.halo = halo_for(stages);
+    g.halo = halo >= 0 ? halo : halo_for(stages);  // (an explicit halo must be a multiple of the columns per lane)
     g.stride = 32 * v.c - 2 * g.halo;
     g.n_strips = (n + g.stride - 1) / g.stride;
     // one resident wave: every warp of the grid is on an SM for the whole pass (no tail wave)
@@ -923,6 +1126,24 @@ void up_launch(const FusedLevel &lv, const double *e, int pitch_c, double omega,
     if (n_partials) *n_partials = norm ? g.n_strips * g.n_chunks : 0;
 }
 
+// geometry of the cross-cycle pass: 4 sweeps + residual + restriction eat 6 columns per side
+template <int C, int PF, int MINB, bool WEIGHTED>
+void cross_launch_w(const FusedLevel &lv_in, double *xb_out, const double *e, int pitch_c, double *cf, int lo, double *d_partials,
+                    int *n_partials, const JacobiCoef &c, const int *done, cudaStream_t st)
+{
+    // lv_in.xb = input (xb_k), lv_in.x = where x_k goes, lv_in.hp = the neighbours' copies of the input array (row slabs)
+    VariantDesc v{C, PF, MINB, 1};
+    StripGeom g = make_geom(lv_in, 6, v, 0, 0, 6);  // strips of 64 columns own 52: 19 % overlap instead of 25 % with 8
+    double inv = 1.0 / (lv_in.h * lv_in.h);
+    int nc = (lv_in.n - 1) / 2 + 1;
+    auto k = k_cross<C, PF, MINB, 2, 2, WEIGHTED>;
+    int sm = WARPS_PER_CTA * SmemFeed<C, PF, 4, true>::SMEM_PER_WARP;
+    PMG_SMEM_ONCE(k, sm);
+    PMG_LAUNCH(k, dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st, lv_in.xb, xb_out, lv_in.x, lv_in.f, e, cf, g, pitch_c, lo, nc, c,
+               inv, d_partials, done, lv_in.hp);
+    if (n_partials) *n_partials = g.n_strips * g.n_chunks;
+}
+
 }  // namespace
 
 bool fused_supported(int nu) { return nu >= 1 && nu <= 4; }
@@ -931,6 +1152,33 @@ int fused_take_bad_nu()
     int v = g_fused_bad_nu;
     g_fused_bad_nu = 0;
     return v;
+}
+
+// Cross-cycle pass on a level or a row slab of it: reads lv.xb (= xb_k), coarse_x (= e_k), lv.f; writes lv.x (= x_k), xb_out
+// (= xb_{k+1}, an array other than lv.xb), coarse_f and the norm partials of x_k.  nu1 = nu2 = 2 only.
+bool fused_cross_supported(int nu1, int nu2) { return nu1 == 2 && nu2 == 2; }
+int g_cross_minb = 4;
+void fused_set_cross_minb(int m) { g_cross_minb = (m >= 2 && m <= 4) ? m : 4; }
+void launch_fused_cross(const FusedLevel &lv, double *xb_out, const double *coarse_x, double *coarse_f, int pitch_c, double omega,
+                        int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st, const int *done)
+{
+    const int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
+    JacobiCoef c = jacobi_coef(lv.h, omega);
+#define PMG_CROSS(MINB)                                                                                                        \
+    do {                                                                                                                       \
+        if (c.weighted)                                                                                                        \
+            cross_launch_w<2, 2, MINB, true>(lv, xb_out, coarse_x, pitch_c, coarse_f, lo, d_partials, n_partials, c, done, st);  \
+        else                                                                                                                   \
+            cross_launch_w<2, 2, MINB, false>(lv, xb_out, coarse_x, pitch_c, coarse_f, lo, d_partials, n_partials, c, done, st); \
+    } while (0)
+    if (g_cross_minb == 4)
+        PMG_CROSS(4);
+    else if (g_cross_minb == 2)
+        PMG_CROSS(2);
+    else
+        PMG_CROSS(3);
+#undef PMG_CROSS
+    count_launch();
 }
 
 int fused_num_variants() { return NUM_VARIANTS; }

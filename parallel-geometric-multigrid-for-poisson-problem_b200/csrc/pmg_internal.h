@@ -318,6 +318,14 @@ void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, 
                      int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st,
                      const int *done = nullptr);
 int fused_max_partials(int n);
+// Cross-cycle pass (level 0 of a V-cycle solve, one GPU): Pass B of cycle k and Pass A of cycle k+1 in one sweep over
+// HBM -- reads lv.xb (xb_k), coarse_x (e_k), lv.f; writes lv.x (x_k), xb_out (xb_{k+1}, NOT lv.xb), coarse_f and the partial
+// sums of the residual norm of x_k.  36 B/point instead of 52.  Row slabs: lv.hp = the neighbours' copies of the INPUT array
+// (x_up / x_dn / x_keep / flags / epoch as for Pass A); rows [0, ny) are written, 6 halo rows above and 4 below are read.
+bool fused_cross_supported(int nu1, int nu2);
+void launch_fused_cross(const FusedLevel &lv, double *xb_out, const double *coarse_x, double *coarse_f, int pitch_c, double omega,
+                        int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st, const int *done = nullptr);
+void fused_set_cross_minb(int m);  // CTAs per SM promised to the compiler for the cross-cycle pass (2, 3, 4)
 // tuning: which (columns per lane, prefetch depth, CTAs per SM) instantiation the nu == 2 passes use
 int fused_num_variants();
 void fused_set_variant(int v);

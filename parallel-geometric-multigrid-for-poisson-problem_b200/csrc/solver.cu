@@ -49,6 +49,7 @@ static int g_debug_signals = install_debug_signals();
 
 thread_local std::string g_last_error;
 static int g_cluster_override = -1;  // pmg_set_cluster_top: -1 = PMG_CLUSTER / the default
+static int g_cross_override = -1;    // pmg_set_cross_cycle: -1 = PMG_CROSS / the default
 
 static pmg_status fail(pmg_status s, const std::string &msg)
 {
@@ -77,6 +78,8 @@ struct Level {
     // NVLink peer-to-peer halo exchange: the neighbours' boundary rows of x and f as seen from this process
     // (upper neighbour's row ny_up - PADY, lower neighbour's row 0) and the raw IPC mappings to close
     const double *up_x = nullptr, *dn_x = nullptr, *up_f = nullptr, *dn_f = nullptr;
+    // (level 0 only) the same for the two arrays the cross-cycle pass alternates between: [0] = xb, [1] = xc
+    const double *up_xb[2] = {nullptr, nullptr}, *dn_xb[2] = {nullptr, nullptr};
     int halo_epoch = 0;
 };
 
@@ -111,6 +114,14 @@ struct pmg_solver {
     cudaEvent_t ev_staged = nullptr, ev_snap = nullptr, ev_fetched = nullptr, ev_consumed = nullptr;
     bool staged = false, fetching = false;
     double *pcg_base[4] = {nullptr, nullptr, nullptr, nullptr};  // r, z, p, A p of pmg_pcg (level-0 layout; lazily allocated)
+    // cross-cycle solve (one GPU, V-cycles): per cycle ONE graph = coarse part from level 1 + the cross-cycle pass on level 0
+    // + the convergence kernel; [parity]: which of the two level-0 arrays is the pass's input
+    cudaGraphExec_t cross_graph[2] = {nullptr, nullptr};
+    int cross_graph_kernels[2] = {0, 0};
+    bool cross_on = true;      // PMG_CROSS=0: the classic two passes per cycle on level 0
+    double *base_xc = nullptr, *xc = nullptr;  // third level-0 array: xb and xc alternate as the cross pass's input / output
+    bool cross_active = false; // (row slabs) cycle_dist runs the cross pass instead of Pass B(0) / Pass A(0) of the next cycle
+    int cross_count = 0;       // cross passes queued in the current solve
     int cluster_top = 0;       // level size from which ONE 16-CTA cluster launch runs the rest of the cycle (257 / 129;
                                // 0: off -- PMG_CLUSTER=0, an unsuitable configuration, or a device that cannot co-schedule
                                // the cluster)
@@ -182,6 +193,11 @@ static void drop_graphs(pmg_solver *s)
             g = nullptr;
         }
     for (auto &g : s->mid_graph)
+        if (g) {
+            cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+    for (auto &g : s->cross_graph)
         if (g) {
             cudaGraphExecDestroy(g);
             g = nullptr;
@@ -507,8 +523,11 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
     // [-6, 8), [ny-8, ny+6) run on the communication stream while the compute stream works on the interior
     // rows [8, ny-8), which need no halo; the streams join before the next level.  Small slabs (the interior
     // is shorter than an exchange): exchange, then one launch.
-    double *halo_field = !x_is_zero ? L.x : (l > 0 ? L.f : nullptr);
-    const bool split = halo_field && L.ny >= s->split_min_rows && (up_nb || dn_nb);
+    // cross-cycle solve (level 0): from the second cycle on there is no Pass A -- the previous cycle's cross pass did its work
+    const bool cross = (l == 0) && s->cross_active;
+    const bool skip_pass_a = cross && s->cross_count > 0;
+    double *halo_field = skip_pass_a ? nullptr : (!x_is_zero ? L.x : (l > 0 ? L.f : nullptr));
+    const bool split = halo_field && !cross && L.ny >= s->split_min_rows && (up_nb || dn_nb);
     FusedLevel v = fused_view(L);
     HaloPeers halo_peers{};
     if (halo_field) {
@@ -583,7 +602,7 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         trace_mark(s, "passA_in", l);
         PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
         trace_mark(s, "passA_bd", l);
-    } else {
+    } else if (!skip_pass_a) {
         if (halo_on_comm) PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
         trace_mark(s, "halo", l);
         v.span_lo = up_nb ? -6 : 0;
@@ -650,8 +669,35 @@ static pmg_status cycle_dist(pmg_solver *s, int l, bool w_form, bool x_is_zero, 
         // with peer-memory exchanges the finest level's last pass ALWAYS looks at the control block's flag: a wait
         // that timed out raises it (HaloPeers::abort), so an iterate built on stale halo rows is never committed
         const int *guard = done ? done : (s->p2p ? &s->d_ctrl->done : nullptr);
-        launch_fused_up(v, coarse_x, K.pitch, c.nu2, c.omega, c.prolong_mode, want_norm ? s->d_partials : nullptr,
-                        n_partials, s->stream, l == 0 ? guard : nullptr);
+        if (cross) {
+            // Pass B of this cycle and Pass A of the next one in one sweep: reads xb_k (buffer `in`, whose halo rows the
+            // first cycle's Pass A computed and every later cycle pulls from the neighbours in the halo prologue), writes
+            // x_k into the iterate's array, xb_{k+1} into the other buffer and the next cycle's coarse right-hand side
+            const int par = s->cross_count & 1;
+            v.ext_lo = v.ext_hi = 0;
+            v.xb = par ? s->xc : L.xb;
+            double *out = par ? L.xb : s->xc;
+            if (s->cross_count > 0) {
+                HaloPeers hp{};
+                hp.x_up = up_nb ? L.up_xb[par] + (ptrdiff_t)PADY * L.pitch : nullptr;
+                hp.x_dn = dn_nb ? L.dn_xb[par] : nullptr;
+                hp.x_keep = v.xb;
+                hp.flag_up = up_nb ? s->d_flags + 0 : nullptr;
+                hp.flag_dn = dn_nb ? s->d_flags + 1 : nullptr;
+                hp.pub_up = up_nb ? s->up_flags + 1 : nullptr;
+                hp.pub_dn = dn_nb ? s->dn_flags + 0 : nullptr;
+                hp.epoch = ++L.halo_epoch;
+                hp.err = s->d_comm_err;
+                hp.abort = &s->d_ctrl->done;
+                v.hp = hp;
+            }
+            launch_fused_cross(v, out, coarse_x, K.f, K.pitch, c.omega, c.prolong_mode, s->d_partials, n_partials, s->stream,
+                               guard);
+            ++s->cross_count;
+        } else {
+            launch_fused_up(v, coarse_x, K.pitch, c.nu2, c.omega, c.prolong_mode, want_norm ? s->d_partials : nullptr,
+                            n_partials, s->stream, l == 0 ? guard : nullptr);
+        }
     }
     trace_mark(s, "passB", l);
     return PMG_OK;
@@ -1148,6 +1194,8 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     };
     (void)fused_max_partials(3);  // warms the cached SM count outside any stream capture
     if (const char *e = getenv("PMG_SMALL_VCYCLE")) s->small_vcycle = !(e[0] == '0');
+    if (const char *e = getenv("PMG_CROSS")) s->cross_on = !(e[0] == '0');
+    if (g_cross_override >= 0) s->cross_on = g_cross_override != 0;
     {
         // cluster kernel: needs the default coarse end of the hierarchy (coarsest level <= 17, reached by halving) and
         // the fused engine; PMG_CLUSTER=0 switches it off, PMG_CLUSTER=257 makes 257 the top instead of 129 (measured:
@@ -1282,6 +1330,9 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
                 s->agg_f[0] = s->aslab.base_f;
                 ok = ok && alloc_zero(&s->agg_f[1], s->aslab.elems) == PMG_OK;
             }
+            // the two arrays the cross-cycle pass alternates between on level 0 (neighbours pull their boundary rows)
+            ok = ok && alloc_zero(&s->base_xc, s->lv[0].elems) == PMG_OK;
+            if (s->base_xc) s->xc = s->base_xc + level_origin(s->lv[0].n);
             // (1) handle exchange: the same list on every rank, whatever happened locally so far
             std::vector<void *> bases;
             bases.push_back(s->d_flags);
@@ -1293,6 +1344,9 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
                 bases.push_back(s->agg_f[0]);
                 bases.push_back(s->agg_f[1]);
             }
+            const size_t cross_base_index = bases.size();
+            bases.push_back(s->lv[0].base_xb);
+            bases.push_back(s->base_xc);
             std::vector<std::vector<unsigned char>> hs(bases.size(), std::vector<unsigned char>((size_t)R * IPC_HANDLE_BYTES));
             for (size_t i = 0; i < bases.size(); ++i)
                 ok = (comm_ipc_exchange(bases[i], hs[i].data(), s->stream) == PMG_OK) && ok;
@@ -1347,6 +1401,21 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
                          cudaMemcpy(s->d_agg_srcs[b], srcs.data(), sizeof(double *) * R, cudaMemcpyHostToDevice) == cudaSuccess;
                 }
             }
+            {   // level 0: the neighbours' xb and xc arrays (cross-cycle pass)
+                Level &L = s->lv[0];
+                const size_t o = level_origin(L.n);
+                for (int which = 0; which < 2; ++which) {
+                    if (me > 0) {
+                        int ny_up = s->y1s[0][me - 1] - s->y0s[0][me - 1];
+                        const double *p = (const double *)open_peer(cross_base_index + which, me - 1);
+                        if (p) L.up_xb[which] = p + o + (ptrdiff_t)(ny_up - PADY) * L.pitch;
+                    }
+                    if (me < R - 1) {
+                        const double *p = (const double *)open_peer(cross_base_index + which, me + 1);
+                        if (p) L.dn_xb[which] = p + o;
+                    }
+                }
+            }
             // (3) every rank takes the same path: NVLink pulls if all mappings exist everywhere, NCCL otherwise
             double *d_agree = nullptr;
             bool all_ok = cudaMalloc((void **)&d_agree, sizeof(double) * (R + 1)) == cudaSuccess &&
@@ -1357,6 +1426,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
                 s->agg_maps.clear();
                 s->up_flags = s->dn_flags = nullptr;
                 for (int l = 0; l < s->agg_level; ++l) s->lv[l].up_x = s->lv[l].dn_x = s->lv[l].up_f = s->lv[l].dn_f = nullptr;
+                for (int w = 0; w < 2; ++w) s->lv[0].up_xb[w] = s->lv[0].dn_xb[w] = nullptr;
                 s->p2p = s->p2p_gather = false;
             } else {
                 const char *eg = getenv("PMG_P2P_GATHER");
@@ -1405,6 +1475,7 @@ void pmg_destroy(pmg_solver *s)
     }
     cudaFree(s->base_f_fmg0);
     for (double *b : s->pcg_base) cudaFree(b);
+    cudaFree(s->base_xc);
     cudaFree(s->base_f_stage);
     cudaFree(s->base_x_snap);
     for (cudaStream_t st : {s->copy_in_stream, s->copy_out_stream})
@@ -1715,6 +1786,18 @@ pmg_status pmg_f_cycle_from(pmg_solver *s, const double *phi_init, const double 
     return PMG_OK;
 }
 
+// cross-cycle pass on row slabs: needs the halo prologue over NVLink peer memory and at least two slab levels (the next
+// cycle's coarse right-hand side is written at the END of a cycle: with one slab level it would land in the all-gather's
+// double buffer of the wrong parity)
+static bool cross_ok_dist(const pmg_solver *s, bool w)
+{
+    return s->cross_on && !w && s->dist && s->p2p && s->p2p_fused && fused_halo_prologue() && s->agg_level >= 2 &&
+           s->xc != nullptr && fused_cross_supported(s->cfg.nu1, s->cfg.nu2) && s->cfg.norm_mode == PMG_NORM_TREE &&
+           g_trace_on != 1 &&
+           (s->rank == 0 || (s->lv[0].up_xb[0] && s->lv[0].up_xb[1])) &&
+           (s->rank == s->n_ranks - 1 || (s->lv[0].dn_xb[0] && s->lv[0].dn_xb[1]));
+}
+
 /* Fused V/W solve with device-side convergence control: cycles are queued one batch ahead of the host's
  * knowledge of the residual, the last kernel of each cycle records ||r||^2 and raises `done`, and every
  * kernel queued after that returns at once.  The GPU never waits for the host between cycles. */
@@ -1740,6 +1823,13 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
         if (rc0 != PMG_OK) return rc0;
     }
     launch_solve_begin(s->d_scalar, s->d_ctrl, s->d_hist2, rel_tol, max_cycles, s->stream);
+    // row slabs: the cross-cycle pass replaces Pass B(0) of a cycle and Pass A(0) of the next one (cycle_dist)
+    s->cross_active = s->dist && cross_ok_dist(s, w);
+    s->cross_count = 0;
+    struct CrossOff {
+        pmg_solver *s;
+        ~CrossOff() { s->cross_active = false; }
+    } cross_off{s};
     // enough queued work to cover a host round trip: one cycle on big grids, a few on small ones
     const int batch = L.n >= 2049 ? 1 : (L.n >= 513 ? 2 : 4);
     int queued = 0, slot = 0;
@@ -1792,6 +1882,134 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
     return PMG_OK;
 }
 
+// ---- cross-cycle solve (one GPU, V-cycles, nu1 = nu2 = 2) -------------------------------------------------------------
+// On level 0 the last pass of cycle k (prolongation, post-smoothing, norm) and the first pass of cycle k+1 (pre-smoothing,
+// residual, restriction) are back-to-back sweeps over the same array.  k_cross does both in one sweep: x_k lives only in
+// the register pipeline, and level 0 moves 28 B/point per cycle instead of 52.  xb and a third array xc alternate as the
+// pass's input and output; when the device-side control reports convergence after cycle k, the input array of that pass
+// (xb_k) and the coarse correction e_k are still intact, and ONE ordinary Pass B produces the iterate the reference
+// returns.  (Row slabs write x_k every cycle instead, see k_cross.)  Iterates are bit-identical to the two-pass path; the
+// norms differ in the last bits only (another grouping of the tree sum).
+static bool cross_ok(const pmg_solver *s, bool w)
+{
+    return s->cross_on && !w && !s->dist && s->fused && fused_cross_supported(s->cfg.nu1, s->cfg.nu2) &&
+           s->cfg.norm_mode == PMG_NORM_TREE && s->lv.size() > 2 && s->lv[1].n > s->cfg.n_coarse && fused_graph_ok(s);
+}
+
+static pmg_status ensure_xc(pmg_solver *s)
+{
+    if (s->base_xc) return PMG_OK;
+    pmg_status rc = alloc_zero(&s->base_xc, s->lv[0].elems);
+    if (rc != PMG_OK) return rc;
+    s->xc = s->base_xc + level_origin(s->lv[0].n);
+    return PMG_OK;
+}
+
+// one cycle's worth of work after the level-0 pre-smoothing: coarse part from level 1, cross pass, convergence kernel
+static pmg_status run_cross_cycle(pmg_solver *s, int parity)
+{
+    cudaGraphExec_t &ge = s->cross_graph[parity];
+    int &gk = s->cross_graph_kernels[parity];
+    if (ge != nullptr) {
+        PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+        count_launch(gk);
+        return PMG_OK;
+    }
+    const pmg_config &c = s->cfg;
+    Level &L = s->lv[0];
+    Level &K = s->lv[1];
+    const int *done = &s->d_ctrl->done;
+    const unsigned long long before = launches_so_far();
+    PMG_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    pmg_status rc = cycle_fused(s, 1, false, true, false, nullptr, done);
+    int np = 0;
+    if (rc == PMG_OK) {
+        FusedLevel v = fused_view(L);
+        v.x = nullptr;                            // x_k is not written (solve_cross produces it once, at the end)
+        v.xb = parity ? s->xc : L.xb;             // input: xb_k
+        double *out = parity ? L.xb : s->xc;      // output: xb_{k+1}
+        launch_fused_cross(v, out, K.x, K.f, K.pitch, c.omega, c.prolong_mode, s->d_partials, &np, s->stream, done);
+        launch_cycle_finish(s->d_partials, np, s->d_ctrl, s->d_hist2, s->stream);
+    }
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaStreamEndCapture (cross cycle): ") + cudaGetErrorString(e));
+    if (rc != PMG_OK) {
+        cudaGraphDestroy(g);
+        return rc;
+    }
+    gk = (int)(launches_so_far() - before);
+    e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(PMG_ERR_CUDA, std::string("cudaGraphInstantiate (cross cycle): ") + cudaGetErrorString(e));
+    PMG_CUDA(cudaGraphLaunch(ge, s->stream));
+    return PMG_OK;
+}
+
+static pmg_status solve_cross(pmg_solver *s, double rel_tol, int max_cycles, double *res_history, int *n_cycles_out)
+{
+    const pmg_config &c = s->cfg;
+    Level &L = s->lv[0];
+    Level &K = s->lv[1];
+    pmg_status rc = ensure_xc(s);
+    if (rc != PMG_OK) return rc;
+    PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = residual_norm2_async(s)) != PMG_OK) return rc;
+    launch_solve_begin(s->d_scalar, s->d_ctrl, s->d_hist2, rel_tol, max_cycles, s->stream);
+    const int *done = &s->d_ctrl->done;
+    // first half of cycle 1: xb = S^nu1(x), coarse f = R(f - A xb)
+    launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, false, s->stream, done);
+    const int batch = L.n >= 2049 ? 1 : (L.n >= 513 ? 2 : 4);
+    int queued = 0, slot = 0;
+    bool pending[2] = {false, false};
+    bool finished = max_cycles <= 0;
+    while (!finished) {
+        const int b = std::min(batch, max_cycles - queued);
+        for (int i = 0; i < b; ++i) {
+            if ((rc = run_cross_cycle(s, queued & 1)) != PMG_OK) return rc;
+            ++queued;
+        }
+        launch_ctrl_to_host(s->d_ctrl, &s->h_ctrl[slot], nullptr, nullptr, 0, s->stream);
+        PMG_CUDA(cudaEventRecord(s->ev_batch[slot], s->stream));
+        pending[slot] = true;
+        const int prev = slot ^ 1;
+        if (pending[prev]) {
+            PMG_CUDA(cudaEventSynchronize(s->ev_batch[prev]));
+            pending[prev] = false;
+            if (((volatile SolveCtrl *)s->h_ctrl)[prev].done) finished = true;
+        }
+        if (queued >= max_cycles || b == 0) finished = true;
+        slot ^= 1;
+    }
+    launch_ctrl_to_host(s->d_ctrl, &s->h_ctrl[0], s->d_hist2, s->h_hist, s->hist_cap, s->stream);
+    PMG_CUDA(cudaStreamSynchronize(s->stream));
+    PMG_CUDA(cudaGetLastError());
+    const int k = ((volatile SolveCtrl *)s->h_ctrl)[0].cycles;
+    if (k < 0 || k > max_cycles)
+        return fail(PMG_ERR_CUDA, "solve control block corrupted (cycles = " + std::to_string(k) + ")");
+    if (k > 0) {
+        // x_k = S^nu2(xb_k + P e_k): xb_k is the input array of the k-th cross pass; e_k is still level 1's iterate, because
+        // every kernel queued after the pass that raised `done` returned at once
+        FusedLevel v = fused_view(L);
+        v.xb = ((k - 1) & 1) ? s->xc : L.xb;
+        launch_fused_up(v, K.x, K.pitch, c.nu2, c.omega, c.prolong_mode, nullptr, nullptr, s->stream, nullptr);
+    }
+    PMG_CUDA(cudaEventRecord(s->ev1, s->stream));
+    PMG_CUDA(cudaEventSynchronize(s->ev1));
+    PMG_CUDA(cudaGetLastError());
+    if (const int bad = fused_take_bad_nu())
+        return fail(PMG_ERR_UNSUPPORTED, "fused engine: no kernel for " + std::to_string(bad) + " sweeps per pass");
+    if (res_history) {
+        const volatile double *h2 = s->h_hist;
+        for (int i = 0; i <= k; ++i) res_history[i] = std::sqrt(h2[i]);
+    }
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    if (n_cycles_out) *n_cycles_out = k;
+    return PMG_OK;
+}
+
 static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol, int max_cycles, double *res_history,
                              int *n_cycles_out);
 
@@ -1811,8 +2029,11 @@ static pmg_status solve_impl(pmg_solver *s, pmg_cycle_kind kind, double rel_tol,
     if (!s || max_cycles < 0) return fail(PMG_ERR_INVALID, "bad argument");
     PMG_CUDA(cudaSetDevice(s->device));
     if (s->fused && (kind == PMG_CYCLE_V || kind == PMG_CYCLE_W) && s->cfg.norm_mode == PMG_NORM_TREE &&
-        s->lv.size() > 1 && s->lv[0].n > s->cfg.n_coarse && (s->dist || fused_graph_ok(s)))
-        return solve_fused_async(s, kind == PMG_CYCLE_W, rel_tol, max_cycles, res_history, n_cycles_out);
+        s->lv.size() > 1 && s->lv[0].n > s->cfg.n_coarse && (s->dist || fused_graph_ok(s))) {
+        if (max_cycles + 1 > s->hist_cap || !cross_ok(s, kind == PMG_CYCLE_W))
+            return solve_fused_async(s, kind == PMG_CYCLE_W, rel_tol, max_cycles, res_history, n_cycles_out);
+        return solve_cross(s, rel_tol, max_cycles, res_history, n_cycles_out);
+    }
     if (s->p2p) PMG_CUDA(cudaMemsetAsync(&s->d_ctrl->done, 0, sizeof(int), s->stream));  // see pmg_cycle
     PMG_CUDA(cudaEventRecord(s->ev0, s->stream));
     pmg_status rc = residual_norm2_async(s);
@@ -1977,6 +2198,11 @@ int pmg_small_vcycle_version(void) { return vcycle_small_version(); }
 /* programmatic dependent launch of the cycle kernels (pmg_internal.h); takes effect for solvers created afterwards
  * (captured graphs keep the edges they were captured with) */
 void pmg_set_pdl(int on) { pdl_set_enabled(on); }
+
+/* cross-cycle solve (level 0: Pass B of cycle k and Pass A of cycle k+1 fused) for solvers created afterwards: 1, 0, or
+ * -1 = PMG_CROSS / the default (on) */
+void pmg_set_cross_cycle(int on) { g_cross_override = on < 0 ? -1 : (on ? 1 : 0); }
+void pmg_fused_set_cross_minb(int m) { fused_set_cross_minb(m); }
 
 /* top level of the 16-CTA cluster kernel for solvers created afterwards: 257, 129, 0 = off, -1 = PMG_CLUSTER / default */
 void pmg_set_cluster_top(int n) { g_cluster_override = (n == 257 || n == 129 || n == 0) ? n : -1; }

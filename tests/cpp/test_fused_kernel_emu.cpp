@@ -126,6 +126,68 @@ static Expected expected_visit(Dense &x, Dense &f, Dense &e, double h, double om
     return E;
 }
 
+// ---- cross-cycle pass: Pass B of cycle k + Pass A of cycle k+1 in one launch (k_cross) -------------------------------
+static void cross_level(int n, double omega, int prolong, int sms, int minb)
+{
+    emu_num_sms = sms;
+    fused_set_cross_minb(minb);
+    const int nc = (n - 1) / 2 + 1;
+    const double h = 1.0 / (n - 1);
+    Dense xb(n), f(n), e(nc);
+    xb.randomize(true);
+    f.randomize(true);
+    e.randomize(false);
+    // what the two separate passes produce
+    Dense xk = xb;
+    orc_prolong_add(xk.v.data(), e.v.data(), n, nc, prolong);
+    orc_jacobi(xk.v.data(), f.v.data(), n, n, h, omega, 1, 0.0, nullptr);
+    Dense r(n);
+    orc_residual(r.v.data(), xk.v.data(), f.v.data(), n, n, h);
+    const double nn = orc_norm(r.v.data(), (long)n * n);
+    Dense xb2 = xk;
+    orc_jacobi(xb2.v.data(), f.v.data(), n, n, h, omega, 1, 0.0, nullptr);
+    Dense r2(n), cf(nc);
+    orc_residual(r2.v.data(), xb2.v.data(), f.v.data(), n, n, h);
+    orc_restrict_fw(r2.v.data(), cf.v.data(), n, nc);
+    // the kernel
+    Padded pin(n, n), pout(n, n), pxk(n, n), pf(n, n), pe(nc, nc), pcf(nc, nc);
+    pin.load(xb, 0, 0, n);
+    pf.load(f, 0, 0, n);
+    pe.load(e, 0, 0, nc);
+    pout.fill_rows(0, n, std::nan(""));
+    pxk.fill_rows(0, n, std::nan(""));
+    Padded pin0 = pin, pf0 = pf, pe0 = pe, pcf0 = pcf;
+    FusedLevel lv{};
+    lv.x = (minb == 2) ? nullptr : pxk.p();  // nullptr: x_k is not written (one-GPU solve)
+    lv.xb = pin.p();
+    lv.f = pf.p();
+    lv.n = n;
+    lv.pitch = pin.pitch;
+    lv.h = h;
+    std::vector<double> partials((size_t)fused_max_partials(n), 0.0);
+    int np = 0;
+    launch_fused_cross(lv, pout.p(), pe.p(), pcf.p(), pe.pitch, omega, prolong, partials.data(), &np, nullptr, nullptr);
+    bool ok_x = true, ok_c = true, ok_k = true;
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) {
+            ok_x = ok_x && same_bits(pout.at(y, x), xb2.at(y, x));
+            ok_k = ok_k && (minb == 2 ? std::isnan(pxk.at(y, x)) : same_bits(pxk.at(y, x), xk.at(y, x)));
+        }
+    check(ok_k, "cross: x_k = S^2(xb + P e)", n, sms, minb);
+    for (int y = 0; y < nc; ++y)
+        for (int x = 0; x < nc; ++x) ok_c = ok_c && same_bits(pcf.at(y, x), cf.at(y, x));
+    double sum = 0.0;
+    for (int i = 0; i < np; ++i) sum += partials[(size_t)i];
+    check(ok_x, "cross: xb' = S^2(S^2(xb + P e))", n, sms, minb);
+    check(ok_c, "cross: coarse f = R(f - A xb')", n, sms, minb);
+    check(std::fabs(sum - nn * nn) <= 1e-12 * nn * nn, "cross: residual norm of x_k", n, sms, minb);
+    check(pin.untouched_outside(pin0, 0, 0) && pf.untouched_outside(pf0, 0, 0) && pe.untouched_outside(pe0, 0, 0),
+          "cross: inputs untouched", n, sms, minb);
+    check(pcf.untouched_outside(pcf0, 1, nc - 1), "cross: coarse ring and padding untouched", n, sms, minb);
+    std::printf("cross-cycle pass n=%d omega=%.3f prolong=%d sms=%d minb=%d: %s\n", n, omega, prolong, sms, minb,
+                (ok_x && ok_c) ? "bit-identical" : "MISMATCH");
+}
+
 // ---- whole level (one GPU) ---------------------------------------------------------------------------------------
 static void whole_level(int n, double omega, int nu1, int nu2, int prolong, bool x_is_zero, int variant, int sms)
 {
@@ -409,6 +471,104 @@ static void slab_visit(int n, int ranks, bool first_visit, bool split, int prolo
     std::fflush(stdout);
 }
 
+// ---- cross-cycle pass on row slabs: the input's halo rows come from the neighbours' arrays through the halo prologue ----
+static void slab_cross(int n, int ranks, int prolong, int sms)
+{
+    emu_num_sms = sms;
+    fused_set_cross_minb(3);
+    const double omega = 2.0 / 3.0;
+    const int nc = (n - 1) / 2 + 1, epoch = 11;
+    const double h = 1.0 / (n - 1);
+    Dense xb(n), f(n), e(nc);
+    xb.randomize(true);
+    f.randomize(false);
+    e.randomize(false);
+    Dense xk = xb;
+    orc_prolong_add(xk.v.data(), e.v.data(), n, nc, prolong);
+    orc_jacobi(xk.v.data(), f.v.data(), n, n, h, omega, 1, 0.0, nullptr);
+    Dense r(n);
+    orc_residual(r.v.data(), xk.v.data(), f.v.data(), n, n, h);
+    const double nn = orc_norm(r.v.data(), (long)n * n);
+    Dense xb2 = xk;
+    orc_jacobi(xb2.v.data(), f.v.data(), n, n, h, omega, 1, 0.0, nullptr);
+    Dense r2(n), cf(nc);
+    orc_residual(r2.v.data(), xb2.v.data(), f.v.data(), n, n, h);
+    orc_restrict_fw(r2.v.data(), cf.v.data(), n, nc);
+    std::vector<Rank> R;
+    for (int q = 0; q < ranks; ++q) {
+        int y0, y1;
+        partition(n, ranks, q, y0, y1);
+        R.emplace_back(n, nc, y0, y1, y0 / 2, (y1 == n) ? nc : y1 / 2);
+    }
+    const double poison = std::nan("");
+    for (int q = 0; q < ranks; ++q) {
+        Rank &K = R[q];
+        const bool up = q > 0, dn = q < ranks - 1;
+        K.xb.load(xb, K.y0, K.y0, K.y1);  // the input array: owned rows; halo rows must come from the neighbours
+        if (up) K.xb.fill_rows(-PADY, 0, poison);
+        if (dn) K.xb.fill_rows(K.ny, K.ny + PADY, poison);
+        K.f.load(f, K.y0, std::max(0, K.y0 - PADY), std::min(n, K.y1 + PADY));  // level 0: the f halo is local
+        K.e.fill_rows(-PADY, K.nyc + PADY, poison);
+        for (int xx = -PADX; xx < K.e.pitch - PADX; ++xx)
+            for (int y = -PADY; y < K.nyc + PADY; ++y)
+                if (xx < 0 || xx >= nc) K.e.at(y, xx) = 0.0;
+        K.e.load(e, K.yc0, std::max(0, K.yc0 - 4), std::min(nc, K.yc1 + 4));
+        if (K.yc0 - 4 < 0) K.e.fill_rows(-PADY, 0, 0.0);
+        if (K.yc1 + 4 > nc) K.e.fill_rows(K.nyc, K.nyc + PADY, 0.0);
+        K.inbox[0] = K.inbox[1] = epoch;
+    }
+    std::vector<int> outbox(2 * ranks, 0);
+    double s2 = 0.0;
+    for (int q = 0; q < ranks; ++q) {
+        Rank &K = R[q];
+        const bool up = q > 0, dn = q < ranks - 1;
+        Padded out(n, K.ny), out0 = out;
+        FusedLevel lv{};
+        lv.x = K.x.p();  // x_k goes here
+        lv.xb = K.xb.p();
+        lv.f = K.f.p();
+        lv.n = n;
+        lv.pitch = K.x.pitch;
+        lv.h = h;
+        lv.ny = K.ny;
+        lv.yoff = K.y0;
+        HaloPeers hp{};
+        hp.x_up = up ? R[q - 1].xb.p() + (ptrdiff_t)R[q - 1].ny * K.x.pitch : nullptr;
+        hp.x_dn = dn ? R[q + 1].xb.p() : nullptr;
+        hp.x_keep = K.xb.p();
+        hp.flag_up = up ? &K.inbox[0] : nullptr;
+        hp.flag_dn = dn ? &K.inbox[1] : nullptr;
+        hp.pub_up = up ? &outbox[2 * q] : nullptr;
+        hp.pub_dn = dn ? &outbox[2 * q + 1] : nullptr;
+        hp.epoch = epoch;
+        int err = 0;
+        hp.err = &err;
+        lv.hp = hp;
+        Padded xk0 = K.x, cf0 = K.cf;
+        std::vector<double> partials((size_t)fused_max_partials(n), 0.0);
+        int np = 0;
+        launch_fused_cross(lv, out.p(), K.e.p(), K.cf.p(), K.cf.pitch, omega, prolong, partials.data(), &np, nullptr, nullptr);
+        check(err == 0, "cross slab: flag wait failed", n, q);
+        check((!up || outbox[2 * q] == epoch) && (!dn || outbox[2 * q + 1] == epoch), "cross slab: epoch not published", n, q);
+        bool ok_b = true, ok_k = true, ok_c = true;
+        for (int y = 0; y < K.ny; ++y)
+            for (int xx = 0; xx < n; ++xx) {
+                ok_b = ok_b && same_bits(out.at(y, xx), xb2.at(y + K.y0, xx));
+                ok_k = ok_k && same_bits(K.x.at(y, xx), xk.at(y + K.y0, xx));
+            }
+        for (int y = 0; y < K.nyc; ++y)
+            for (int xx = 0; xx < nc; ++xx) ok_c = ok_c && same_bits(K.cf.at(y, xx), cf.at(y + K.yc0, xx));
+        check(ok_b, "cross slab: xb'", n, q, ranks);
+        check(ok_k, "cross slab: x_k", n, q, ranks);
+        check(ok_c, "cross slab: coarse f", n, q, ranks);
+        check(out.untouched_outside(out0, 0, K.ny) && K.x.untouched_outside(xk0, 0, K.ny), "cross slab wrote outside the owned rows", n, q);
+        check(K.cf.untouched_outside(cf0, 0, K.nyc), "cross slab wrote coarse f outside the owned rows", n, q);
+        for (int i = 0; i < np; ++i) s2 += partials[(size_t)i];
+    }
+    check(std::fabs(s2 - nn * nn) <= 1e-12 * nn * nn, "cross slab: residual norm summed over the ranks", n, ranks);
+    std::printf("cross-cycle pass on %d slabs n=%d prolong=%d sms=%d: done\n", ranks, n, prolong, sms);
+}
+
 int main(int argc, char **argv)
 {
     const bool full = argc > 1 && std::strcmp(argv[1], "full") == 0;
@@ -422,6 +582,14 @@ int main(int argc, char **argv)
     whole_level(33, 0.8, 3, 1, ORC_PROLONG_REFERENCE, true, -1, 1);
     whole_level(33, w, 4, 4, ORC_PROLONG_REFERENCE, false, -1, 148);
     for (int nu = 1; nu <= 4; ++nu) smoothing_pass(65, w, nu, nu == 3 ? 1 : 148);
+    // cross-cycle pass (Pass B of cycle k + Pass A of cycle k+1): strips of 52 owned columns, several chunk geometries
+    cross_level(65, w, ORC_PROLONG_REFERENCE, 148, 3);
+    cross_level(129, w, ORC_PROLONG_FULL, 148, 4);
+    cross_level(129, 1.0, ORC_PROLONG_REFERENCE, 2, 2);   // few SMs: tall chunks, chunk overlap exercised
+    cross_level(257, w, ORC_PROLONG_REFERENCE, 1, 3);
+    slab_cross(129, 2, ORC_PROLONG_REFERENCE, 148);
+    slab_cross(257, 3, ORC_PROLONG_FULL, 2);
+    slab_cross(257, 4, ORC_PROLONG_REFERENCE, 148);
     // row slabs
     slab_visit(129, 2, false, false, ORC_PROLONG_REFERENCE, 148, true);   // finest level, iterate exchanged
     slab_visit(129, 2, true, false, ORC_PROLONG_REFERENCE, 148, false);   // coarse level, first visit: f exchanged

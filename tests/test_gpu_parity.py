@@ -489,3 +489,42 @@ def test_jacobi_pass_blocking_is_bit_exact(orc):
         s.smooth(8, block)
         assert np.array_equal(s.get_solution(), want)
         s.close()
+
+
+@pytest.mark.parametrize("n,prolong,omega", [(257, pmg.PROLONG_REFERENCE, 2.0 / 3.0), (1025, pmg.PROLONG_FULL, 1.0),
+                                             (4097, pmg.PROLONG_REFERENCE, 2.0 / 3.0)])
+def test_cross_cycle_solve_matches_two_pass_solve(orc, n, prolong, omega):
+    """pmg_solve's cross-cycle path (level 0: Pass B of cycle k and Pass A of cycle k+1 in ONE sweep, k_cross; the
+    default for V(2,2) solves) against the classic two passes per cycle: same cycle count, iterate bit-identical, norms
+    equal to the last bits (the tree sum runs over another strip geometry); max_cycles cut-offs and a second solve on the
+    same handle included; at N = 257 also against the oracle."""
+    f = cc.random_rhs(n, seed=91)
+    phi0 = np.random.default_rng(92).standard_normal((n, n))
+    got = {}
+    for cross in (0, 1):
+        pmg.set_cross_cycle(cross)
+        with pmg.Solver(n, omega=omega, prolong_mode=prolong) as s:
+            s.set_rhs(f)
+            s.set_guess(phi0)
+            k, hist = s.solve(pmg.V, rel_tol=1e-8, max_cycles=60)
+            x_full = s.get_solution()
+            s.set_guess(phi0)
+            k3, hist3 = s.solve(pmg.V, rel_tol=0.0, max_cycles=3)    # even / odd numbers of cross passes
+            x3 = s.get_solution()
+            k4, hist4 = s.solve(pmg.V, rel_tol=0.0, max_cycles=4)    # continues from x3
+            x7 = s.get_solution()
+            norm_after = s.cycle(pmg.V)                              # the classic cycle still works on the same handle
+            got[cross] = (k, hist, x_full, k3, hist3, x3, k4, hist4, x7, norm_after)
+    pmg.set_cross_cycle(-1)
+    a, b = got[0], got[1]
+    assert a[0] == b[0] and a[3] == b[3] == 3 and a[6] == b[6] == 4
+    for i in (2, 5, 8):
+        assert np.array_equal(a[i], b[i]), i
+    for i in (1, 4, 7):
+        assert np.max(np.abs(a[i] - b[i]) / a[i]) <= 1e-13, i
+    assert abs(a[9] - b[9]) <= 1e-13 * a[9]
+    if n == 257:
+        want = phi0.copy()
+        for _ in range(3):
+            orc.cycle(want, f, kind=cc.V, omega=omega, eps=0.0, alpha=1, prolong=prolong)
+        assert np.array_equal(b[5], want)
