@@ -162,12 +162,17 @@ def hbm_peak():
 
 def ncu_traffic(kernel_prefix, n):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r1_ncu_full_fused_passes_n16385.json, level-0 passes at N = 16385)."""
+    `ncu --set full` captures (profiles/r1_ncu_full_fused_passes_n16385.json: the two level-0 passes;
+    profiles/r2_ncu_full_k_cross_n16385.json: the cross-cycle pass), N = 16385."""
     if n != 16385:
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_fused_passes_n16385.json")) as fh:
-            recs = json.load(fh)
+        recs = []
+        for name in ("r1_ncu_full_fused_passes_n16385.json", "r2_ncu_full_k_cross_n16385.json"):
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                with open(path) as fh:
+                    recs += json.load(fh)
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         tot = []
         for r in recs:
@@ -424,6 +429,7 @@ def run_single(args):
     s = pmg.Solver(n, omega=OMEGA, prolong_mode=prolong, device=0)
     s.set_rhs_sine()
     max_cycles = 100
+    cross_cycle = s.cross_cycle
 
     def step():
         s.zero_guess()
@@ -451,10 +457,21 @@ def run_single(args):
     # ---- roofline of the dominant kernel (level-0 fused passes), timed alone with CUDA events ----
     t_down = s.bench_pass(0, 0, 5)
     t_upn = s.bench_pass(1, 0, 5)
-    alg_bytes = BYTES_PER_POINT_PASS * n * n
-    dom_ms, dom_name = (t_upn, "k_up<nu2=2,prolong,norm>") if t_upn >= t_down else (t_down, "k_down<nu1=2,resid>")
+    try:
+        t_cross = s.bench_pass(4, 0, 5)   # the kernel pmg_solve actually spends its time in (cross-cycle pass)
+    except Exception:  # noqa: BLE001
+        t_cross = None
+    if t_cross is not None:
+        # one launch does a whole level visit's streaming work: SURVEY 8(d)'s per-unit figure is 52 B per level-point
+        # (Pass B + Pass A); the pass itself moves 28 B per point -- both reported, `frac` by the SURVEY figure
+        alg_bytes = 2 * BYTES_PER_POINT_PASS * n * n
+        dom_ms, dom_name = t_cross, "k_cross<nu2=2,nu1=2> (Pass B of cycle k + Pass A of cycle k+1 in one sweep)"
+        traffic = ncu_traffic("k_cross", n)
+    else:
+        alg_bytes = BYTES_PER_POINT_PASS * n * n
+        dom_ms, dom_name = (t_upn, "k_up<nu2=2,prolong,norm>") if t_upn >= t_down else (t_down, "k_down<nu1=2,resid>")
+        traffic = ncu_traffic("k_up" if t_upn >= t_down else "k_down", n)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = ncu_traffic("k_up" if t_upn >= t_down else "k_down", n)
     cycle_gbs = BYTES_PER_DOF_CYCLE * n * n * k / (dev_ms / args.steps * 1e-3) / 1e9
     # Jacobi sweep sub-metric: one HBM pass per sweep, 24 B/point
     s.smooth(3, 1)
@@ -500,7 +517,7 @@ def run_single(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
             "cycles_to_converge": k, "converged": converged, "final_rel_residual": float(hist[-1] / hist[0]),
             "cycles_match": parity["cycles_match"], "history_max_rel_dev": parity["history_max_rel_dev"],
-            "history_parity": parity,
+            "history_parity": parity, "cross_cycle_pass": cross_cycle,
             "gdof_cycle_per_s": n * n * k / (dev_ms / args.steps * 1e-3) / 1e9,
             "device_ms_per_step": dev_ms / args.steps,
             "legs": legs,
@@ -509,8 +526,14 @@ def run_single(args):
                          "traffic_source": "committed ncu --set full capture (profiles/), not re-measured in this run",
                          "kernel": dom_name,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms, "peak_source": peak_src,
-                         "pass_down_ms": t_down, "pass_up_norm_ms": t_upn,
-                         "vcycle_effective_gbs_at_69.3B_per_dof": cycle_gbs, "vcycle_frac": cycle_gbs / peak},
+                         "pass_down_ms": t_down, "pass_up_norm_ms": t_upn, "pass_cross_ms": t_cross,
+                         "two_pass_frac": BYTES_PER_POINT_PASS * n * n / (max(t_down, t_upn) * 1e-3) / 1e9 / peak,
+                         "cross_pass_bytes_moved_per_point": 28.0,
+                         "cross_pass_frac_at_28B_per_point": (28.0 * n * n / (t_cross * 1e-3) / 1e9 / peak) if t_cross else None,
+                         "note": "the cross-cycle pass is issue- and energy-bound, not HBM-bound: it does the work the "
+                                 "SURVEY figure prices at 52 B/point while moving 28 (DESIGN.md 4.4)",
+                         "vcycle_effective_gbs_at_69.3B_per_dof": cycle_gbs, "vcycle_frac": cycle_gbs / peak,
+                         "vcycle_frac_at_45.3B_per_dof_cross_minimum": cycle_gbs * (45.3 / BYTES_PER_DOF_CYCLE) / peak},
             "jacobi_sweep": {"gbs_24B_per_point": jac_gbs, "frac": jac_gbs / peak,
                              "blocked4_effective_gbs": jac_blocked_gbs},
             "cpu_baseline": cpu, "reference_cuda_build": ref_cuda, "e2e": e2e, "gpu_launches": int(launches),

@@ -48,6 +48,7 @@ def run(args):
                    agglomerate_below=args.agglomerate_below)
     y0, y1 = s.local_rows
     ny = y1 - y0
+    cross_cycle = s.cross_cycle
     s.set_rhs_sine()
     max_cycles = 100
 
@@ -133,7 +134,7 @@ def run(args):
                 "cycles_to_converge": k, "converged": bool(hist[-1] < bench.REL_TOL * hist[0]),
                 "final_rel_residual": float(hist[-1] / hist[0]),
                 "cycles_match": parity["cycles_match"], "history_max_rel_dev": parity["history_max_rel_dev"],
-                "history_parity": parity, "legs": legs,
+                "history_parity": parity, "cross_cycle_pass": cross_cycle, "legs": legs,
                 "gdof_cycle_per_s": n * n * k / (dev_ms / args.steps * 1e-3) / 1e9,
                 "device_ms_per_step": dev_ms / args.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

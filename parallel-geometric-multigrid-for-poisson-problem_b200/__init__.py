@@ -353,6 +353,14 @@ class Solver:
         return v.value
 
     @property
+    def cross_cycle(self):
+        """True if pmg_solve(V) on this handle takes the cross-cycle path (level 0: Pass B + next Pass A in one sweep)."""
+        L = lib()
+        L.pmg_cross_cycle_active.restype = ctypes.c_int
+        L.pmg_cross_cycle_active.argtypes = [ctypes.c_void_p]
+        return bool(L.pmg_cross_cycle_active(self._h))
+
+    @property
     def cluster_top(self):
         """Level size from which one cluster launch runs the rest of the cycle (0: not in use)."""
         L = lib()
@@ -444,7 +452,7 @@ def set_cross_cycle(on, minb=None):
     L = lib()
     L.pmg_set_cross_cycle.restype = None
     L.pmg_set_cross_cycle.argtypes = [ctypes.c_int]
-    L.pmg_set_cross_cycle(-1 if on == -1 else (1 if on else 0))
+    L.pmg_set_cross_cycle(-1 if on == -1 else (2 if on == 2 else (1 if on else 0)))
     if minb is not None:
         L.pmg_fused_set_cross_minb.restype = None
         L.pmg_fused_set_cross_minb.argtypes = [ctypes.c_int]

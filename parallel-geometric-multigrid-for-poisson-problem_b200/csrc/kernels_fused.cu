@@ -1156,9 +1156,24 @@ int fused_take_bad_nu()
 
 // Cross-cycle pass on a level or a row slab of it: reads lv.xb (= xb_k), coarse_x (= e_k), lv.f; writes lv.x (= x_k), xb_out
 // (= xb_{k+1}, an array other than lv.xb), coarse_f and the norm partials of x_k.  nu1 = nu2 = 2 only.
-bool fused_cross_supported(int nu1, int nu2) { return nu1 == 2 && nu2 == 2; }
 int g_cross_minb = 4;
-void fused_set_cross_minb(int m) { g_cross_minb = (m >= 2 && m <= 4) ? m : 4; }
+bool fused_cross_supported(int nu1, int nu2) { return nu1 == 2 && nu2 == 2; }
+// Fraction of the resident warp slots the cross-cycle pass fills on an n-column level of `rows` rows.  The grid is one
+// resident wave of (strips x chunks) warps with chunks = floor(slots / strips): at n = 32769 the 631 strips of 52 columns
+// leave 3 chunks = 80 % of the slots (the two-pass kernels' 586 strips of 56 columns give 4 chunks = 99 %), and the pass
+// is then SLOWER than the two passes it replaces (8 GPUs, N = 32769: 1.81 -> 1.86 ms per cycle).  The solve uses it only
+// above 0.9.
+double fused_cross_utilisation(int n, int rows)
+{
+    FusedLevel lv{};
+    lv.n = n;
+    lv.ny = rows;
+    lv.pitch = level_pitch(n);
+    VariantDesc v{2, 2, g_cross_minb, 1};
+    StripGeom g = make_geom(lv, 6, v, 0, 0, 6);
+    return (double)(g.n_strips * g.n_chunks) / (double)(num_sms() * v.minb * WARPS_PER_CTA);
+}
+void fused_set_cross_minb(int m) { g_cross_minb = (m >= 2 && m <= 6) ? m : 4; }
 void launch_fused_cross(const FusedLevel &lv, double *xb_out, const double *coarse_x, double *coarse_f, int pitch_c, double omega,
                         int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st, const int *done)
 {
@@ -1175,6 +1190,10 @@ void launch_fused_cross(const FusedLevel &lv, double *xb_out, const double *coar
         PMG_CROSS(4);
     else if (g_cross_minb == 2)
         PMG_CROSS(2);
+    else if (g_cross_minb == 5)
+        PMG_CROSS(5);
+    else if (g_cross_minb == 6)
+        PMG_CROSS(6);
     else
         PMG_CROSS(3);
 #undef PMG_CROSS

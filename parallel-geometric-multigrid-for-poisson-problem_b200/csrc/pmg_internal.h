@@ -323,6 +323,7 @@ int fused_max_partials(int n);
 // sums of the residual norm of x_k.  36 B/point instead of 52.  Row slabs: lv.hp = the neighbours' copies of the INPUT array
 // (x_up / x_dn / x_keep / flags / epoch as for Pass A); rows [0, ny) are written, 6 halo rows above and 4 below are read.
 bool fused_cross_supported(int nu1, int nu2);
+double fused_cross_utilisation(int n, int rows);  // resident warp slots the pass fills (the solve wants >= 0.9)
 void launch_fused_cross(const FusedLevel &lv, double *xb_out, const double *coarse_x, double *coarse_f, int pitch_c, double omega,
                         int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st, const int *done = nullptr);
 void fused_set_cross_minb(int m);  // CTAs per SM promised to the compiler for the cross-cycle pass (2, 3, 4)

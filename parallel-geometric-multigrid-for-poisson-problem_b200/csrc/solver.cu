@@ -119,6 +119,7 @@ struct pmg_solver {
     cudaGraphExec_t cross_graph[2] = {nullptr, nullptr};
     int cross_graph_kernels[2] = {0, 0};
     bool cross_on = true;      // PMG_CROSS=0: the classic two passes per cycle on level 0
+    bool cross_forced = false; // PMG_CROSS=2 / pmg_set_cross_cycle(2): also where the pass does not fill the machine
     double *base_xc = nullptr, *xc = nullptr;  // third level-0 array: xb and xc alternate as the cross pass's input / output
     bool cross_active = false; // (row slabs) cycle_dist runs the cross pass instead of Pass B(0) / Pass A(0) of the next cycle
     int cross_count = 0;       // cross passes queued in the current solve
@@ -1194,8 +1195,14 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     };
     (void)fused_max_partials(3);  // warms the cached SM count outside any stream capture
     if (const char *e = getenv("PMG_SMALL_VCYCLE")) s->small_vcycle = !(e[0] == '0');
-    if (const char *e = getenv("PMG_CROSS")) s->cross_on = !(e[0] == '0');
-    if (g_cross_override >= 0) s->cross_on = g_cross_override != 0;
+    if (const char *e = getenv("PMG_CROSS")) {
+        s->cross_on = !(e[0] == '0');
+        s->cross_forced = (e[0] == '2');
+    }
+    if (g_cross_override >= 0) {
+        s->cross_on = g_cross_override != 0;
+        s->cross_forced = g_cross_override == 2;
+    }
     {
         // cluster kernel: needs the default coarse end of the hierarchy (coarsest level <= 17, reached by halving) and
         // the fused engine; PMG_CLUSTER=0 switches it off, PMG_CLUSTER=257 makes 257 the top instead of 129 (measured:
@@ -1793,7 +1800,7 @@ static bool cross_ok_dist(const pmg_solver *s, bool w)
 {
     return s->cross_on && !w && s->dist && s->p2p && s->p2p_fused && fused_halo_prologue() && s->agg_level >= 2 &&
            s->xc != nullptr && fused_cross_supported(s->cfg.nu1, s->cfg.nu2) && s->cfg.norm_mode == PMG_NORM_TREE &&
-           g_trace_on != 1 &&
+           g_trace_on != 1 && (s->cross_forced || fused_cross_utilisation(s->lv[0].n, s->lv[0].ny) >= 0.9) &&
            (s->rank == 0 || (s->lv[0].up_xb[0] && s->lv[0].up_xb[1])) &&
            (s->rank == s->n_ranks - 1 || (s->lv[0].dn_xb[0] && s->lv[0].dn_xb[1]));
 }
@@ -1893,7 +1900,8 @@ static pmg_status solve_fused_async(pmg_solver *s, bool w, double rel_tol, int m
 static bool cross_ok(const pmg_solver *s, bool w)
 {
     return s->cross_on && !w && !s->dist && s->fused && fused_cross_supported(s->cfg.nu1, s->cfg.nu2) &&
-           s->cfg.norm_mode == PMG_NORM_TREE && s->lv.size() > 2 && s->lv[1].n > s->cfg.n_coarse && fused_graph_ok(s);
+           s->cfg.norm_mode == PMG_NORM_TREE && s->lv.size() > 2 && s->lv[1].n > s->cfg.n_coarse && fused_graph_ok(s) &&
+           (s->cross_forced || fused_cross_utilisation(s->lv[0].n, s->lv[0].n) >= 0.9);
 }
 
 static pmg_status ensure_xc(pmg_solver *s)
@@ -2201,7 +2209,13 @@ void pmg_set_pdl(int on) { pdl_set_enabled(on); }
 
 /* cross-cycle solve (level 0: Pass B of cycle k and Pass A of cycle k+1 fused) for solvers created afterwards: 1, 0, or
  * -1 = PMG_CROSS / the default (on) */
-void pmg_set_cross_cycle(int on) { g_cross_override = on < 0 ? -1 : (on ? 1 : 0); }
+void pmg_set_cross_cycle(int on) { g_cross_override = on < 0 ? -1 : (on >= 2 ? 2 : (on ? 1 : 0)); }
+/* 1 if the last / next pmg_solve(PMG_CYCLE_V) on this handle takes the cross-cycle path */
+int pmg_cross_cycle_active(const pmg_solver *s)
+{
+    if (!s) return 0;
+    return s->dist ? (cross_ok_dist(s, false) ? 1 : 0) : (cross_ok(s, false) ? 1 : 0);
+}
 void pmg_fused_set_cross_minb(int m) { fused_set_cross_minb(m); }
 
 /* top level of the 16-CTA cluster kernel for solvers created afterwards: 257, 129, 0 = off, -1 = PMG_CLUSTER / default */
@@ -2310,7 +2324,8 @@ pmg_status pmg_smooth(pmg_solver *s, int sweeps, int block)
 }
 
 /* Times one fused pass of level `level` in isolation: which = 0 Pass A (sweeps+residual+restriction),
- * 1 Pass B with the residual norm, 2 Pass B without, 3 Pass A with x == 0 (coarse-level form).  `reps`
+ * 1 Pass B with the residual norm, 2 Pass B without, 3 Pass A with x == 0 (coarse-level form), 4 the cross-cycle pass
+ * (Pass B of one cycle + Pass A of the next; level 0, one GPU, x_k not written as in pmg_solve).  `reps`
  * launches between two CUDA events on the solver stream; *ms_avg = average per launch.  Clobbers the
  * iterate (benchmark use only). */
 pmg_status pmg_bench_pass(pmg_solver *s, int which, int level, int reps, double *ms_avg)
@@ -2322,8 +2337,18 @@ pmg_status pmg_bench_pass(pmg_solver *s, int which, int level, int reps, double 
     Level &K = s->lv[level + 1];
     const pmg_config &c = s->cfg;
     int np = 0;
+    if (which == 4) {
+        if (level != 0 || s->dist || !fused_cross_supported(c.nu1, c.nu2))
+            return fail(PMG_ERR_UNSUPPORTED, "cross-cycle pass: level 0, one GPU, nu1 = nu2 = 2");
+        pmg_status rcx = ensure_xc(s);
+        if (rcx != PMG_OK) return rcx;
+    }
     auto one = [&]() {
-        if (which == 0 || which == 3)
+        if (which == 4) {
+            FusedLevel v = fused_view(L);
+            v.x = nullptr;
+            launch_fused_cross(v, s->xc, K.x, K.f, K.pitch, c.omega, c.prolong_mode, s->d_partials, &np, s->stream);
+        } else if (which == 0 || which == 3)
             launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, which == 3, s->stream);
         else
             launch_fused_up(fused_view(L), K.x, K.pitch, c.nu2, c.omega, c.prolong_mode,

@@ -14,7 +14,7 @@ ok = True
 for n, prolong in ((257, pmg.PROLONG_REFERENCE), (1025, pmg.PROLONG_FULL), (4097, pmg.PROLONG_REFERENCE),
                    (16385, pmg.PROLONG_REFERENCE), (16385, pmg.PROLONG_FULL)):
     ref = None
-    for cross, minb in ((0, 3), (1, 2), (1, 3), (1, 4), (0, 3)):
+    for cross, minb in ((0, 3), (1, 3), (1, 4), (1, 5), (1, 6), (0, 3)):
         pmg.set_cross_cycle(cross, minb)
         s = pmg.Solver(n, omega=2.0 / 3.0, prolong_mode=prolong)
         s.set_rhs_sine()
