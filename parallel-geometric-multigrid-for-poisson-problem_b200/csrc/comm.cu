@@ -49,6 +49,7 @@ struct NcclApi {
 
 NcclApi g_nccl;
 ncclComm_t g_comm = nullptr;
+double *g_agree = nullptr;  // 1 + n_ranks doubles, allocated with the communicator: comm_all_agree must never need memory
 int g_rank = 0, g_nranks = 1, g_device = 0;
 
 bool load_nccl(std::string &err)
@@ -259,6 +260,8 @@ void *comm_ipc_open(const unsigned char *handle)
 bool comm_all_agree(bool ok, double *d_scratch /* 1 + n_ranks doubles */, cudaStream_t st)
 {
     if (!g_comm) return ok;
+    if (d_scratch == nullptr) d_scratch = g_agree;
+    if (d_scratch == nullptr) return false;
     double mine = ok ? 1.0 : 0.0;
     std::vector<double> all((size_t)g_nranks, 0.0);
     cudaMemcpyAsync(d_scratch, &mine, sizeof(double), cudaMemcpyHostToDevice, st);
@@ -345,6 +348,10 @@ pmg_status pmg_comm_init(const unsigned char id[PMG_COMM_ID_BYTES], int rank, in
     g_rank = rank;
     g_nranks = n_ranks;
     g_device = device;
+    if (cudaMalloc((void **)&g_agree, sizeof(double) * (size_t)(n_ranks + 1)) != cudaSuccess) {
+        cudaGetLastError();
+        g_agree = nullptr;
+    }
     return PMG_OK;
 }
 
@@ -353,6 +360,10 @@ pmg_status pmg_comm_finalize(void)
     if (g_comm) {
         g_nccl.CommDestroy(g_comm);
         g_comm = nullptr;
+    }
+    if (g_agree) {
+        cudaFree(g_agree);
+        g_agree = nullptr;
     }
     g_rank = 0;
     g_nranks = 1;

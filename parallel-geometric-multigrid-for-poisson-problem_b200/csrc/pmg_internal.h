@@ -362,7 +362,7 @@ pmg_status comm_allgather_double(const double *d_mine, double *d_all, cudaStream
 constexpr int IPC_HANDLE_BYTES = 64;
 pmg_status comm_ipc_exchange(void *base, unsigned char *handles /* n_ranks * IPC_HANDLE_BYTES */, cudaStream_t st);
 void *comm_ipc_open(const unsigned char *handle);
-bool comm_all_agree(bool ok, double *d_scratch /* 1 + n_ranks doubles */, cudaStream_t st);
+bool comm_all_agree(bool ok, double *d_scratch /* 1 + n_ranks doubles; nullptr: the communicator's own */, cudaStream_t st);
 void comm_ipc_close(void *peer);
 
 // ---- NVLink peer-to-peer halo exchange (kernels_basic.cu) -------------------------------------------------

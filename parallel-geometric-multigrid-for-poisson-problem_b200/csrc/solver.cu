@@ -1189,6 +1189,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     s->fused = (cfg->engine == PMG_ENGINE_FUSED) && fused_supported(cfg->nu1) && fused_supported(cfg->nu2) &&
                !(cfg->smoother_eps > 0.0) && cfg->smoother == PMG_SMOOTHER_JACOBI && !cfg->smoother_fp32;
     pmg_status rc = PMG_OK;
+    pmg_status local_fail = PMG_OK;  // (several ranks) first rank-local failure of the set-up, agreed upon collectively
     auto bail = [&](pmg_status st) {
         pmg_destroy(s);
         return st;
@@ -1263,17 +1264,17 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         s->aslab = s->lv[la];
         slab_shape(s->aslab, la);
         Level &A = s->aslab;
-        if ((rc = alloc_zero(&A.base_x, A.elems)) != PMG_OK) return bail(rc);
-        if ((rc = alloc_zero(&A.base_f, A.elems)) != PMG_OK) return bail(rc);
+        if ((rc = alloc_zero(&A.base_x, A.elems)) != PMG_OK) local_fail = rc;
+        if ((rc = alloc_zero(&A.base_f, A.elems)) != PMG_OK) local_fail = rc;
         A.x = A.base_x + level_origin(A.n);
         A.f = A.base_f + level_origin(A.n);
-        if ((rc = alloc_zero(&s->d_gather, (size_t)cfg->n_ranks)) != PMG_OK) return bail(rc);
+        if ((rc = alloc_zero(&s->d_gather, (size_t)cfg->n_ranks)) != PMG_OK) local_fail = rc;
         // highest priority: its small latency-bound kernels (NCCL, boundary strips) are scheduled ahead of the
         // bandwidth-bound interior pass they run beside
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         if (cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess)
-            return bail(fail(PMG_ERR_CUDA, "cudaStreamCreate failed"));
+            local_fail = fail(PMG_ERR_CUDA, "cudaStreamCreate failed");
         cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s->ev_passb, cudaEventDisableTiming);
@@ -1304,9 +1305,11 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
     }
     for (size_t l = 0; l < s->lv.size(); ++l) {
         Level &L = s->lv[l];
-        if ((rc = alloc_zero(&L.base_x, L.elems)) != PMG_OK) return bail(rc);
-        if ((rc = alloc_zero(&L.base_xb, L.elems)) != PMG_OK) return bail(rc);
-        if ((rc = alloc_zero(&L.base_f, L.elems)) != PMG_OK) return bail(rc);
+        // (several ranks: a failure here must not leave the OTHER ranks waiting in the IPC collectives below -- it is
+        // recorded and every rank leaves together after comm_all_agree)
+        if ((rc = alloc_zero(&L.base_x, L.elems)) != PMG_OK) { if (!dist) return bail(rc); local_fail = rc; }
+        if ((rc = alloc_zero(&L.base_xb, L.elems)) != PMG_OK) { if (!dist) return bail(rc); local_fail = rc; }
+        if ((rc = alloc_zero(&L.base_f, L.elems)) != PMG_OK) { if (!dist) return bail(rc); local_fail = rc; }
         size_t o = level_origin(L.n);
         L.x = L.base_x + o;
         L.xb = L.base_xb + o;
@@ -1317,6 +1320,11 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         }
     }
     if (dist) {
+        // every rank-local allocation is behind us: agree on the outcome before the first collective of the set-up
+        if (!comm_all_agree(local_fail == PMG_OK, nullptr, s->stream)) {
+            if (local_fail == PMG_OK) fail(PMG_ERR_ALLOC, "set-up failed on another rank (allocation); all ranks leave pmg_create together");
+            return bail(local_fail == PMG_OK ? PMG_ERR_ALLOC : local_fail);
+        }
         const char *env = getenv("PMG_P2P");
         bool want = !(env && env[0] == '0');
         if (want) {
@@ -2450,6 +2458,28 @@ pmg_status pmg_test_fused_up(const pmg_test_slab *t, const double *coarse_x, int
     PMG_CUDA(cudaDeviceSynchronize());
     PMG_CUDA(cudaGetLastError());
     return PMG_OK;
+}
+
+/* the cross-cycle pass on a caller-built slab: t->xb = input (xb_k), t->x = where x_k goes (nullable), t->x_up / x_dn /
+ * x_keep / flags = the neighbours' copies of the INPUT array (halo prologue) */
+pmg_status pmg_test_fused_cross(const pmg_test_slab *t, double *xb_out, const double *coarse_x, double *coarse_f, int pitch_c,
+                                double omega, int prolong_mode, double *d_partials, int *n_partials)
+{
+    if (!t || !xb_out || !coarse_x || !coarse_f || !d_partials) return fail(PMG_ERR_INVALID, "bad argument");
+    pmg_status rc = require_device();
+    if (rc != PMG_OK) return rc;
+    launch_fused_cross(test_view(t), xb_out, coarse_x, coarse_f, pitch_c, omega, prolong_mode, d_partials, n_partials, nullptr);
+    PMG_CUDA(cudaDeviceSynchronize());
+    PMG_CUDA(cudaGetLastError());
+    return PMG_OK;
+}
+
+/* wall-time limit of the peer-flag waits (PMG_P2P_TIMEOUT_S), in milliseconds: lets a test provoke the time-out path */
+void pmg_set_p2p_timeout_ms(double ms)
+{
+    const unsigned long long ns = (unsigned long long)((ms > 0.0 ? ms : 30000.0) * 1e6);
+    fused_set_wait_timeout_ns(ns);
+    basic_set_wait_timeout_ns(ns);
 }
 
 int pmg_test_fused_max_partials(int n) { return fused_max_partials(n); }

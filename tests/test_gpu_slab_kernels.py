@@ -253,3 +253,146 @@ def test_slab_passes_match_oracle_on_one_gpu(orc, n, ranks, first_visit, split, 
         total += float(partials.numpy()[:np_out.value].sum())
     if level0 and not first_visit:
         assert abs(total - want_norm2) <= 1e-12 * want_norm2
+
+
+def _lib_cross():
+    L = _lib()
+    L.pmg_test_fused_cross.argtypes = [ctypes.POINTER(TestSlab), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.POINTER(ctypes.c_int)]
+    L.pmg_set_p2p_timeout_ms.restype = None
+    L.pmg_set_p2p_timeout_ms.argtypes = [ctypes.c_double]
+    return L
+
+
+def _cross_ranks(orc, n, ranks, prolong, seed):
+    """inputs of one cross-cycle pass on `ranks` row slabs + what the oracle's operator sequence gives on the whole level:
+    x_k = S^2 (xb + P e), ||f - A x_k||^2, xb' = S^2 x_k, coarse f = R (f - A xb')"""
+    nc, h = (n - 1) // 2 + 1, 1.0 / (n - 1)
+    rng = np.random.default_rng(seed)
+    xb = rng.uniform(-1, 1, (n, n))
+    f = np.zeros((n, n))
+    f[1:-1, 1:-1] = rng.uniform(-1, 1, (n - 2, n - 2))
+    e = np.zeros((nc, nc))
+    e[1:-1, 1:-1] = rng.uniform(-1, 1, (nc - 2, nc - 2))
+    xk = xb.copy()
+    orc.prolong_add(xk, e, prolong)
+    orc.jacobi(xk, f, h, omega=OMEGA, num_iter=1)
+    norm2 = orc.norm(orc.residual(xk, f, h)) ** 2
+    xb2 = xk.copy()
+    orc.jacobi(xb2, f, h, omega=OMEGA, num_iter=1)
+    cf = orc.restrict_fw(orc.residual(xb2, f, h))
+    R = []
+    for r in range(ranks):
+        y0, y1 = partition(n, ranks, r)
+        c0, c1 = y0 // 2, (nc if y1 == n else y1 // 2)
+        ny, nyc = y1 - y0, c1 - c0
+        up, dn = r > 0, r < ranks - 1
+        K = dict(y0=y0, y1=y1, ny=ny, c0=c0, nyc=nyc, up=up, dn=dn)
+        pxb, pxk, pout, pf, pcf, pe = (Padded(n, ny), Padded(n, ny), Padded(n, ny), Padded(n, ny), Padded(nc, nyc),
+                                       Padded(nc, nyc))
+        pxb.view(0, ny)[:] = xb[y0:y1]  # the input array: owned rows; the halo rows must come from the neighbours
+        if up:
+            pxb.view(-PADY, 0)[:] = np.nan
+        if dn:
+            pxb.view(ny, ny + PADY)[:] = np.nan
+        a, b = max(0, y0 - PADY), min(n, y1 + PADY)  # level 0: the f halo is local
+        pf.view(a - y0, b - y0)[:] = f[a:b]
+        pe.view(-PADY, nyc + PADY)[:] = np.nan
+        a, b = max(0, c0 - 4), min(nc, c0 + nyc + 4)
+        pe.view(a - c0, b - c0)[:] = e[a:b]
+        if c0 - 4 < 0:
+            pe.view(-PADY, 0)[:] = 0.0
+        if c0 + nyc + 4 > nc:
+            pe.view(nyc, nyc + PADY)[:] = 0.0
+        for p in (pxb, pxk, pout, pf, pcf, pe):
+            p.upload()
+        K.update(xb=pxb, xk=pxk, out=pout, f=pf, cf=pcf, e=pe, inbox=DevInts([EPOCH, EPOCH]), outbox=DevInts([0, 0]),
+                 err=DevInts([0]))
+        R.append(K)
+    return R, dict(xk=xk, xb2=xb2, cf=cf, norm2=norm2, nc=nc, h=h)
+
+
+def _cross_slab(R, r, n, h):
+    K = R[r]
+    t = TestSlab()
+    t.x, t.xb, t.f = K["xk"].ptr(), K["xb"].ptr(), K["f"].ptr()
+    t.n, t.pitch, t.h, t.ny, t.yoff = n, K["xb"].pitch, h, K["ny"], K["y0"]
+    t.span_lo, t.span_hi = 0, K["ny"]
+    t.x_up = R[r - 1]["xb"].ptr(R[r - 1]["ny"]) if K["up"] else None
+    t.x_dn = R[r + 1]["xb"].ptr() if K["dn"] else None
+    t.x_keep = K["xb"].ptr()
+    t.flag_up = K["inbox"].at(0) if K["up"] else None
+    t.flag_dn = K["inbox"].at(1) if K["dn"] else None
+    t.pub_up = K["outbox"].at(0) if K["up"] else None
+    t.pub_dn = K["outbox"].at(1) if K["dn"] else None
+    t.epoch, t.err = EPOCH, K["err"].ptr
+    return t
+
+
+@pytest.mark.parametrize("n,ranks,prolong", [
+    (257, 2, pmg.PROLONG_REFERENCE),
+    (257, 3, pmg.PROLONG_FULL),
+    (513, 4, pmg.PROLONG_REFERENCE),
+    (1025, 8, pmg.PROLONG_REFERENCE),
+])
+def test_cross_cycle_pass_on_slabs_matches_oracle_on_one_gpu(orc, n, ranks, prolong):
+    """GPU twin of slab_cross in tests/cpp/test_fused_kernel_emu.cpp: Pass B of cycle k + Pass A of cycle k+1 in one
+    sweep over a row slab, the input's halo rows pulled from the neighbours by the halo prologue"""
+    L = _lib_cross()
+    R, W = _cross_ranks(orc, n, ranks, prolong, 300 + n + ranks)
+    maxp = L.pmg_test_fused_max_partials(n)
+    total = 0.0
+    for r, K in enumerate(R):
+        t = _cross_slab(R, r, n, W["h"])
+        partials = pmg.DeviceArray.from_numpy(np.zeros(maxp))
+        np_out = ctypes.c_int()
+        pmg.check(L.pmg_test_fused_cross(ctypes.byref(t), K["out"].ptr(), K["e"].ptr(), K["cf"].ptr(), K["cf"].pitch, OMEGA,
+                                         prolong, partials.ptr, ctypes.byref(np_out)))
+        assert K["err"].get()[0] == 0
+        out = K["outbox"].get()
+        assert (not K["up"] or out[0] == EPOCH) and (not K["dn"] or out[1] == EPOCH), "epoch not published"
+        ny, y0 = K["ny"], K["y0"]
+        for name, want in (("out", W["xb2"]), ("xk", W["xk"])):
+            got = K[name].download()
+            assert np.array_equal(got.view(0, ny), want[y0:y0 + ny]), "rank %d: %s" % (r, name)
+            outside = got.h.copy()
+            outside[PADY:PADY + ny, PADX:PADX + n] = 0.0
+            assert not outside.any(), "rank %d: the cross pass wrote %s outside the owned rows" % (r, name)
+        gcf = K["cf"].download()
+        assert np.array_equal(gcf.view(0, K["nyc"]), W["cf"][K["c0"]:K["c0"] + K["nyc"]]), "rank %d: coarse f" % r
+        outside = gcf.h.copy()
+        outside[PADY:PADY + K["nyc"], PADX:PADX + W["nc"]] = 0.0
+        assert not outside.any(), "rank %d: the cross pass wrote the coarse array outside its owned rows" % r
+        total += float(partials.numpy()[:np_out.value].sum())
+    assert abs(total - W["norm2"]) <= 1e-12 * W["norm2"]
+
+
+def test_peer_flag_wait_times_out_and_reports(orc):
+    """A neighbour that never publishes its epoch: the wait gives up after the wall-time limit (PMG_P2P_TIMEOUT_S; 50 ms
+    here), raises the error word and the kernel still terminates -- the path pmg_solve turns into PMG_ERR_COMM"""
+    import time
+    L = _lib_cross()
+    n, ranks = 257, 2
+    R, W = _cross_ranks(orc, n, ranks, pmg.PROLONG_REFERENCE, 77)
+    K = R[1]
+    K["inbox"] = DevInts([EPOCH - 1, EPOCH - 1])  # the upper neighbour is one epoch behind
+    t = _cross_slab(R, 1, n, W["h"])
+    partials = pmg.DeviceArray.from_numpy(np.zeros(L.pmg_test_fused_max_partials(n)))
+    np_out = ctypes.c_int()
+    L.pmg_set_p2p_timeout_ms(50.0)
+    try:
+        t0 = time.perf_counter()
+        pmg.check(L.pmg_test_fused_cross(ctypes.byref(t), K["out"].ptr(), K["e"].ptr(), K["cf"].ptr(), K["cf"].pitch, OMEGA,
+                                         pmg.PROLONG_REFERENCE, partials.ptr, ctypes.byref(np_out)))
+        dt = time.perf_counter() - t0
+        assert K["err"].get()[0] != 0, "the time-out did not raise the error word"
+        assert 0.04 <= dt < 5.0, "waited %.3f s for a 50 ms limit" % dt
+        # the same wait in Pass A (halo prologue flavour)
+        K["err"] = DevInts([0])
+        t.err = K["err"].ptr
+        t.span_lo, t.span_hi = -6, K["ny"]
+        pmg.check(L.pmg_test_fused_down(ctypes.byref(t), K["cf"].ptr(), K["cf"].pitch, 2, OMEGA, 0, 1))
+        assert K["err"].get()[0] != 0
+    finally:
+        L.pmg_set_p2p_timeout_ms(0.0)  # back to the default
