@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(1024)
         c.h2 = h[k] * h[k];
         c.omega = omega;
         c.om1 = 1.0 - omega;
+        c.w4 = 0.25 * omega;
         c.weighted = (omega != 1.0);
         return c;
     };
@@ -714,6 +715,7 @@ inline JacobiCoef make_coef(double h, double omega)
     c.h2 = h * h;
     c.omega = omega;
     c.om1 = 1.0 - omega;
+    c.w4 = 0.25 * omega;
     c.weighted = (omega != 1.0);
     return c;
 }

@@ -137,14 +137,16 @@ __device__ __forceinline__ void co_fill_htab(double *tab, int t, double h0, int 
 // bilinear prolongation weight pattern (MultiGrid.hpp:208-226) without divergent branches: all four coarse neighbours are
 // loaded (they exist for every interior fine point), the three candidate sums are formed in the reference's order and the
 // one that applies to the point's parity is selected -- the selected value is bit-identical to the branchy form
-__device__ __forceinline__ double prolong_value(const double *q, int nc, int x, int y)
+__device__ __forceinline__ double prolong_add(double fine, const double *q, int nc, int x, int y)
 {
     const double q0 = q[0], q1 = q[1], qn = q[nc], qn1 = q[nc + 1];
-    const double ex = dmul(0.5, dadd(q0, q1));
-    const double ey = dmul(0.5, dadd(q0, qn));
-    const double exy = dmul(0.25, dadd(dadd(dadd(q0, q1), qn), qn1));
+    const double sx = dadd(q0, q1);
+    const double sy = dadd(q0, qn);
+    const double sxy = dadd(dadd(sx, qn), qn1);
     const bool ox = (x & 1) != 0, oy = (y & 1) != 0;
-    return oy ? (ox ? exy : ey) : (ox ? ex : q0);
+    const double sum = oy ? (ox ? sxy : sy) : (ox ? sx : q0);
+    const double w = oy ? (ox ? 0.25 : 0.5) : (ox ? 0.5 : 1.0);
+    return dfma_pow2(w, sum, fine);  // the weight is a power of two: one rounding, that of fine + w * sum
 }
 
 // this thread's points of level N: index into an N x N array, or -1
@@ -180,8 +182,7 @@ __device__ __forceinline__ void co_sweeps(double *&cur, double *&oth, const doub
         for (int p = 0; p < Geo<N>::PTS; ++p) {
             const int i = P.idx[p];
             double acc = dadd(dadd(dadd(dadd(hf[p], cur[i - 1]), cur[i + 1]), cur[i - N]), cur[i + N]);
-            double jac = dmul(0.25, acc);
-            double v = WEIGHTED ? dadd(dmul(c.om1, xc[p]), dmul(c.omega, jac)) : jac;
+            double v = WEIGHTED ? dadd(dmul(c.om1, xc[p]), dmul(c.w4, acc)) : dmul(0.25, acc);
             if (P.act[p]) oth[i] = v;
             xc[p] = v;
         }
@@ -266,8 +267,8 @@ __device__ void co_visit(CoCtx &c, const int t)
             for (int p = 0; p < G::PTS; ++p) {
                 const int i = P.idx[p];
                 const int y = i / N, x = i - y * N;
-                const double v = prolong_value(e + (y >> 1) * NC + (x >> 1), NC, x, y);
-                if (P.act[p] && y >= c.lo && x >= c.lo) cur[i] = dadd(cur[i], v);
+                const double v = prolong_add(cur[i], e + (y >> 1) * NC + (x >> 1), NC, x, y);
+                if (P.act[p] && y >= c.lo && x >= c.lo) cur[i] = v;
             }
             group_sync<N>();
         }
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(Geo<N0>::THREADS)
     c.gamma = gamma;
     c.coef.omega = omega;
     c.coef.om1 = 1.0 - omega;
+    c.coef.w4 = 0.25 * omega;
     c.coef.weighted = WEIGHTED ? 1 : 0;
     c.coef.h2 = 0.0;
     c.par = 0u;
@@ -453,8 +455,7 @@ __device__ __forceinline__ void dist_sweeps(double *&cur, double *&oth, const do
         for (int p = 0; p < G::PTS; ++p) {
             const int i = P.idx[p];
             double acc = dadd(dadd(dadd(dadd(hf[p], cur[i - 1]), cur[i + 1]), cur[i - N]), cur[i + N]);
-            double jac = dmul(0.25, acc);
-            double v = WEIGHTED ? dadd(dmul(c.om1, xc[p]), dmul(c.omega, jac)) : jac;
+            double v = WEIGHTED ? dadd(dmul(c.om1, xc[p]), dmul(c.w4, acc)) : dmul(0.25, acc);
             if (P.act[p]) oth[i] = v;
             if (P.push_up[p]) *co_map_rank(oth + (G::R + 1) * N + 1 + P.tx, rank - 1) = v;
             if (P.push_dn[p]) *co_map_rank(oth + 1 + P.tx, rank + 1) = v;
@@ -571,7 +572,7 @@ __device__ void dist_visit(CoCtx &c, const int t, const int rank)
                     q = e + (((j - 1) >> 1) + 1) * NC + (x >> 1);  // stored coarse row of global coarse row y >> 1
                 else
                     q = e + (y >> 1) * NC + (x >> 1);
-                cur[j * N + x] = dadd(cur[j * N + x], prolong_value(q, NC, x, y));
+                cur[j * N + x] = prolong_add(cur[j * N + x], q, NC, x, y);
             }
         }
         __syncthreads();
@@ -626,6 +627,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
     c.gamma = gamma;
     c.coef.omega = omega;
     c.coef.om1 = 1.0 - omega;
+    c.coef.w4 = 0.25 * omega;
     c.coef.weighted = WEIGHTED ? 1 : 0;
     c.coef.h2 = 0.0;
     c.par = 0u;

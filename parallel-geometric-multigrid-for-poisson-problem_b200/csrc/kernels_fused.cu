@@ -109,6 +109,14 @@ __device__ __forceinline__ void neighbours(const Row<C> &c, Row<C> &w, Row<C> &e
     }
 }
 
+// fine += P e for one point: `sum` = the coarse values the point interpolates, unscaled (1, 2 or 4 of them); the weight
+// 1 / 0.5 / 0.25 follows from the parities of the fine row and column and is applied inside the addition (exact)
+__device__ __forceinline__ double add_correction(double fine, double sum, int odd_row, int odd_col)
+{
+    if (!odd_row && !odd_col) return dadd(fine, sum);
+    return dfma_pow2((odd_row && odd_col) ? 0.25 : 0.5, sum, fine);
+}
+
 // One weighted-Jacobi stage of the row pipeline.  `cen[p]` = input row i-1 (p = parity of the step; the two
 // slots ping-pong so that no register has to be copied at the loop back-edge), `part` = the partial sum
 // ((h^2 f + W) + E) + S of row i-1.  Given input row i (`in`) and f of row i it returns the finished output
@@ -130,8 +138,8 @@ struct SweepStage {
         const Row<C> &prev = cen[p];
 #pragma unroll
         for (int k = 0; k < C; ++k) {
-            double jac = dmul(0.25, dadd(part.v[k], in.v[k]));
-            double val = WEIGHTED ? dadd(dmul(c.om1, prev.v[k]), dmul(c.omega, jac)) : jac;
+            const double sum = dadd(part.v[k], in.v[k]);
+            double val = WEIGHTED ? dadd(dmul(c.om1, prev.v[k]), dmul(c.w4, sum)) : dmul(0.25, sum);
             out.v[k] = (out_row_interior && col_interior[k]) ? val : prev.v[k];
         }
         neighbours<C>(in, w, e);
@@ -163,7 +171,7 @@ struct ResidualStage {
         neighbours<C>(in, w, e);
 #pragma unroll
         for (int k = 0; k < C; ++k)
-            part.v[k] = dsub(dsub(dsub(dmul(4.0, in.v[k]), w.v[k]), e.v[k]), cen[p].v[k]);
+            part.v[k] = dsub(dsub(dfma_pow2(4.0, in.v[k], -w.v[k]), e.v[k]), cen[p].v[k]);
         cen[p ^ 1] = in;
         return r;
     }
@@ -538,7 +546,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                         double west = (q == 0) ? left : r.v[q == 0 ? 0 : 2 * q - 1];
                         double edge = dadd(dadd(c_ew[q], r.v[2 * q]), s_mid[q]);
                         double corner = dadd(dadd(s_cor[q], west), r.v[2 * q + 1]);
-                        double val = dadd(dadd(dmul(0.25, c_mid[q]), dmul(0.125, edge)), dmul(0.0625, corner));
+                        double val = dfma_pow2(0.0625, corner, dfma_pow2(0.125, edge, dmul(0.25, c_mid[q])));
                         o[q] = (ic + q >= 1 && ic + q < nc - 1) ? val : 0.0;
                         // this row is also the south row of coarse row jc+1
                         s_mid[q] = r.v[2 * q];
@@ -653,7 +661,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             Row<C> cur = feed.begin(u, jj);
             if (PROLONG) {
                 const bool rowp = (jj + g.yoff >= lo) && (jj + g.yoff <= g.n - 2);
-                double corr[C];
+                double corr[C];  // the coarse values each point interpolates, summed but not yet weighted
                 if ((u & 1) == 0) {
                     // coarse row jc+1 arrives (loaded one pair ago); fetch jc+2 for the next pair
                     en = eb;
@@ -663,20 +671,19 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         corr[2 * q] = ec.v[q];
-                        corr[2 * q + 1] = dmul(0.5, dadd(ec.v[q], ec.v[q + 1]));
+                        corr[2 * q + 1] = dadd(ec.v[q], ec.v[q + 1]);
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
-                        corr[2 * q] = dmul(0.5, dadd(ec.v[q], en.v[q]));
-                        corr[2 * q + 1] =
-                            dmul(0.25, dadd(dadd(dadd(ec.v[q], ec.v[q + 1]), en.v[q]), en.v[q + 1]));
+                        corr[2 * q] = dadd(ec.v[q], en.v[q]);
+                        corr[2 * q + 1] = dadd(dadd(dadd(ec.v[q], ec.v[q + 1]), en.v[q]), en.v[q + 1]);
                     }
                     ec = en;
                 }
 #pragma unroll
                 for (int k = 0; k < C; ++k)
-                    if (rowp && cprol[k]) cur.v[k] = dadd(cur.v[k], corr[k]);
+                    if (rowp && cprol[k]) cur.v[k] = add_correction(cur.v[k], corr[k], u & 1, k & 1);
             }
 #pragma unroll
             for (int k = 0; k < S; ++k) {
@@ -815,7 +822,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
             Row<C> cur = feed.begin(u, jj);
             {   // prolongation-and-add (MultiGrid.hpp:86)
                 const bool rowp = (jj + g.yoff >= lo) && (jj + g.yoff <= g.n - 2);
-                double corr[C];
+                double corr[C];  // the coarse values each point interpolates, summed but not yet weighted
                 if ((u & 1) == 0) {
                     en = eb;
                     en.v[NP] = __shfl_down_sync(0xffffffffu, eb.v[0], 1);
@@ -824,19 +831,19 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         corr[2 * q] = ec.v[q];
-                        corr[2 * q + 1] = dmul(0.5, dadd(ec.v[q], ec.v[q + 1]));
+                        corr[2 * q + 1] = dadd(ec.v[q], ec.v[q + 1]);
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
-                        corr[2 * q] = dmul(0.5, dadd(ec.v[q], en.v[q]));
-                        corr[2 * q + 1] = dmul(0.25, dadd(dadd(dadd(ec.v[q], ec.v[q + 1]), en.v[q]), en.v[q + 1]));
+                        corr[2 * q] = dadd(ec.v[q], en.v[q]);
+                        corr[2 * q + 1] = dadd(dadd(dadd(ec.v[q], ec.v[q + 1]), en.v[q]), en.v[q + 1]);
                     }
                     ec = en;
                 }
 #pragma unroll
                 for (int k = 0; k < C; ++k)
-                    if (rowp && cprol[k]) cur.v[k] = dadd(cur.v[k], corr[k]);
+                    if (rowp && cprol[k]) cur.v[k] = add_correction(cur.v[k], corr[k], u & 1, k & 1);
             }
             // post-smoothing of cycle k (:89): stage k finishes x row jj-k-1
 #pragma unroll
@@ -878,7 +885,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                         double west = (q == 0) ? left : r.v[q == 0 ? 0 : 2 * q - 1];
                         double edge = dadd(dadd(c_ew[q], r.v[2 * q]), s_mid[q]);
                         double corner = dadd(dadd(s_cor[q], west), r.v[2 * q + 1]);
-                        double val = dadd(dadd(dmul(0.25, c_mid[q]), dmul(0.125, edge)), dmul(0.0625, corner));
+                        double val = dfma_pow2(0.0625, corner, dfma_pow2(0.125, edge, dmul(0.25, c_mid[q])));
                         o[q] = (ic + q >= 1 && ic + q < nc - 1) ? val : 0.0;
                         s_mid[q] = r.v[2 * q];
                         s_cor[q] = dadd(west, r.v[2 * q + 1]);

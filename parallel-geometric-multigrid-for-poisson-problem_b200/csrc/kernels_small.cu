@@ -76,8 +76,7 @@ __device__ __forceinline__ void vs_sweeps(double *&cur, double *&oth, const doub
             for (int y = 1 + ty; y <= n - 2; y += rows) {
                 const int i = y * n + 1 + tx;
                 double acc = dadd(dadd(dadd(dadd(dmul(c.h2, f[i]), cur[i - 1]), cur[i + 1]), cur[i - n]), cur[i + n]);
-                double jac = dmul(0.25, acc);
-                oth[i] = WEIGHTED ? dadd(dmul(c.om1, cur[i]), dmul(c.omega, jac)) : jac;
+                oth[i] = WEIGHTED ? dadd(dmul(c.om1, cur[i]), dmul(c.w4, acc)) : dmul(0.25, acc);
             }
         vs_sync(k, warps);
         double *t = cur;
@@ -142,6 +141,7 @@ __global__ void __launch_bounds__(1024)
     JacobiCoef c;
     c.omega = omega;
     c.om1 = 1.0 - omega;
+    c.w4 = 0.25 * omega;
     c.weighted = WEIGHTED ? 1 : 0;
     c.h2 = 0.0;
     const int warp = t >> 5;

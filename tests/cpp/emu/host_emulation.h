@@ -37,6 +37,7 @@ typedef void *cudaStream_t;
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 
 // Model C (below) runs every CUDA thread of a whole thread-block cluster as a fiber inside ONE OS thread; a fiber that
 // has to wait at a barrier yields to the scheduler through this hook

@@ -26,6 +26,7 @@ JacobiCoef jacobi_coef(double h, double omega)
     c.h2 = h * h;
     c.omega = omega;
     c.om1 = 1.0 - omega;
+    c.w4 = 0.25 * omega;
     c.weighted = (omega != 1.0);
     return c;
 }
