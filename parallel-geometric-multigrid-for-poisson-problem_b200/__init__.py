@@ -448,7 +448,9 @@ def set_cluster_top(n):
 
 def set_cross_cycle(on, minb=None):
     """Cross-cycle solve on level 0 (Pass B of cycle k fused with Pass A of cycle k+1) for solvers created afterwards:
-    True / False, or -1 = PMG_CROSS / the default (on).  minb: CTAs per SM of the cross pass (2, 3, 4)."""
+    True / False, or -1 = PMG_CROSS / the default (on).  minb: shape of the cross pass -- 2 = strips of 128 columns, 4 per
+    lane, 8 warps per SM (default; 7 = the same with deeper prefetch); 3 .. 6 = strips of 64 columns with that many CTAs
+    per SM; 0 = back to the default."""
     L = lib()
     L.pmg_set_cross_cycle.restype = None
     L.pmg_set_cross_cycle.argtypes = [ctypes.c_int]

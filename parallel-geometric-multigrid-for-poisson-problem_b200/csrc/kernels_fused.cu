@@ -82,9 +82,19 @@ __device__ __forceinline__ Row<C> load_row(const double *__restrict__ p)
 template <int C>
 __device__ __forceinline__ void store_row(double *__restrict__ p, const Row<C> &r)
 {
+#ifndef PMG_HOST_EMULATION
+    if constexpr (C == 4) {
+        // one 256-bit store per lane (sm_100: STG.E.ENL2.256): a warp writes 1 KB of a row with one instruction instead
+        // of two half-sector ones; p is 32-byte aligned (columns per lane = 4, PADX and the pitch multiples of 4)
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3])
+                     : "memory");
+    } else
+#endif
+    {
 #pragma unroll
-    for (int k = 0; k < C / 2; ++k)
-        reinterpret_cast<double2 *>(p)[k] = make_double2(r.v[2 * k], r.v[2 * k + 1]);
+        for (int k = 0; k < C / 2; ++k)
+            reinterpret_cast<double2 *>(p)[k] = make_double2(r.v[2 * k], r.v[2 * k + 1]);
+    }
 }
 
 template <int C>
@@ -804,14 +814,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 
     const int cc = col >> 1;
     const int nc_last_row = ((g.ny - 1) >> 1) + PADY;
-    CoarseRow<C> ec, en, eb;
+    // Coarse rows: ec = row jc, en = row jc+1, eq[i] = row jc+1+i on its way from HBM (raw, before the shuffle).  With the
+    // wide strips only 2 warps per scheduler are resident and one row pair (~0.9 us of work) does not cover a loaded-DRAM
+    // round trip: with a single row in flight 23 % of all warp samples sat on the shuffle that consumes it (ncu source
+    // page), so the wide shape keeps three rows in flight.
+    constexpr int CPF = (C == 4) ? 3 : 1;
+    CoarseRow<C> ec, en, eq[CPF];
 #pragma unroll
-    for (int q = 0; q <= NP; ++q) ec.v[q] = en.v[q] = eb.v[q] = 0.0;
+    for (int q = 0; q <= NP; ++q) ec.v[q] = en.v[q] = 0.0;
     {
         const int jc0 = j_start >> 1;
         ec = load_coarse<C>(e + (ptrdiff_t)jc0 * pitch_c + cc);
         ec.v[NP] = __shfl_down_sync(0xffffffffu, ec.v[0], 1);
-        eb = load_coarse<C>(e + (ptrdiff_t)(jc0 + 1) * pitch_c + cc);
+#pragma unroll
+        for (int i = 0; i < CPF; ++i) {
+            eq[i].v[NP] = 0.0;
+            eq[i] = load_coarse<C>(e + (ptrdiff_t)min(jc0 + 1 + i, nc_last_row) * pitch_c + cc);
+        }
     }
     const int ycoarse = g.yoff >> 1;
 
@@ -824,10 +843,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
                 const bool rowp = (jj + g.yoff >= lo) && (jj + g.yoff <= g.n - 2);
                 double corr[C];  // the coarse values each point interpolates, summed but not yet weighted
                 if ((u & 1) == 0) {
-                    en = eb;
-                    en.v[NP] = __shfl_down_sync(0xffffffffu, eb.v[0], 1);
-                    int nr = min((jj >> 1) + 2, nc_last_row);
-                    eb = load_coarse<C>(e + (ptrdiff_t)nr * pitch_c + cc);
+                    en = eq[0];
+                    en.v[NP] = __shfl_down_sync(0xffffffffu, eq[0].v[0], 1);
+#pragma unroll
+                    for (int i = 0; i + 1 < CPF; ++i) eq[i] = eq[i + 1];
+                    int nr = min((jj >> 1) + 1 + CPF, nc_last_row);
+                    eq[CPF - 1] = load_coarse<C>(e + (ptrdiff_t)nr * pitch_c + cc);
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         corr[2 * q] = ec.v[q];
@@ -1140,7 +1161,8 @@ void cross_launch_w(const FusedLevel &lv_in, double *xb_out, const double *e, in
 {
     // lv_in.xb = input (xb_k), lv_in.x = where x_k goes, lv_in.hp = the neighbours' copies of the input array (row slabs)
     VariantDesc v{C, PF, MINB, 1};
-    StripGeom g = make_geom(lv_in, 6, v, 0, 0, 6);  // strips of 64 columns own 52: 19 % overlap instead of 25 % with 8
+    // strips of 64 columns own 52 (19 % overlap instead of 25 % with a halo of 8); 4 columns per lane: 128 own 112
+    StripGeom g = make_geom(lv_in, 6, v, 0, 0, C == 2 ? 6 : 8);
     double inv = 1.0 / (lv_in.h * lv_in.h);
     int nc = (lv_in.n - 1) / 2 + 1;
     auto k = k_cross<C, PF, MINB, 2, 2, WEIGHTED>;
@@ -1163,7 +1185,14 @@ int fused_take_bad_nu()
 
 // Cross-cycle pass on a level or a row slab of it: reads lv.xb (= xb_k), coarse_x (= e_k), lv.f; writes lv.x (= x_k), xb_out
 // (= xb_{k+1}, an array other than lv.xb), coarse_f and the norm partials of x_k.  nu1 = nu2 = 2 only.
-int g_cross_minb = 4;
+// Shape of the cross-cycle pass.  2 (default): 4 columns per lane -- strips of 128 columns own 112 --, 2 CTAs of 4 warps
+// per SM with up to 255 registers: a quarter fewer instructions per point than the narrow shape (half the shuffles and
+// row bookkeeping per point, 12.5 % instead of 19 % halo columns) and 11 % faster at N = 16385 although only 8 warps per SM
+// are resident.  3 .. 6: 2 columns per lane with that many CTAs per SM (4 was the default before; 5 and 6 spill).
+// 7: the wide shape with one more row of prefetch.  (12 wide warps per SM -- 168 registers -- spill and are 1.5x slower;
+// the two-pass kernels, which are bandwidth- and not instruction-bound, are SLOWER with wide strips: 3.2-3.9 TB/s.)
+constexpr int PMG_CROSS_SHAPE_DEFAULT = 2;
+int g_cross_minb = PMG_CROSS_SHAPE_DEFAULT;
 bool fused_cross_supported(int nu1, int nu2) { return nu1 == 2 && nu2 == 2; }
 // Fraction of the resident warp slots the cross-cycle pass fills on an n-column level of `rows` rows.  The grid is one
 // resident wave of (strips x chunks) warps with chunks = floor(slots / strips): at n = 32769 the 631 strips of 52 columns
@@ -1176,11 +1205,12 @@ double fused_cross_utilisation(int n, int rows)
     lv.n = n;
     lv.ny = rows;
     lv.pitch = level_pitch(n);
-    VariantDesc v{2, 2, g_cross_minb, 1};
-    StripGeom g = make_geom(lv, 6, v, 0, 0, 6);
+    const bool wide = g_cross_minb == 2 || g_cross_minb == 7;
+    VariantDesc v{wide ? 4 : 2, 2, wide ? 2 : g_cross_minb, 1};
+    StripGeom g = make_geom(lv, 6, v, 0, 0, wide ? 8 : 6);
     return (double)(g.n_strips * g.n_chunks) / (double)(num_sms() * v.minb * WARPS_PER_CTA);
 }
-void fused_set_cross_minb(int m) { g_cross_minb = (m >= 2 && m <= 6) ? m : 4; }
+void fused_set_cross_minb(int m) { g_cross_minb = (m >= 2 && m <= 7) ? m : PMG_CROSS_SHAPE_DEFAULT; }
 void launch_fused_cross(const FusedLevel &lv, double *xb_out, const double *coarse_x, double *coarse_f, int pitch_c, double omega,
                         int prolong_mode, double *d_partials, int *n_partials, cudaStream_t st, const int *done)
 {
@@ -1195,8 +1225,20 @@ void launch_fused_cross(const FusedLevel &lv, double *xb_out, const double *coar
     } while (0)
     if (g_cross_minb == 4)
         PMG_CROSS(4);
-    else if (g_cross_minb == 2)
-        PMG_CROSS(2);
+    else if (g_cross_minb == 2 || g_cross_minb == 7) {  // 4 columns per lane, 8 warps per SM; 7 = one more row of prefetch
+#define PMG_CROSS4(PF)                                                                                                         \
+    do {                                                                                                                       \
+        if (c.weighted)                                                                                                        \
+            cross_launch_w<4, PF, 2, true>(lv, xb_out, coarse_x, pitch_c, coarse_f, lo, d_partials, n_partials, c, done, st);   \
+        else                                                                                                                   \
+            cross_launch_w<4, PF, 2, false>(lv, xb_out, coarse_x, pitch_c, coarse_f, lo, d_partials, n_partials, c, done, st);  \
+    } while (0)
+        if (g_cross_minb == 2)
+            PMG_CROSS4(2);
+        else
+            PMG_CROSS4(3);
+#undef PMG_CROSS4
+    }
     else if (g_cross_minb == 5)
         PMG_CROSS(5);
     else if (g_cross_minb == 6)

@@ -473,10 +473,10 @@ static void slab_visit(int n, int ranks, bool first_visit, bool split, int prolo
 }
 
 // ---- cross-cycle pass on row slabs: the input's halo rows come from the neighbours' arrays through the halo prologue ----
-static void slab_cross(int n, int ranks, int prolong, int sms)
+static void slab_cross(int n, int ranks, int prolong, int sms, int minb = 3)
 {
     emu_num_sms = sms;
-    fused_set_cross_minb(3);
+    fused_set_cross_minb(minb);
     const double omega = 2.0 / 3.0;
     const int nc = (n - 1) / 2 + 1, epoch = 11;
     const double h = 1.0 / (n - 1);
@@ -576,6 +576,7 @@ int main(int argc, char **argv)
     const double w = 2.0 / 3.0;
     // whole levels: the headline V(2,2) flavours on every variant, then the other sweep counts
     for (int v = 0; v < fused_num_variants(); ++v) whole_level(65, w, 2, 2, ORC_PROLONG_REFERENCE, false, v, 148);
+    for (int v = 5; v < fused_num_variants(); ++v) whole_level(257, w, 2, 2, ORC_PROLONG_FULL, v == 6, v, 3);  // 128-column strips
     whole_level(65, w, 2, 2, ORC_PROLONG_REFERENCE, true, -1, 148);
     whole_level(33, 1.0, 2, 2, ORC_PROLONG_FULL, false, -1, 148);
     whole_level(129, w, 2, 2, ORC_PROLONG_REFERENCE, false, -1, 2);  // few SMs: 14-row chunks, chunk overlap exercised
@@ -588,9 +589,15 @@ int main(int argc, char **argv)
     cross_level(129, w, ORC_PROLONG_FULL, 148, 4);
     cross_level(129, 1.0, ORC_PROLONG_REFERENCE, 2, 2);   // few SMs: tall chunks, chunk overlap exercised
     cross_level(257, w, ORC_PROLONG_REFERENCE, 1, 3);
+    // 4 columns per lane (strips of 128 columns own 112), prefetch depths 2 / 3 / 4
+    cross_level(257, w, ORC_PROLONG_REFERENCE, 148, 2);
+    cross_level(129, w, ORC_PROLONG_FULL, 2, 7);
+    cross_level(513, w, ORC_PROLONG_REFERENCE, 4, 8);
     slab_cross(129, 2, ORC_PROLONG_REFERENCE, 148);
     slab_cross(257, 3, ORC_PROLONG_FULL, 2);
     slab_cross(257, 4, ORC_PROLONG_REFERENCE, 148);
+    slab_cross(257, 3, ORC_PROLONG_REFERENCE, 148, 2);
+    slab_cross(513, 2, ORC_PROLONG_FULL, 3, 7);
     // row slabs
     slab_visit(129, 2, false, false, ORC_PROLONG_REFERENCE, 148, true);   // finest level, iterate exchanged
     slab_visit(129, 2, true, false, ORC_PROLONG_REFERENCE, 148, false);   // coarse level, first visit: f exchanged

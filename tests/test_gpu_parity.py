@@ -501,8 +501,8 @@ def test_cross_cycle_solve_matches_two_pass_solve(orc, n, prolong, omega):
     f = cc.random_rhs(n, seed=91)
     phi0 = np.random.default_rng(92).standard_normal((n, n))
     got = {}
-    for cross in (0, 1):
-        pmg.set_cross_cycle(cross)
+    for cross, shape in ((0, 0), (1, 0), (1, 4)):  # shape 0 = default (strips of 128 columns), 4 = strips of 64
+        pmg.set_cross_cycle(cross, shape)
         with pmg.Solver(n, omega=omega, prolong_mode=prolong) as s:
             s.set_rhs(f)
             s.set_guess(phi0)
@@ -514,15 +514,17 @@ def test_cross_cycle_solve_matches_two_pass_solve(orc, n, prolong, omega):
             k4, hist4 = s.solve(pmg.V, rel_tol=0.0, max_cycles=4)    # continues from x3
             x7 = s.get_solution()
             norm_after = s.cycle(pmg.V)                              # the classic cycle still works on the same handle
-            got[cross] = (k, hist, x_full, k3, hist3, x3, k4, hist4, x7, norm_after)
-    pmg.set_cross_cycle(-1)
-    a, b = got[0], got[1]
-    assert a[0] == b[0] and a[3] == b[3] == 3 and a[6] == b[6] == 4
-    for i in (2, 5, 8):
-        assert np.array_equal(a[i], b[i]), i
-    for i in (1, 4, 7):
-        assert np.max(np.abs(a[i] - b[i]) / a[i]) <= 1e-13, i
-    assert abs(a[9] - b[9]) <= 1e-13 * a[9]
+            got[(cross, shape)] = (k, hist, x_full, k3, hist3, x3, k4, hist4, x7, norm_after)
+    pmg.set_cross_cycle(-1, 0)
+    a = got[(0, 0)]
+    for key in ((1, 0), (1, 4)):
+        b = got[key]
+        assert a[0] == b[0] and a[3] == b[3] == 3 and a[6] == b[6] == 4, key
+        for i in (2, 5, 8):
+            assert np.array_equal(a[i], b[i]), (key, i)
+        for i in (1, 4, 7):
+            assert np.max(np.abs(a[i] - b[i]) / a[i]) <= 1e-13, (key, i)
+        assert abs(a[9] - b[9]) <= 1e-13 * a[9], key
     if n == 257:
         want = phi0.copy()
         for _ in range(3):

@@ -27,6 +27,7 @@ def main(rep, out):
             continue
         name = r[hdr.index("Kernel Name")]
         name = re.sub(r"^void |pmg::<unnamed>::|\(.*$", "", name)
+        name = re.sub(r"^.*::(?=k_)", "", name)  # whatever is left of an anonymous-namespace prefix
         rec = {"kernel": name}
         for k in KEYS:
             if k in hdr:
