@@ -436,15 +436,39 @@ struct FeedSelect<C, PF, S, USE_X, true> {
     using type = SmemFeed<C, PF, S, USE_X>;
 };
 
+// coarse rows of the prolongation (Pass B, the cross-cycle pass and Pass A's prolong-in form)
+template <int C>
+struct CoarseRow {
+    double v[C / 2 + 1];  // coarse columns cc .. cc + C/2
+};
+
+template <int C>
+__device__ __forceinline__ CoarseRow<C> load_coarse(const double *__restrict__ p)
+{
+    CoarseRow<C> r;
+    if (C == 4) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Pass A.  S sweeps; RESID adds residual + full weighting into the coarse RHS; ZEROX: x == 0 on entry.
 // ---------------------------------------------------------------------------------------------------
-template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID, bool WEIGHTED, bool PROLOGUE = false>
+// PIN ("prolong in", one GPU, with ZEROX): the iterate on entry is P e_in -- the bilinear prolongation of a coarse iterate
+// into a zeroed grid (nested iteration, MultiGrid.hpp:161-164) -- formed on the fly from the coarse rows instead of being
+// written by a fill + a prolongation kernel and read back (8 + 18 + 8 B per point less).
+template <int C, int PF, int MINB, bool SM, int S, bool ZEROX, bool RESID, bool WEIGHTED, bool PROLOGUE = false, bool PIN = false>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_down(const double *__restrict__ x, double *__restrict__ xo, const double *__restrict__ f,
            double *__restrict__ cf, StripGeom g, int pitch_c, int nc, JacobiCoef coef, double inv_h2,
-           const int *__restrict__ done, HaloPeers hp)
+           const int *__restrict__ done, HaloPeers hp, const double *__restrict__ e_in, int pitch_e, int lo)
 {
+    static_assert(!PIN || (ZEROX && SM), "prolong-in: the iterate is not read, shared-memory feed (row pairs)");
     using Feed = typename FeedSelect<C, PF, S, !ZEROX, SM>::type;
     pdl_wait();
     const bool pdl_early = gridDim.x <= 296u;  // at most two CTAs per SM: a latency-bound level (pmg_internal.h)
@@ -463,7 +487,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     // Rows this chunk must finish: x_S on [r0, r1) and, for the coarse rows it owns (fine row 2jc inside
     // the chunk AND inside the slab), r on [2jc-1, 2jc+1], i.e. x_S two rows earlier and one row later.
     const int lead = RESID ? 2 : 0;
-    const int j_start = min(r0, max(r0, 0) - lead) - S;
+    int j_start_ = min(r0, max(r0, 0) - lead) - S;
+    if (PIN) j_start_ -= (j_start_ & 1);  // even: the row parity of the prolongation is static in the unrolled body
+    const int j_start = j_start_;
     const int j_end = max(r1 - 1, min(r1, g.ny) - 1 + (RESID ? 1 : 0)) + S;  // inclusive
 
     SweepStage<C> st[S];
@@ -545,11 +571,52 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     feed.init(x, f, g.pitch, col, j_start, g.ny + PADY - 1, lane, threadIdx.x >> 5, feed_peers, g.ny);
     const int ycoarse = g.yoff >> 1;  // global coarse row of local coarse row 0
 
+    // prolong-in: coarse rows ec = row jc, en = row jc+1, eb = prefetch of row jc+2 (as in Pass B)
+    static_assert(!PIN || Feed::UNROLL % 2 == 0, "rows are processed in (even, odd) pairs");
+    const int cc = col >> 1;
+    const int nc_last_row = ((g.ny - 1) >> 1) + PADY;
+    CoarseRow<C> ec, en, eb;
+    bool cprol[C];
+    if (PIN) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) cprol[k] = (col + k >= lo) && (col + k <= g.n - 2);
+        const int jc0 = j_start >> 1;
+        ec = load_coarse<C>(e_in + (ptrdiff_t)jc0 * pitch_e + cc);
+        ec.v[NP] = __shfl_down_sync(0xffffffffu, ec.v[0], 1);
+        eb = load_coarse<C>(e_in + (ptrdiff_t)(jc0 + 1) * pitch_e + cc);
+        en = ec;
+    }
+
     for (int j = j_start; j <= j_end; j += Feed::UNROLL) {
 #pragma unroll
         for (int u = 0; u < Feed::UNROLL; ++u) {
             const int jj = j + u;  // input row of this step (steps past j_end are harmless: stores are masked)
             Row<C> cur = feed.begin(u, jj);
+            if (PIN) {  // cur (zero) += P e_in: row jj of the iterate the sweeps start from
+                const bool rowp = (jj + g.yoff >= lo) && (jj + g.yoff <= g.n - 2);
+                double corr[C];  // the coarse values each point interpolates, summed but not yet weighted
+                if ((u & 1) == 0) {
+                    en = eb;
+                    en.v[NP] = __shfl_down_sync(0xffffffffu, eb.v[0], 1);
+                    const int nr = min((jj >> 1) + 2, nc_last_row);
+                    eb = load_coarse<C>(e_in + (ptrdiff_t)nr * pitch_e + cc);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        corr[2 * q] = ec.v[q];
+                        corr[2 * q + 1] = dadd(ec.v[q], ec.v[q + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        corr[2 * q] = dadd(ec.v[q], en.v[q]);
+                        corr[2 * q + 1] = dadd(dadd(dadd(ec.v[q], ec.v[q + 1]), en.v[q]), en.v[q + 1]);
+                    }
+                    ec = en;
+                }
+#pragma unroll
+                for (int k = 0; k < C; ++k)
+                    if (rowp && cprol[k]) cur.v[k] = add_correction(cur.v[k], corr[k], u & 1, k & 1);
+            }
             // sweeps: stage k consumes x_k row jj-k and finishes x_{k+1} row jj-k-1
 #pragma unroll
             for (int k = 0; k < S; ++k) {
@@ -608,25 +675,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 // Pass B.  x = S^nu2(xb + P e) ; NORM adds sum over the interior of (f - A x)^2 (one partial per warp).
 // PROLONG = false makes it a plain smoothing (+norm) pass.
 // ---------------------------------------------------------------------------------------------------
-template <int C>
-struct CoarseRow {
-    double v[C / 2 + 1];  // coarse columns cc .. cc + C/2
-};
-
-template <int C>
-__device__ __forceinline__ CoarseRow<C> load_coarse(const double *__restrict__ p)
-{
-    CoarseRow<C> r;
-    if (C == 4) {
-        const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
-        r.v[0] = t.x;
-        r.v[1] = t.y;
-    } else {
-        r.v[0] = __ldg(p);
-    }
-    return r;
-}
-
 template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM, bool WEIGHTED>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
     k_up(const double *__restrict__ xb, double *__restrict__ xo, const double *__restrict__ f,
@@ -1104,27 +1152,27 @@ void down_launch_w(const FusedLevel &lv, double *cf, int pitch_c, bool x_is_zero
         auto k = k_down<C, PF, MINB, SM, S, true, true, WEIGHTED, CAN_PROLOGUE>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
         PMG_SMEM_ONCE(k, sm);
-        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp, (const double *)nullptr, 0, 0);
     } else if (resid && prologue) {
         auto k = k_down<C, PF, MINB, SM, S, false, true, WEIGHTED, CAN_PROLOGUE>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         PMG_SMEM_ONCE(k, sm);
-        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp, (const double *)nullptr, 0, 0);
     } else if (resid && x_is_zero) {
         auto k = k_down<C, PF, MINB, SM, S, true, true, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, false, SM>::type::SMEM_PER_WARP;
         PMG_SMEM_ONCE(k, sm);
-        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp, (const double *)nullptr, 0, 0);
     } else if (resid) {
         auto k = k_down<C, PF, MINB, SM, S, false, true, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         PMG_SMEM_ONCE(k, sm);
-        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp);
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done, lv.hp, (const double *)nullptr, 0, 0);
     } else {
         auto k = k_down<C, PF, MINB, SM, S, false, false, WEIGHTED>;
         int sm = WARPS_PER_CTA * FeedSelect<C, PF, S, true, SM>::type::SMEM_PER_WARP;
         PMG_SMEM_ONCE(k, sm);
-        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, (double *)nullptr, g, 0, nc, c, inv, done, lv.hp);
+        PMG_LAUNCH(k, grid, block, sm, st, lv.x, lv.xb, lv.f, (double *)nullptr, g, 0, nc, c, inv, done, lv.hp, (const double *)nullptr, 0, 0);
     }
 }
 
@@ -1143,6 +1191,22 @@ void down_launch(const FusedLevel &lv, double *cf, int pitch_c, double omega, bo
         down_launch_w<C, PF, MINB, SM, S, false>(lv, cf, pitch_c, x_is_zero, resid, g, nc, c, inv, grid, block, done, st);
     }
     count_launch();
+}
+
+// Pass A whose iterate on entry is P e_in (prolong-in form of k_down): headline sweep count, the x == 0 variant's shape
+template <bool WEIGHTED>
+void down_prolong_launch_w(const FusedLevel &lv, const double *e_in, int pitch_e, int lo, double *cf, int pitch_c,
+                           const JacobiCoef &c, const int *done, cudaStream_t st)
+{
+    constexpr int C = 2, PF = 3, MINB = 5, S = 2;
+    StripGeom g = make_geom(lv, S + 2, VariantDesc{C, PF, MINB, 1}, lv.ext_lo, lv.ext_hi);
+    const double inv = 1.0 / (lv.h * lv.h);
+    const int nc = (lv.n - 1) / 2 + 1;
+    auto k = k_down<C, PF, MINB, true, S, true, true, WEIGHTED, false, true>;
+    int sm = WARPS_PER_CTA * SmemFeed<C, PF, S, false>::SMEM_PER_WARP;
+    PMG_SMEM_ONCE(k, sm);
+    PMG_LAUNCH(k, dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st, lv.x, lv.xb, lv.f, cf, g, pitch_c, nc, c, inv, done,
+               HaloPeers{}, e_in, pitch_e, lo);
 }
 
 template <int C, int PF, int MINB, bool SM, int S, bool PROLONG, bool NORM, bool WEIGHTED>
@@ -1352,6 +1416,21 @@ void launch_fused_down(const FusedLevel &lv, double *coarse_f, int pitch_c, int 
         case 4: down_launch<2, 2, 4, true, 4>(lv, coarse_f, pitch_c, omega, x_is_zero, resid, done, st); break;
         default: break;
     }
+}
+
+bool fused_down_prolong_supported(int nu1) { return nu1 == 2; }
+// xb = S^2(P e_in), coarse_f = R(f - A xb): Pass A of the first cycle on a level that nested iteration has just reached
+// (MultiGrid.hpp:161-167) without materialising P e_in.  One GPU, nu1 = 2.
+void launch_fused_down_prolong(const FusedLevel &lv, const double *e_in, int pitch_e, double *coarse_f, int pitch_c, double omega,
+                               int prolong_mode, cudaStream_t st, const int *done)
+{
+    const int lo = prolong_mode == PMG_PROLONG_FULL ? 1 : 2;
+    JacobiCoef c = jacobi_coef(lv.h, omega);
+    if (c.weighted)
+        down_prolong_launch_w<true>(lv, e_in, pitch_e, lo, coarse_f, pitch_c, c, done, st);
+    else
+        down_prolong_launch_w<false>(lv, e_in, pitch_e, lo, coarse_f, pitch_c, c, done, st);
+    count_launch();
 }
 
 void launch_fused_up(const FusedLevel &lv, const double *coarse_x, int pitch_c, int nu2, double omega,

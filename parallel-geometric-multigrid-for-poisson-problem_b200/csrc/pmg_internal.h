@@ -310,6 +310,10 @@ struct FusedLevel {
 // Pass A (down): xb = S^nu1(x);  coarse_f(interior) = R(f - A xb).  x_is_zero: the iterate is known to
 // be identically zero on entry (coarse levels of a V-cycle) so x is not read.
 bool fused_supported(int nu);
+// Pass A with the iterate on entry given as P e_in (prolongation of a coarse iterate into zero), never materialised
+bool fused_down_prolong_supported(int nu1);
+void launch_fused_down_prolong(const FusedLevel &lv, const double *e_in, int pitch_e, double *coarse_f, int pitch_c, double omega,
+                               int prolong_mode, cudaStream_t st, const int *done = nullptr);
 // a launcher called with an unsupported sweep count launches nothing and records the count; returns and clears it
 // (0 = none): the cycle drivers turn it into PMG_ERR_UNSUPPORTED instead of a silently skipped pass
 int fused_take_bad_nu();

@@ -101,6 +101,8 @@ struct pmg_solver {
     // F-cycle: level-0 analytic RHS lives in its own array so the caller's f survives
     double *base_f_fmg0 = nullptr, *f_fmg0 = nullptr;
     bool fmg_ready = false;
+    bool rhs_is_analytic = false;  // level 0's f was written by pmg_set_rhs_sine and by nothing since (one GPU)
+    bool fmg0_rhs_cached = false;  // f_fmg0 holds the analytic right-hand side of level 0 (a constant of the hierarchy)
     // CUDA graphs of one fused cycle, keyed by [kind V/W][0: no norm, 1: norm -> d_scalar,
     // 2: norm -> device-side solve control (asynchronous solve)]
     cudaGraphExec_t graph[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
@@ -337,8 +339,10 @@ static pmg_status cycle_operator(pmg_solver *s, int l, bool w_form, bool x_is_ze
 }
 
 // The same cycle on the fused engine: two streaming passes per level visit.
+// prolong_in (nested iteration, streaming levels only): the iterate of level l on entry is P (prolong_in->x) into a zeroed
+// grid; it is formed inside Pass A and never written (fmg_up_from)
 static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero, bool want_norm, int *n_partials,
-                              const int *done = nullptr)
+                              const int *done = nullptr, const Level *prolong_in = nullptr)
 {
     const pmg_config &c = s->cfg;
     Level &L = s->lv[l];
@@ -357,7 +361,11 @@ static pmg_status cycle_fused(pmg_solver *s, int l, bool w_form, bool x_is_zero,
         return PMG_OK;
     }
     Level &K = s->lv[l + 1];
-    launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, done);
+    if (prolong_in != nullptr)
+        launch_fused_down_prolong(fused_view(L), prolong_in->x, prolong_in->pitch, K.f, K.pitch, c.omega, c.prolong_mode,
+                                  s->stream, done);
+    else
+        launch_fused_down(fused_view(L), K.f, K.pitch, c.nu1, c.omega, x_is_zero, s->stream, done);
     int reps = w_form ? c.gamma : 1;
     for (int k = 0; k < reps; ++k) {
         pmg_status rc = cycle_fused(s, l + 1, w_form, k == 0, false, nullptr, done);
@@ -772,8 +780,11 @@ static void analytic_rhs(pmg_solver *s, const Level &L, double *f)
 // MultigridSolver::f_cycle (MultiGrid.hpp:138-183): nested iteration from level l_init -- whose x / f arrays hold the
 // starting iterate and right-hand side -- up to the finest level, with the ANALYTIC right-hand side on every finer
 // level (:162); the result is the finest level's iterate.
-static pmg_status fmg_up_from(pmg_solver *s, int l_init)
+// norm_np (nullable): if the last V-cycle can deliver the residual norm of the result (its Pass B on level 0 sums
+// (f - A x)^2 against the analytic right-hand side), *norm_np receives the number of partial sums in s->d_partials; -1 if not
+static pmg_status fmg_up_from(pmg_solver *s, int l_init, int *norm_np = nullptr)
 {
+    if (norm_np) *norm_np = -1;
     const pmg_config &c = s->cfg;
     pmg_status rc = PMG_OK;
     double *user_f = s->lv[0].f;
@@ -790,11 +801,25 @@ static pmg_status fmg_up_from(pmg_solver *s, int l_init)
             if (rc != PMG_OK) break;
         }
         double *f_l = (l == 0) ? s->f_fmg0 : L.f;
-        analytic_rhs(s, L, f_l);                                                             // :162
-        launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);                               // :161
-        launch_prolong_add(K.x, L.x, K.n, L.n, K.pitch, L.pitch, c.prolong_mode, s->stream);  // :164
+        if (l != 0 || !s->fmg0_rhs_cached) analytic_rhs(s, L, f_l);                          // :162
+        if (l == 0) s->fmg0_rhs_cached = true;  // level 0's copy is a dedicated array: written once per hierarchy
+        // On the levels the V-cycle streams (n >= 513: never the cluster / single-CTA kernels), "zero the fine grid, add
+        // P phi_coarse" (:161, :164) is folded into Pass A of the V-cycle (:167): the prolonged iterate is never written.
+        const bool fold = s->fused && L.n >= 513 && L.n > c.n_coarse && fused_down_prolong_supported(c.nu1) &&
+                          !c.smoother_fp32 && c.smoother == PMG_SMOOTHER_JACOBI;
+        if (!fold) {
+            launch_fill2d(L.x, L.pitch, L.n, L.n, 0.0, s->stream);                               // :161
+            launch_prolong_add(K.x, L.x, K.n, L.n, K.pitch, L.pitch, c.prolong_mode, s->stream);  // :164
+        }
         if (l == 0) L.f = s->f_fmg0;
-        rc = s->fused ? cycle_fused(s, l, false, false, false, nullptr) : cycle_operator(s, l, false, false);  // :167
+        // the runner's residual after the pass (MultiGridTestRunner.hpp:210-211) is taken against the caller's f: the
+        // last Pass B can deliver it only if that f IS the analytic right-hand side (pmg_set_rhs_sine, untouched since)
+        const bool fold_norm = norm_np != nullptr && l == 0 && s->fused && s->rhs_is_analytic &&
+                               c.norm_mode != PMG_NORM_SEQUENTIAL && L.n >= 513 && L.n > c.n_coarse;
+        int np = 0;
+        rc = s->fused ? cycle_fused(s, l, false, false, fold_norm, fold_norm ? &np : nullptr, nullptr, fold ? &K : nullptr)
+                      : cycle_operator(s, l, false, false);  // :167
+        if (fold_norm && rc == PMG_OK) *norm_np = np;
         if (l == 0) L.f = user_f;
         if (rc != PMG_OK) break;
     }
@@ -815,8 +840,9 @@ static void restrict_chain(pmg_solver *s, const double *src0, int l_out)
 
 // The runner's F-cycle wrapper (MultiGridTestRunner.hpp:192-205) = compute_coarsest_grid + f_cycle from the
 // coarsest level with the analytic coarse right-hand side (:142).
-static pmg_status cycle_f(pmg_solver *s)
+static pmg_status cycle_f(pmg_solver *s, int *norm_np = nullptr)
 {
+    if (norm_np) *norm_np = -1;
     pmg_status rc = ensure_fmg(s);
     if (rc != PMG_OK) return rc;
     const int nl = (int)s->lv.size();
@@ -828,7 +854,7 @@ static pmg_status cycle_f(pmg_solver *s)
     launch_copy2d(s->lv[lc].x, s->lv[lc].pitch, s->lv[lc].xb, s->lv[lc].pitch, s->lv[lc].n, s->lv[lc].n, s->stream);
     // (2) nested iteration upwards
     analytic_rhs(s, s->lv[lc], s->lv[lc].f);  // MultiGridTestRunner.hpp:142
-    return fmg_up_from(s, lc);
+    return fmg_up_from(s, lc, norm_np);
 }
 
 // PMG_CYCLE_FMG: one full-multigrid pass for an arbitrary right-hand side and Dirichlet ring (pmg.h; not a
@@ -846,6 +872,7 @@ static pmg_status cycle_fmg_general(pmg_solver *s)
     if (L0.n > 2) launch_fill2d(L0.x + L0.pitch + 1, L0.pitch, L0.n - 2, L0.n - 2, 0.0, s->stream);
     if (lc == 0 || L0.n <= c.n_coarse) return smooth_operator(s, 0, c.coarse_sweeps, false);
     // r0 = f - A x into the spare array (interior; its ring is never read), then the chain of restrictions
+    s->fmg0_rhs_cached = false;  // the spare level-0 array is scratch here
     launch_residual(s->f_fmg0, L0.x, L0.f, L0.n, L0.n, L0.pitch, L0.pitch, L0.pitch, L0.h, s->stream);
     for (int l = 0; l < lc; ++l) {
         const Level &L = s->lv[l];
@@ -1059,8 +1086,14 @@ static pmg_status run_cycle_inner(pmg_solver *s, pmg_cycle_kind kind, bool want_
         return rc;
     }
     if (kind == PMG_CYCLE_F) {
-        rc = s->dist ? cycle_f_dist(s) : cycle_f(s);
-        if (rc == PMG_OK && want_norm) rc = residual_norm2_async(s);
+        int np = -1;
+        rc = s->dist ? cycle_f_dist(s) : cycle_f(s, want_norm ? &np : nullptr);
+        if (rc == PMG_OK && want_norm) {
+            if (np >= 0)
+                launch_final_sum(s->d_partials, np, s->d_scalar, s->stream);  // the last Pass B summed (f - A x)^2
+            else
+                rc = residual_norm2_async(s);
+        }
         return rc;
     }
     if (kind != PMG_CYCLE_V && kind != PMG_CYCLE_W) return fail(PMG_ERR_INVALID, "unknown cycle kind");
@@ -1552,6 +1585,7 @@ static pmg_status copy_in(pmg_solver *s, double *dst_logical, const double *src,
 
 pmg_status pmg_set_rhs(pmg_solver *s, const double *f, pmg_mem where)
 {
+    if (s) s->rhs_is_analytic = false;
     return copy_in(s, s ? s->lv[0].f : nullptr, f, where);
 }
 
@@ -1623,6 +1657,7 @@ pmg_status pmg_commit_rhs(pmg_solver *s)
     PMG_CUDA(cudaStreamWaitEvent(s->stream, s->ev_staged, 0));
     // a device copy (1.4 ms at N = 16385) rather than a pointer swap: the captured cycle graphs and, on several GPUs,
     // the neighbours' peer mappings keep addressing the same f array
+    s->rhs_is_analytic = false;
     PMG_CUDA(cudaMemcpyAsync(L.base_f, s->base_f_stage, L.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
     PMG_CUDA(cudaEventRecord(s->ev_consumed, s->stream));
     s->staged = false;
@@ -1677,6 +1712,7 @@ pmg_status pmg_set_rhs_sine(pmg_solver *s)
                              L.d_sin + ga, s->stream);
     } else {
         analytic_rhs(s, s->lv[0], s->lv[0].f);
+        s->rhs_is_analytic = true;
     }
     PMG_CUDA(cudaStreamSynchronize(s->stream));
     PMG_CUDA(cudaGetLastError());

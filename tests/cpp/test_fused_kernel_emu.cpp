@@ -189,6 +189,49 @@ static void cross_level(int n, double omega, int prolong, int sms, int minb)
                 (ok_x && ok_c) ? "bit-identical" : "MISMATCH");
 }
 
+// ---- Pass A in its prolong-in form: xb = S^2(P e), coarse f = R(f - A xb), P e never written (nested iteration) --------
+static void prolong_down_level(int n, double omega, int prolong, int sms)
+{
+    emu_num_sms = sms;
+    const int nc = (n - 1) / 2 + 1;
+    const double h = 1.0 / (n - 1);
+    Dense f(n), e(nc);
+    f.randomize(true);
+    e.randomize(false);
+    Dense x0(n);  // zeroed fine grid (MultiGrid.hpp:161)
+    orc_prolong_add(x0.v.data(), e.v.data(), n, nc, prolong);
+    Dense xb = x0;
+    orc_jacobi(xb.v.data(), f.v.data(), n, n, h, omega, 1, 0.0, nullptr);
+    Dense r(n), cf(nc);
+    orc_residual(r.v.data(), xb.v.data(), f.v.data(), n, n, h);
+    orc_restrict_fw(r.v.data(), cf.v.data(), n, nc);
+    Padded px(n, n), pxb(n, n), pf(n, n), pe(nc, nc), pcf(nc, nc);
+    px.fill_rows(0, n, std::nan(""));  // the iterate array must not be read
+    pf.load(f, 0, 0, n);
+    pe.load(e, 0, 0, nc);
+    Padded pf0 = pf, pe0 = pe, pcf0 = pcf, pxb0 = pxb;
+    FusedLevel lv{};
+    lv.x = px.p();
+    lv.xb = pxb.p();
+    lv.f = pf.p();
+    lv.n = n;
+    lv.pitch = px.pitch;
+    lv.h = h;
+    launch_fused_down_prolong(lv, pe.p(), pe.pitch, pcf.p(), pcf.pitch, omega, prolong, nullptr, nullptr);
+    bool ok_x = true, ok_c = true;
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) ok_x = ok_x && same_bits(pxb.at(y, x), xb.at(y, x));
+    for (int y = 0; y < nc; ++y)
+        for (int x = 0; x < nc; ++x) ok_c = ok_c && same_bits(pcf.at(y, x), cf.at(y, x));
+    check(ok_x, "prolong-in Pass A: xb = S^2(P e)", n, sms, prolong);
+    check(ok_c, "prolong-in Pass A: coarse f = R(f - A xb)", n, sms, prolong);
+    check(pf.untouched_outside(pf0, 0, 0) && pe.untouched_outside(pe0, 0, 0), "prolong-in Pass A: inputs untouched", n, sms, prolong);
+    check(pxb.untouched_outside(pxb0, 0, n), "prolong-in Pass A wrote xb outside the level", n, sms, prolong);
+    check(pcf.untouched_outside(pcf0, 1, nc - 1), "prolong-in Pass A: coarse ring and padding untouched", n, sms, prolong);
+    std::printf("prolong-in Pass A n=%d omega=%.3f prolong=%d sms=%d: %s\n", n, omega, prolong, sms,
+                (ok_x && ok_c) ? "bit-identical" : "MISMATCH");
+}
+
 // ---- whole level (one GPU) ---------------------------------------------------------------------------------------
 static void whole_level(int n, double omega, int nu1, int nu2, int prolong, bool x_is_zero, int variant, int sms)
 {
@@ -585,6 +628,9 @@ int main(int argc, char **argv)
     whole_level(33, w, 4, 4, ORC_PROLONG_REFERENCE, false, -1, 148);
     for (int nu = 1; nu <= 4; ++nu) smoothing_pass(65, w, nu, nu == 3 ? 1 : 148);
     // cross-cycle pass (Pass B of cycle k + Pass A of cycle k+1): strips of 52 owned columns, several chunk geometries
+    prolong_down_level(65, w, ORC_PROLONG_REFERENCE, 148);
+    prolong_down_level(129, w, ORC_PROLONG_FULL, 2);
+    prolong_down_level(257, 1.0, ORC_PROLONG_REFERENCE, 5);
     cross_level(65, w, ORC_PROLONG_REFERENCE, 148, 3);
     cross_level(129, w, ORC_PROLONG_FULL, 148, 4);
     cross_level(129, 1.0, ORC_PROLONG_REFERENCE, 2, 2);   // few SMs: tall chunks, chunk overlap exercised

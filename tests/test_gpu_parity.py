@@ -393,6 +393,39 @@ def test_cluster_kernel_matches_streaming_path_and_oracle(orc, n, kind, gamma, o
         assert np.array_equal(got[129][1], want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,prolong,omega", [(1025, pmg.PROLONG_REFERENCE, 2.0 / 3.0), (2049, pmg.PROLONG_FULL, 1.0)])
+def test_f_cycle_folded_passes_match_oracle(orc, n, prolong, omega):
+    """Nested iteration on the streaming levels (n >= 513) folds "zero the fine grid, add P phi_coarse" into Pass A of the
+    level's V-cycle (k_down's prolong-in form) and -- when the right-hand side is the analytic one (pmg_set_rhs_sine) --
+    the residual norm into the last Pass B.  Both forms against the oracle's F-cycle (MultiGridTestRunner.hpp:192-205):
+    iterates bit-identical; the folded norm equals the separately computed one to the last bits (another summation tree);
+    a right-hand side set with pmg_set_rhs (even the same values) takes the unfolded norm."""
+    phi0 = np.random.default_rng(5).standard_normal((n, n))
+    phi0[0, :] = phi0[-1, :] = phi0[:, 0] = phi0[:, -1] = 0.0
+    f = orc.rhs(n)
+    want = phi0.copy()
+    for _ in range(2):
+        orc.cycle(want, f, kind=cc.F, omega=omega, eps=0.0, alpha=1, prolong=prolong)
+    want_norm = orc.norm(orc.residual(want, f, 1.0 / (n - 1)))
+    got = {}
+    for analytic in (True, False):
+        with pmg.Solver(n, omega=omega, prolong_mode=prolong) as s:
+            if analytic:
+                s.set_rhs_sine()
+            else:
+                s.set_rhs(f)
+            s.set_guess(phi0)
+            norms = [s.cycle(pmg.F) for _ in range(2)]
+            got[analytic] = (norms, s.get_solution(), s.residual_norm())
+    for analytic in (True, False):
+        assert np.array_equal(got[analytic][1], want), analytic
+        assert abs(got[analytic][0][1] - want_norm) <= 1e-10 * want_norm, analytic  # the oracle sums left to right
+        assert abs(got[analytic][2] - want_norm) <= 1e-10 * want_norm, analytic
+    assert abs(got[True][0][1] - got[False][0][1]) <= 1e-13 * want_norm, "folded against unfolded norm"
+    assert got[False][0][1] == got[False][2], "the unfolded norm IS pmg_residual_norm"
+
+
 def _pinned(shape):
     import ctypes
     nbytes = int(np.prod(shape)) * 8

@@ -3,7 +3,8 @@
 kernel is its own launch); `passes` runs the two level-0 fused passes alone (1 warm-up + 2 launches each).
 `wcycle` is `cycle` with W(gamma = 2) recursion; `solve` runs pmg_solve for 4 cycles with graphs off (the cross-cycle path:
 Pass A once, then per cycle the coarse part, k_cross and the convergence kernel).
-Usage: python tools/profile_cycle.py {cycle|wcycle|solve|passes} [N]"""
+`fcycle` runs 1 warm-up + 2 timed F-cycle passes (the runner's wrapper: restrict phi to the coarsest grid, nested iteration up).
+Usage: python tools/profile_cycle.py {cycle|wcycle|fcycle|solve|passes} [N]"""
 import os
 import sys
 
@@ -23,6 +24,14 @@ if mode == "solve":
         s.zero_guess()
         k, hist = s.solve(pmg.V, rel_tol=0.0, max_cycles=4)
     print("N=%d solve of %d cycles: %.4f ms -> %.4f ms per cycle; norms %s" % (n, k, s.last_ms, s.last_ms / k, list(hist)))
+elif mode == "fcycle":
+    s.cycle(pmg.F)
+    t = []
+    for _ in range(2):
+        s.zero_guess()
+        s.cycle(pmg.F)
+        t.append(s.last_ms)
+    print("N=%d F-cycle pass ms: %s" % (n, t))
 elif mode in ("cycle", "wcycle"):
     kind = pmg.W if mode == "wcycle" else pmg.V
     s.cycle(kind)
