@@ -1241,7 +1241,7 @@ pmg_status pmg_create(const pmg_config *cfg, pmg_solver **out)
         // cluster kernel: needs the default coarse end of the hierarchy (coarsest level <= 17, reached by halving) and
         // the fused engine; PMG_CLUSTER=0 switches it off, PMG_CLUSTER=257 makes 257 the top instead of 129 (measured:
         // 129 is the faster split -- the level-257 visit costs 18 000 cycles in the cluster, about what its two
-        // streaming passes take; profiles/r2_coarse_kernels.md)
+        // streaming passes take; profiles/r2_small_kernel_probe.log)
         int want = 129;
         if (const char *e = getenv("PMG_CLUSTER")) want = (e[0] == '0') ? 0 : (atoi(e) == 257 ? 257 : 129);
         if (g_cluster_override >= 0) want = g_cluster_override;
