@@ -301,7 +301,6 @@ struct RegFeed {
 #ifdef PMG_HOST_EMULATION
 #define g_dyn_smem emu_smem
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr) { std::memcpy(emu_smem + saddr, gptr, 16); }
-__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *gptr) { std::memcpy(emu_smem + saddr, gptr, 8); }
 __device__ __forceinline__ void cp_async_commit() {}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {}
@@ -311,12 +310,6 @@ __device__ __forceinline__ void lds_v2(uint32_t a, double &v0, double &v1)
     std::memcpy(&v1, emu_smem + a + 8, 8);
 }
 __device__ __forceinline__ void sts_zero_v2(uint32_t a) { std::memset(emu_smem + a, 0, 16); }
-__device__ __forceinline__ double lds_f64(uint32_t a)
-{
-    double v;
-    std::memcpy(&v, emu_smem + a, 8);
-    return v;
-}
 __device__ __forceinline__ void publish_epoch(int *flag, int epoch) { *(volatile int *)flag = epoch; }
 __device__ __forceinline__ void __threadfence_system() {}
 __device__ __forceinline__ bool wait_flag(const int *flag, int epoch) { return *(const volatile int *)flag >= epoch; }
@@ -324,10 +317,6 @@ __device__ __forceinline__ bool wait_flag(const int *flag, int epoch) { return *
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *gptr)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -342,12 +331,6 @@ __device__ __forceinline__ void lds_v2(uint32_t a, double &v0, double &v1)
 __device__ __forceinline__ void sts_zero_v2(uint32_t a)
 {
     asm volatile("st.shared.v2.f64 [%0], {%1, %1};\n" ::"r"(a), "d"(0.0) : "memory");
-}
-__device__ __forceinline__ double lds_f64(uint32_t a)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
-    return v;
 }
 __device__ __forceinline__ void publish_epoch(int *flag, int epoch)
 {
@@ -879,43 +862,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 
     const int cc = col >> 1;
     const int nc_last_row = ((g.ny - 1) >> 1) + PADY;
-    // Coarse rows: ec = row jc, en = row jc+1 in registers; rows jc+2 .. jc+1+CPF are on their way from HBM into a
-    // per-warp ring of lane-private slots (one cp.async per lane and row, riding in the commit group of the fine rows
-    // issued in the same step, so the wait that feed.begin() does anyway covers them).  With the wide strips only 2 warps
-    // per scheduler are resident and one row pair (~0.9 us of work) does not cover a loaded-DRAM round trip: with the coarse
-    // row loaded into registers one pair ahead, 23 % of all warp samples sat on the instruction that consumes it (ncu
-    // source page) -- and a deeper REGISTER queue does not help, because shifting the queue already waits for the load.
-    constexpr int CPF = 3, NCS = 4;                 // rows in flight; ring slots (power of two > CPF)
-    constexpr int CSLOT = 32 * NP * 8;              // bytes per slot: NP doubles per lane
-    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(g_dyn_smem) + WARPS_PER_CTA * Feed::SMEM_PER_WARP +
-                           (threadIdx.x >> 5) * (NCS * CSLOT) + lane * (NP * 8);
-    auto coarse_issue = [&](int row) {  // coarse row `row` (clamped) -> slot row mod NCS; joins the next commit group
-        const double *src = e + (ptrdiff_t)min(row, nc_last_row) * pitch_c + cc;
-        const uint32_t dst = cbase + (uint32_t)(row & (NCS - 1)) * CSLOT;
-        if (NP == 2)
-            cp_async16(dst, src);
-        else
-            cp_async8(dst, src);
-    };
-    auto coarse_take = [&](int row) {  // the lane's NP values of coarse row `row`, plus the right neighbour's first
-        CoarseRow<C> r;
-        const uint32_t a = cbase + (uint32_t)(row & (NCS - 1)) * CSLOT;
-        if (NP == 2)
-            lds_v2(a, r.v[0], r.v[1]);
-        else
-            r.v[0] = lds_f64(a);
-        r.v[NP] = __shfl_down_sync(0xffffffffu, r.v[0], 1);
-        return r;
-    };
-    CoarseRow<C> ec, en;
+    // Coarse rows: ec = row jc, en = row jc+1, eq[i] = row jc+1+i on its way from HBM (raw, before the shuffle).  With the
+    // wide strips only 2 warps per scheduler are resident and one row pair (~0.9 us of work) does not cover a loaded-DRAM
+    // round trip: with a single row in flight 23 % of all warp samples sat on the shuffle that consumes it (ncu source
+    // page), so the wide shape keeps three rows in flight.
+    constexpr int CPF = (C == 4) ? 3 : 1;
+    CoarseRow<C> ec, en, eq[CPF];
+#pragma unroll
+    for (int q = 0; q <= NP; ++q) ec.v[q] = en.v[q] = 0.0;
     {
         const int jc0 = j_start >> 1;
+        ec = load_coarse<C>(e + (ptrdiff_t)jc0 * pitch_c + cc);
+        ec.v[NP] = __shfl_down_sync(0xffffffffu, ec.v[0], 1);
 #pragma unroll
-        for (int i = 0; i <= CPF; ++i) coarse_issue(jc0 + i);
-        cp_async_commit();
-        cp_async_wait<0>();  // once per warp: the first rows (and the fine rows feed.init asked for) have landed
-        ec = coarse_take(jc0);
-        en = ec;
+        for (int i = 0; i < CPF; ++i) {
+            eq[i].v[NP] = 0.0;
+            eq[i] = load_coarse<C>(e + (ptrdiff_t)min(jc0 + 1 + i, nc_last_row) * pitch_c + cc);
+        }
     }
     const int ycoarse = g.yoff >> 1;
 
@@ -923,13 +886,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, MINB)
 #pragma unroll
         for (int u = 0; u < Feed::UNROLL; ++u) {
             const int jj = j + u;  // u even: fine row 2jc, u odd: 2jc+1
-            if ((u & 1) == 0) coarse_issue((jj >> 1) + 1 + CPF);  // committed by feed.begin() together with the fine rows
             Row<C> cur = feed.begin(u, jj);
             {   // prolongation-and-add (MultiGrid.hpp:86)
                 const bool rowp = (jj + g.yoff >= lo) && (jj + g.yoff <= g.n - 2);
                 double corr[C];  // the coarse values each point interpolates, summed but not yet weighted
                 if ((u & 1) == 0) {
-                    en = coarse_take((jj >> 1) + 1);
+                    en = eq[0];
+                    en.v[NP] = __shfl_down_sync(0xffffffffu, eq[0].v[0], 1);
+#pragma unroll
+                    for (int i = 0; i + 1 < CPF; ++i) eq[i] = eq[i + 1];
+                    int nr = min((jj >> 1) + 1 + CPF, nc_last_row);
+                    eq[CPF - 1] = load_coarse<C>(e + (ptrdiff_t)nr * pitch_c + cc);
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         corr[2 * q] = ec.v[q];
@@ -1263,7 +1230,7 @@ void cross_launch_w(const FusedLevel &lv_in, double *xb_out, const double *e, in
     double inv = 1.0 / (lv_in.h * lv_in.h);
     int nc = (lv_in.n - 1) / 2 + 1;
     auto k = k_cross<C, PF, MINB, 2, 2, WEIGHTED>;
-    int sm = WARPS_PER_CTA * (SmemFeed<C, PF, 4, true>::SMEM_PER_WARP + 4 * 32 * (C / 2) * 8);  // + the coarse-row ring
+    int sm = WARPS_PER_CTA * SmemFeed<C, PF, 4, true>::SMEM_PER_WARP;
     PMG_SMEM_ONCE(k, sm);
     PMG_LAUNCH(k, dim3(grid_for(g)), dim3(32 * WARPS_PER_CTA), sm, st, lv_in.xb, xb_out, lv_in.x, lv_in.f, e, cf, g, pitch_c, lo, nc, c,
                inv, d_partials, done, lv_in.hp);
