@@ -639,6 +639,10 @@ int main(int argc, char **argv)
     cross_level(257, w, ORC_PROLONG_REFERENCE, 148, 2);
     cross_level(129, w, ORC_PROLONG_FULL, 2, 7);
     cross_level(513, w, ORC_PROLONG_REFERENCE, 4, 8);
+    if (full) {
+        cross_level(1025, w, ORC_PROLONG_REFERENCE, 148, 2);   // ten strips of 112 columns, the B200's wave
+        prolong_down_level(513, w, ORC_PROLONG_FULL, 148);
+    }
     slab_cross(129, 2, ORC_PROLONG_REFERENCE, 148);
     slab_cross(257, 3, ORC_PROLONG_FULL, 2);
     slab_cross(257, 4, ORC_PROLONG_REFERENCE, 148);
